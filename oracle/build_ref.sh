@@ -1,0 +1,37 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY -- builds the *real* reference BuildGraph (OpenMP) as a parity checker / CPU baseline.
+#
+# Compiles /root/reference/src/BuildGraph/src/*.cpp (sources stay where they lie; nothing is copied into the repo)
+# in a throw-away scratch directory with the two patches SURVEY.md section 8(c) documents:
+#   1. compile fix: Common.h:68  SSTR() dynamic_cast on an rvalue stream is rejected by libstdc++ >= 11
+#   2. canonical numbering: sort reads by fileIndex before IDs are assigned (before Dataset.cpp:133),
+#      which is what the MPI siblings do (their loader has no OpenMP) and makes the output thread-count independent.
+# Output: oracle/_ref/buildG (git-ignored, travels to the GPU box with the snapshot).
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${DISCO_REFERENCE:-/root/reference}/src/BuildGraph/src"
+OUT="$HERE/_ref"
+if [ ! -d "$REF" ]; then
+  echo "build_ref: $REF not present (GPU box?) - keeping prebuilt $OUT/buildG" >&2
+  [ -x "$OUT/buildG" ] && exit 0 || exit 3
+fi
+mkdir -p "$OUT"
+TMP="$(mktemp -d /tmp/disco_ref_build.XXXXXX)"
+trap 'rm -rf "$TMP"' EXIT
+cp "$REF"/*.cpp "$REF"/*.h "$TMP"/
+chmod -R u+w "$TMP"
+sed -i 's|^#define SSTR( x ).*|#define SSTR( x ) (static_cast< std::ostringstream \&\& >( std::ostringstream() << std::dec << x ).str())|' "$TMP/Common.h"
+# insert the sort right before the "Assing ID's to the reads" loop
+python3 - "$TMP/Dataset.cpp" <<'PY'
+import sys
+p = sys.argv[1]
+src = open(p).read()
+needle = "\tfor(UINT64 i = 0 ; i < reads->size(); i++) \t\t// Assing ID's to the reads."
+assert src.count(needle) == 1, "Dataset.cpp numbering loop not found"
+patch = "\tstd::sort(reads->begin(), reads->end(), [](Read*a, Read*b){return a->getFileIndex()<b->getFileIndex();});\n"
+open(p, "w").write(src.replace(needle, patch + needle))
+PY
+GZ=""
+if echo '#include <zlib.h>' | g++ -x c++ -fsyntax-only - 2>/dev/null; then GZ="-DINCLUDE_READGZ"; GZL="-lz"; else GZL=""; fi
+g++ $GZ -Wno-sign-compare -fopenmp -std=c++11 -O3 -w -o "$OUT/buildG" "$TMP"/*.cpp $GZL
+echo "build_ref: built $OUT/buildG"
