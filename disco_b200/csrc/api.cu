@@ -1,0 +1,571 @@
+// api.cu -- the C ABI of include/disco_gpu.h: context, device buffers, phase orchestration, result read-back.
+// No CPU implementation of the path exists in this library: every entry point needs a CUDA device or fails.
+#include "../../include/disco_gpu.h"
+#include "dna.cuh"
+#include "kernels.cuh"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace disco;
+
+namespace {
+thread_local std::string g_create_error;
+
+enum Cursor { CUR_WORK = 0, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_COUNT };
+enum Ev { EV_T0 = 0, EV_TABLE_ALL, EV_CONTAINED, EV_FINISH, EV_TABLE_NC, EV_EDGES, EV_MARK, EV_EMIT, EV_COUNT };
+} // namespace
+
+struct disco_ctx {
+    int device = 0;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+
+    // reads
+    uint64_t *d_words = nullptr;
+    uint16_t *d_len = nullptr;
+    ReadsView reads{};
+    // run parameters
+    int K = 0, cap = 0;
+    bool begun = false, have_contained = false, have_edges = false, have_reduced = false;
+    // table
+    uint64_t *d_slots = nullptr;
+    uint64_t nbuckets = 0;
+    // containment
+    unsigned long long *d_best = nullptr;
+    uint32_t *d_bits = nullptr;
+    disco_crow *d_crows = nullptr;
+    uint64_t n_contained = 0;
+    // adjacency
+    uint64_t *d_rowinfo = nullptr;
+    uint64_t *d_rows = nullptr;
+    uint64_t rows_cap = 0, rows_used = 0; // rows_used = cursor (includes warp-slice slack)
+    // output
+    disco_edge *d_edges = nullptr;
+    uint64_t edges_cap = 0, n_edges = 0;
+    // counters / stats
+    unsigned long long *d_cursors = nullptr;  // CUR_COUNT
+    unsigned long long *d_stats_c = nullptr;  // containment pass
+    unsigned long long *d_stats_e = nullptr;  // edge pass + reduction
+    cudaEvent_t ev[EV_COUNT] = {};
+    bool ev_done[EV_COUNT] = {};
+    disco_stats stats{};
+};
+
+namespace {
+
+int fail(disco_ctx *c, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? DISCO_E_NOMEM : DISCO_E_CUDA, "%s failed: %s (%s:%d)", #call, \
+                        cudaGetErrorString(e__), __FILE__, __LINE__);                                         \
+    } while (0)
+
+template <typename T>
+void dfree(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int pick_stride(int max_len)
+{
+    const int W = (max_len + 31) / 32;
+    const int regs[] = {2, 4, 6, 8, 10, 12, 16};
+    for (int s : regs) if (W <= s) return s;
+    return (W + 1) & ~1; // long reads: generic (global-walking) matcher, still 16-byte aligned rows
+}
+
+void free_run_buffers(disco_ctx *c)
+{
+    dfree(c->d_slots); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
+    dfree(c->d_rowinfo); dfree(c->d_rows); dfree(c->d_edges);
+    c->rows_cap = c->edges_cap = 0;
+    c->begun = c->have_contained = c->have_edges = c->have_reduced = false;
+}
+
+void free_reads(disco_ctx *c)
+{
+    dfree(c->d_words); dfree(c->d_len);
+    c->reads = ReadsView{};
+}
+
+int record(disco_ctx *ctx, int which)
+{
+    CK(cudaEventRecord(ctx->ev[which], ctx->stream));
+    ctx->ev_done[which] = true;
+    return DISCO_OK;
+}
+
+int alloc_reads(disco_ctx *ctx, uint64_t n, int min_len, int max_len)
+{
+    free_run_buffers(ctx);
+    free_reads(ctx);
+    if (n == 0) return fail(ctx, DISCO_E_ARG, "no reads");
+    if (n > 0x7FFFFFF0ULL) return fail(ctx, DISCO_E_LIMIT, "at most 2^31-16 reads per context (record ids are 32 bit)");
+    if (max_len > 32767) return fail(ctx, DISCO_E_LIMIT, "read length %d exceeds the 15-bit limit of the reference record header (HashTable.cpp:437)", max_len);
+    if (min_len < 1) return fail(ctx, DISCO_E_ARG, "empty read");
+    const int stride = pick_stride(max_len);
+    CK(cudaMalloc(&ctx->d_words, n * (uint64_t)stride * sizeof(uint64_t)));
+    CK(cudaMalloc(&ctx->d_len, n * sizeof(uint16_t)));
+    ctx->reads.words = ctx->d_words; ctx->reads.len = ctx->d_len; ctx->reads.n = n; ctx->reads.stride = stride;
+    ctx->reads.min_len = min_len; ctx->reads.max_len = max_len;
+    ctx->reads.uniform_len = (min_len == max_len) ? max_len : 0;
+    return DISCO_OK;
+}
+
+int copy_reads(disco_ctx *ctx, const uint64_t *packed, const uint16_t *len, uint32_t wpr, cudaMemcpyKind kind)
+{
+    const uint64_t n = ctx->reads.n;
+    const int stride = ctx->reads.stride;
+    const int W = (ctx->reads.max_len + 31) / 32;
+    if ((int)wpr < W) return fail(ctx, DISCO_E_ARG, "words_per_read %u too small for max length %d", wpr, ctx->reads.max_len);
+    const size_t width = (size_t)std::min<int>((int)wpr, stride) * sizeof(uint64_t);
+    if (width < (size_t)stride * sizeof(uint64_t))
+        CK(cudaMemsetAsync(ctx->d_words, 0, n * (uint64_t)stride * sizeof(uint64_t), ctx->stream));
+    CK(cudaMemcpy2DAsync(ctx->d_words, (size_t)stride * sizeof(uint64_t), packed, (size_t)wpr * sizeof(uint64_t), width, n, kind, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_len, len, n * sizeof(uint16_t), kind, ctx->stream));
+    return DISCO_OK;
+}
+
+} // namespace
+
+// ===================================================================================================================
+extern "C" {
+
+int disco_gpu_create(disco_ctx **out, int device)
+{
+    disco_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, DISCO_E_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, DISCO_E_CUDA, "no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, DISCO_E_ARG, "device %d out of range (%d devices)", device, count);
+    ctx = new (std::nothrow) disco_ctx();
+    if (!ctx) return fail(nullptr, DISCO_E_NOMEM, "out of host memory");
+    ctx->device = device;
+    auto bail = [&](cudaError_t ce, const char *what) {
+        fail(nullptr, DISCO_E_CUDA, "%s failed: %s", what, cudaGetErrorString(ce));
+        delete ctx;
+        return DISCO_E_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(e, "cudaSetDevice");
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
+    if (prop.major < 10) { fail(nullptr, DISCO_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); delete ctx; return DISCO_E_CUDA; }
+    ctx->num_sms = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
+    ctx->own_stream = true;
+    for (auto &ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
+    if ((e = cudaMalloc(&ctx->d_cursors, CUR_COUNT * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_stats_c, ST_COUNT * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    if ((e = cudaMalloc(&ctx->d_stats_e, ST_COUNT * sizeof(unsigned long long))) != cudaSuccess) return bail(e, "cudaMalloc");
+    *out = ctx;
+    return DISCO_OK;
+}
+
+void disco_gpu_destroy(disco_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_run_buffers(ctx);
+    free_reads(ctx);
+    dfree(ctx->d_cursors); dfree(ctx->d_stats_c); dfree(ctx->d_stats_e);
+    for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char *disco_gpu_last_error(const disco_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int disco_gpu_set_stream(disco_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return DISCO_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) { cudaStreamDestroy(ctx->stream); ctx->own_stream = false; }
+    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    return DISCO_OK;
+}
+
+int disco_gpu_load_reads(disco_ctx *ctx, const uint64_t *packed, const uint16_t *len, uint64_t n_reads, uint32_t words_per_read)
+{
+    if (!ctx) return DISCO_E_ARG;
+    if (!packed || !len) return fail(ctx, DISCO_E_ARG, "NULL input");
+    CK(cudaSetDevice(ctx->device));
+    int mn = 1 << 30, mx = 0;
+    for (uint64_t i = 0; i < n_reads; i++) { int l = len[i]; mn = std::min(mn, l); mx = std::max(mx, l); }
+    int rc = alloc_reads(ctx, n_reads, mn, mx);
+    if (rc) return rc;
+    return copy_reads(ctx, packed, len, words_per_read, cudaMemcpyHostToDevice);
+}
+
+int disco_gpu_load_reads_device(disco_ctx *ctx, const uint64_t *d_packed, const uint16_t *d_len, uint64_t n_reads,
+                                uint32_t words_per_read, uint32_t min_len, uint32_t max_len)
+{
+    if (!ctx) return DISCO_E_ARG;
+    if (!d_packed || !d_len) return fail(ctx, DISCO_E_ARG, "NULL input");
+    if (min_len > max_len) return fail(ctx, DISCO_E_ARG, "min_len > max_len");
+    CK(cudaSetDevice(ctx->device));
+    int rc = alloc_reads(ctx, n_reads, (int)min_len, (int)max_len);
+    if (rc) return rc;
+    return copy_reads(ctx, d_packed, d_len, words_per_read, cudaMemcpyDeviceToDevice);
+}
+
+// ---- phases -------------------------------------------------------------------------------------------------------
+int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_kmer)
+{
+    if (!ctx) return DISCO_E_ARG;
+    if (!ctx->d_words) return fail(ctx, DISCO_E_ARG, "load reads first");
+    if (min_overlap < 2) return fail(ctx, DISCO_E_ARG, "min_overlap must be >= 2");
+    if (max_edge_per_kmer < 1 || max_edge_per_kmer > 8) return fail(ctx, DISCO_E_ARG, "max_edge_per_kmer must be in 1..8");
+    if ((uint32_t)ctx->reads.min_len <= min_overlap)
+        return fail(ctx, DISCO_E_ARG, "every read must be longer than min_overlap (Dataset.cpp:305): shortest is %d", ctx->reads.min_len);
+    CK(cudaSetDevice(ctx->device));
+    free_run_buffers(ctx);
+    ctx->K = (int)min_overlap - 1; // hashStringLength (HashTable.cpp:50)
+    ctx->cap = (int)max_edge_per_kmer;
+    if (!search_edges_fits(ctx->reads.max_len, ctx->K, ctx->cap))
+        return fail(ctx, DISCO_E_LIMIT, "max read length %d with min_overlap %u needs more shared memory per warp than one SM has", ctx->reads.max_len, min_overlap);
+    const uint64_t n = ctx->reads.n;
+    // 2n records, four 8-byte slots per 32-byte bucket, load factor 1/3 (the reference sizes its table at 8n+1
+    // index words, HashTable.cpp:53)
+    ctx->nbuckets = std::max<uint64_t>(1024, n + n / 2);
+    CK(cudaMalloc(&ctx->d_slots, ctx->nbuckets * 4 * sizeof(uint64_t)));
+    CK(cudaMalloc(&ctx->d_best, n * sizeof(unsigned long long)));
+    CK(cudaMalloc(&ctx->d_bits, ((n + 31) / 32) * sizeof(uint32_t)));
+    CK(cudaMalloc(&ctx->d_rowinfo, n * sizeof(uint64_t)));
+    CK(cudaMemsetAsync(ctx->d_best, 0xFF, n * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_rowinfo, 0, n * sizeof(uint64_t), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_cursors, 0, CUR_COUNT * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_stats_c, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_stats_e, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
+    ctx->stats = disco_stats{};
+    ctx->stats.n_reads = n;
+    ctx->stats.table_buckets = ctx->nbuckets;
+    for (auto &d : ctx->ev_done) d = false;
+    ctx->n_contained = ctx->n_edges = 0;
+    ctx->begun = true;
+    return record(ctx, EV_T0);
+}
+
+int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained)
+{
+    if (!ctx || !ctx->begun) return fail(ctx, DISCO_E_ARG, "call disco_gpu_begin first");
+    if (exclude_contained && !ctx->have_contained) return fail(ctx, DISCO_E_ARG, "containment pass not finished");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_slots, 0xFF, ctx->nbuckets * 4 * sizeof(uint64_t), ctx->stream));
+    TableView tv{ctx->d_slots, ctx->nbuckets};
+    CK(launch_table_insert(ctx->reads, tv, ctx->K, exclude_contained ? ctx->d_bits : nullptr, ctx->num_sms, ctx->stream));
+    return record(ctx, exclude_contained ? EV_TABLE_NC : EV_TABLE_ALL);
+}
+
+int disco_gpu_phase_contained(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
+{
+    if (!ctx || !ctx->begun) return fail(ctx, DISCO_E_ARG, "call disco_gpu_begin first");
+    if (q_lo > q_hi || q_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad query range");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    SearchParams p{};
+    p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets};
+    p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
+    p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_c; p.best = ctx->d_best;
+    if (q_hi > q_lo) CK(launch_search_contained(p, ctx->num_sms, ctx->stream));
+    return record(ctx, EV_CONTAINED);
+}
+
+int disco_gpu_phase_finish_contained(disco_ctx *ctx)
+{
+    if (!ctx || !ctx->begun) return fail(ctx, DISCO_E_ARG, "call disco_gpu_begin first");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_cursors + CUR_NCONTAINED, 0, 2 * sizeof(unsigned long long), ctx->stream)); // + CUR_CROWS
+    CK(launch_contained_finish(ctx->d_best, ctx->reads.n, ctx->d_bits, ctx->d_cursors + CUR_NCONTAINED, ctx->stream));
+    unsigned long long nc = 0;
+    CK(cudaMemcpyAsync(&nc, ctx->d_cursors + CUR_NCONTAINED, sizeof nc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->n_contained = nc;
+    dfree(ctx->d_crows);
+    if (nc) {
+        CK(cudaMalloc(&ctx->d_crows, nc * sizeof(disco_crow)));
+        CK(launch_contained_rows(ctx->d_best, ctx->reads, ctx->K, ctx->d_crows, ctx->d_cursors + CUR_CROWS, ctx->stream));
+    }
+    ctx->have_contained = true;
+    ctx->stats.n_contained = nc;
+    return record(ctx, EV_FINISH);
+}
+
+int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
+{
+    if (!ctx || !ctx->begun || !ctx->have_contained) return fail(ctx, DISCO_E_ARG, "containment pass not finished");
+    if (q_lo > q_hi || q_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad query range");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t nq = q_hi - q_lo;
+    const int rowcap = ctx->cap * (ctx->reads.max_len - ctx->K);
+    SearchParams p{};
+    p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets};
+    p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
+    p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
+    p.contained_bits = ctx->d_bits; p.rows_cursor = ctx->d_cursors + CUR_ROWS; p.rowinfo = ctx->d_rowinfo;
+    p.rowcap = rowcap; p.hcap = std::min(rowcap, 192);
+    // adjacency capacity: start from 48 entries per query read (30x, 150 bp, minOverlap 50 needs ~33), bounded by free
+    // memory; the kernel keeps counting on overflow so that one retry with the exact size always succeeds
+    if (!ctx->d_rows) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        uint64_t want = std::max<uint64_t>(nq * 48, 1 << 20);
+        const uint64_t lim = (uint64_t)(free_b * 0.6) / sizeof(uint64_t);
+        if (want > lim) want = std::max<uint64_t>(lim, 1 << 16);
+        CK(cudaMalloc(&ctx->d_rows, want * sizeof(uint64_t)));
+        ctx->rows_cap = want;
+    }
+    for (int attempt = 0;; attempt++) {
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, 2 * sizeof(unsigned long long), ctx->stream)); // + CUR_ROWS
+        CK(cudaMemsetAsync(ctx->d_stats_e, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
+        if (attempt) CK(cudaMemsetAsync(ctx->d_rowinfo + q_lo, 0, nq * sizeof(uint64_t), ctx->stream));
+        p.rows = ctx->d_rows; p.rows_cap = ctx->rows_cap;
+        if (nq) CK(launch_search_edges(p, ctx->num_sms, ctx->stream));
+        unsigned long long cur[2] = {0, 0}, st[ST_COUNT];
+        CK(cudaMemcpyAsync(cur, ctx->d_cursors + CUR_WORK, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(st, ctx->d_stats_e, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->rows_used = cur[1];
+        ctx->stats.raw_directed_edges = st[ST_ENTRIES];
+        ctx->stats.max_degree = st[ST_MAXDEG];
+        if (!st[ST_OVERFLOW]) break;
+        if (attempt >= 2) return fail(ctx, DISCO_E_NOMEM, "adjacency buffer overflow after retry (%llu entries needed)", cur[1]);
+        // slices are handed out per warp, so the slack differs between runs: add one slice per resident warp
+        const uint64_t need = cur[1] + (uint64_t)ctx->num_sms * 64 * 1024;
+        dfree(ctx->d_rows);
+        ctx->rows_cap = 0;
+        CK(cudaMalloc(&ctx->d_rows, need * sizeof(uint64_t)));
+        ctx->rows_cap = need;
+    }
+    ctx->stats.edge_capacity = ctx->rows_cap;
+    ctx->have_edges = true;
+    return record(ctx, EV_EDGES);
+}
+
+int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
+{
+    if (!ctx || !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass not finished");
+    if (u_lo > u_hi || u_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad node range");
+    CK(cudaSetDevice(ctx->device));
+    ReduceParams p{};
+    p.reads = ctx->reads; p.rows = ctx->d_rows; p.rowinfo = ctx->d_rowinfo; p.u_lo = u_lo; p.u_hi = u_hi;
+    p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
+    p.maxdeg = (int)std::max<uint64_t>(ctx->stats.max_degree, 1);
+    if ((size_t)p.maxdeg * 5 * 8 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
+    CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_mark(p, ctx->num_sms, ctx->stream));
+    int rc = record(ctx, EV_MARK);
+    if (rc) return rc;
+    if (!ctx->d_edges) {
+        const uint64_t want = std::max<uint64_t>(ctx->stats.raw_directed_edges / 4, 1 << 16);
+        CK(cudaMalloc(&ctx->d_edges, want * sizeof(disco_edge)));
+        ctx->edges_cap = want;
+    }
+    for (int attempt = 0;; attempt++) {
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_EDGES, 0, sizeof(unsigned long long), ctx->stream));
+        p.edges_out = ctx->d_edges; p.edges_cap = ctx->edges_cap; p.edges_cursor = ctx->d_cursors + CUR_EDGES;
+        if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_emit(p, ctx->num_sms, ctx->stream));
+        unsigned long long ne = 0;
+        CK(cudaMemcpyAsync(&ne, ctx->d_cursors + CUR_EDGES, sizeof ne, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->n_edges = ne;
+        if (ne <= ctx->edges_cap) break;
+        if (attempt >= 1) return fail(ctx, DISCO_E_NOMEM, "edge buffer overflow after retry");
+        dfree(ctx->d_edges);
+        CK(cudaMalloc(&ctx->d_edges, ne * sizeof(disco_edge)));
+        ctx->edges_cap = ne;
+    }
+    ctx->stats.n_edges = ctx->n_edges;
+    ctx->have_reduced = true;
+    return record(ctx, EV_EMIT);
+}
+
+int disco_gpu_build_graph(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_kmer)
+{
+    int rc;
+    if ((rc = disco_gpu_begin(ctx, min_overlap, max_edge_per_kmer))) return rc;
+    const uint64_t n = ctx->reads.n;
+    if ((rc = disco_gpu_phase_table(ctx, 0))) return rc;
+    if ((rc = disco_gpu_phase_contained(ctx, 0, n))) return rc;
+    if ((rc = disco_gpu_phase_finish_contained(ctx))) return rc;
+    if ((rc = disco_gpu_phase_table(ctx, 1))) return rc;
+    if ((rc = disco_gpu_phase_edges(ctx, 0, n))) return rc;
+    if ((rc = disco_gpu_phase_reduce(ctx, 0, n))) return rc;
+    return DISCO_OK;
+}
+
+// ---- results ------------------------------------------------------------------------------------------------------
+int disco_gpu_counts(disco_ctx *ctx, uint64_t *n_contained, uint64_t *n_edges)
+{
+    if (!ctx) return DISCO_E_ARG;
+    if (n_contained) *n_contained = ctx->n_contained;
+    if (n_edges) *n_edges = ctx->n_edges;
+    return DISCO_OK;
+}
+
+int disco_gpu_get_contained(disco_ctx *ctx, disco_crow *rows, uint64_t capacity, uint64_t *n_written)
+{
+    if (!ctx || !ctx->have_contained) return fail(ctx, DISCO_E_ARG, "containment pass not finished");
+    if (capacity < ctx->n_contained) return fail(ctx, DISCO_E_ARG, "capacity %llu < %llu rows", (unsigned long long)capacity, (unsigned long long)ctx->n_contained);
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->n_contained;
+    if (n) {
+        CK(cudaMemcpyAsync(rows, ctx->d_crows, n * sizeof(disco_crow), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<uint16_t> len;
+        if (!ctx->reads.uniform_len) {
+            len.resize(ctx->reads.n);
+            CK(cudaMemcpyAsync(len.data(), ctx->d_len, ctx->reads.n * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CK(cudaStreamSynchronize(ctx->stream));
+        // reference emission order at -t 1: container ascending, then k-mer position, then record (prefix before suffix)
+        const int K = ctx->K, UL = ctx->reads.uniform_len;
+        auto key = [&](const disco_crow &r) {
+            const int L1 = UL ? UL : len[r.container];
+            // orient 3/2 <- types 0/2: start = j ; orient 0/1 <- types 1/3: start = L1 - K - j   (OverlapGraph.cpp:428-434)
+            const int j = (r.orient == 3 || r.orient == 2) ? (int)r.start : L1 - K - (int)r.start;
+            const int kind = (r.orient == 3 || r.orient == 1) ? 0 : 1;
+            return std::make_tuple(r.container, j, 2ULL * r.contained + kind);
+        };
+        std::sort(rows, rows + n, [&](const disco_crow &a, const disco_crow &b) { return key(a) < key(b); });
+    }
+    if (n_written) *n_written = n;
+    return DISCO_OK;
+}
+
+int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, uint64_t *n_written)
+{
+    if (!ctx || !ctx->have_reduced) return fail(ctx, DISCO_E_ARG, "reduction not finished");
+    if (capacity < ctx->n_edges) return fail(ctx, DISCO_E_ARG, "capacity too small");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_edges) {
+        CK(cudaMemcpyAsync(edges, ctx->d_edges, ctx->n_edges * sizeof(disco_edge), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (n_written) *n_written = ctx->n_edges;
+    return DISCO_OK;
+}
+
+int disco_gpu_get_row(disco_ctx *ctx, uint64_t read, disco_edge *out, uint64_t capacity, uint64_t *n_written)
+{
+    if (!ctx || !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass not finished");
+    if (read >= ctx->reads.n) return fail(ctx, DISCO_E_ARG, "read out of range");
+    CK(cudaSetDevice(ctx->device));
+    uint64_t ri = 0;
+    CK(cudaMemcpyAsync(&ri, ctx->d_rowinfo + read, sizeof ri, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t deg = rowinfo_deg(ri);
+    if (deg > capacity) return fail(ctx, DISCO_E_ARG, "capacity too small");
+    std::vector<uint64_t> e(deg);
+    if (deg) {
+        CK(cudaMemcpyAsync(e.data(), ctx->d_rows + rowinfo_start(ri), deg * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    for (uint32_t i = 0; i < deg; i++) {
+        out[i].src = (uint32_t)read; out[i].dst = (uint32_t)entry_nbr(e[i]);
+        out[i].offset = (uint32_t)entry_offset(e[i]); out[i].orient = (uint32_t)entry_orient(e[i]);
+    }
+    if (n_written) *n_written = deg;
+    return DISCO_OK;
+}
+
+int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out)
+{
+    if (!ctx || !out) return DISCO_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    unsigned long long sc[ST_COUNT] = {}, se[ST_COUNT] = {};
+    CK(cudaMemcpy(sc, ctx->d_stats_c, sizeof sc, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(se, ctx->d_stats_e, sizeof se, cudaMemcpyDeviceToHost));
+    disco_stats &s = ctx->stats;
+    s.probes_contained = sc[ST_PROBES]; s.buckets_contained = sc[ST_BUCKETS]; s.verified_contained = sc[ST_VERIFIED];
+    s.probes_edges = se[ST_PROBES]; s.buckets_edges = se[ST_BUCKETS]; s.verified_edges = se[ST_VERIFIED];
+    s.cap_fired = se[ST_CAP_FIRED]; s.slow_path_reads = se[ST_SLOW_READS];
+    s.multi_overlap_pairs = se[ST_MULTI_OVERLAP]; s.one_sided_edges = se[ST_ONE_SIDED];
+    s.reduce_rows_fetched = se[ST_ROWS_FETCHED]; s.reduce_entries_fetched = se[ST_ENTRIES_FETCHED];
+    auto ms = [&](int a, int b) {
+        float t = 0.f;
+        if (ctx->ev_done[a] && ctx->ev_done[b]) cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);
+        return t;
+    };
+    s.ms_table_all = ms(EV_T0, EV_TABLE_ALL); s.ms_contained = ms(EV_TABLE_ALL, EV_CONTAINED);
+    s.ms_finish_contained = ms(EV_CONTAINED, EV_FINISH); s.ms_table_nc = ms(EV_FINISH, EV_TABLE_NC);
+    s.ms_edges = ms(EV_TABLE_NC, EV_EDGES); s.ms_mark = ms(EV_EDGES, EV_MARK); s.ms_emit = ms(EV_MARK, EV_EMIT);
+    s.ms_total = ms(EV_T0, EV_EMIT);
+    *out = s;
+    return DISCO_OK;
+}
+
+// ---- multi-GPU plumbing ---------------------------------------------------------------------------------------------
+void *disco_gpu_dev_contained_keys(disco_ctx *ctx) { return ctx ? ctx->d_best : nullptr; }
+void *disco_gpu_dev_rowinfo(disco_ctx *ctx) { return ctx ? ctx->d_rowinfo : nullptr; }
+void *disco_gpu_dev_rows(disco_ctx *ctx, uint64_t *n_entries)
+{
+    if (!ctx) return nullptr;
+    if (n_entries) *n_entries = ctx->rows_used;
+    return ctx->d_rows;
+}
+
+int disco_gpu_rebase_rows(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi, uint64_t base)
+{
+    if (!ctx || !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass not finished");
+    if (u_lo > u_hi || u_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad node range");
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_rebase_rowinfo(ctx->d_rowinfo, u_lo, u_hi, base, ctx->stream));
+    return DISCO_OK;
+}
+
+int disco_gpu_adopt_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entries)
+{
+    if (!ctx || !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass not finished");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx->d_rows);
+    ctx->rows_cap = 0;
+    CK(cudaMalloc(&ctx->d_rows, std::max<uint64_t>(n_entries, 1) * sizeof(uint64_t)));
+    ctx->rows_cap = ctx->rows_used = n_entries;
+    if (n_entries) CK(cudaMemcpyAsync(ctx->d_rows, d_rows, n_entries * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    return DISCO_OK;
+}
+
+int disco_gpu_set_max_degree(disco_ctx *ctx, uint64_t max_degree)
+{
+    if (!ctx) return DISCO_E_ARG;
+    ctx->stats.max_degree = max_degree;
+    return DISCO_OK;
+}
+
+int disco_gpu_sync(disco_ctx *ctx)
+{
+    if (!ctx) return DISCO_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DISCO_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,749 @@
+// kernels.cu -- hand-written sm_100a kernels of the BuildGraph hot path.  Integer / bit work only (hashing, 2-bit
+// compares, neighbour-list marking): bound by random 32-byte HBM sectors, not by math, so no tensor cores.
+//
+//   k_table_insert     HashTable::insertIntoTable  (HashTable.cpp:423-514)   2 records per read, quad-cooperative CAS
+//   k_search<CONTAIN>  markContainedReads          (OverlapGraph.cpp:333-505) + checkOverlapForContainedRead (:517)
+//   k_search<EDGES>    insertAllEdgesOfRead        (OverlapGraph.cpp:631-678) + checkOverlap (:567)
+//   k_reduce_mark      markTransitiveEdges         (OverlapGraph.cpp:687-723)
+//   k_reduce_emit      removeTransitiveEdges + canonical src<dst selection (OverlapGraph.cpp:731-761, :808)
+//
+// Common shape: one warp per read, the read (forward + reverse complement) staged in shared memory, one lane per
+// k-mer position so that a warp keeps 32 independent table sectors in flight; reads are handed out in chunks through
+// an atomic work counter (persistent grid sized from the SM count).
+#include "dna.cuh"
+#include "kernels.cuh"
+#include "../../include/disco_gpu.h"
+
+namespace disco {
+
+#define FULL 0xffffffffu
+constexpr int kThreads = 256;  // 8 warps per block
+constexpr int kWarps = kThreads / 32;
+constexpr int kChunk = 8;      // reads per work-counter grab
+constexpr int kScanLimit = 6;  // buckets a lane may walk on the fast path before the read is deferred to the slow path
+constexpr int kRowBlock = 1024; // adjacency entries a warp reserves per global atomic
+constexpr int kBestMax = 16;   // slow path: smallest-record candidates kept per position (>= 2 * cap)
+
+// ---------------------------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_bucket(const uint64_t *slots, uint64_t b, uint64_t (&v)[4])
+{
+    // one 32-byte sector, one instruction (LDG.E.256, sm_100+)
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];"
+                 : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3])
+                 : "l"(slots + 4 * b));
+}
+
+// candidate read held in registers (NW = words per read = the device stride, even)
+template <int NW>
+struct RegMatcher {
+    uint64_t v[NW];
+    __device__ __forceinline__ void load(const uint64_t *words, uint64_t r)
+    {
+        const ulonglong2 *p = reinterpret_cast<const ulonglong2 *>(words + r * NW);
+#pragma unroll
+        for (int i = 0; i < NW / 2; i++) {
+            ulonglong2 q = __ldg(p + i); // 128-bit loads, rows are 16-byte aligned
+            v[2 * i] = q.x; v[2 * i + 1] = q.y;
+        }
+    }
+    __device__ __forceinline__ bool operator()(const uint64_t *P, int a, int b, int n) const
+    {
+        uint64_t diff = 0;
+#pragma unroll
+        for (int w = 0; w < NW; w++) {
+            int lo = b - 32 * w; if (lo < 0) lo = 0;
+            int hi = b + n - 32 * w; if (hi > 32) hi = 32;
+            if (lo < hi) diff |= (fetch64(P, a + 32 * w - b) ^ v[w]) & base_mask(lo, hi);
+        }
+        return diff == 0;
+    }
+};
+// long reads: walk the candidate's words in global memory
+struct GlobalLoader {
+    const uint64_t *p;
+    __device__ __forceinline__ uint64_t operator()(int w) const { return __ldg(p + w); }
+};
+template <>
+struct RegMatcher<0> {
+    LoaderMatcher<GlobalLoader> m;
+    int stride;
+    __device__ __forceinline__ void load(const uint64_t *words, uint64_t r) { m.s2.p = words + r * (uint64_t)stride; }
+    __device__ __forceinline__ bool operator()(const uint64_t *P, int a, int b, int n) const { return m(P, a, b, n); }
+};
+
+// stage read r into the warp's padded arrays A (forward) and R (reverse complement); WP = words(max_len) + 2
+__device__ __forceinline__ void stage_read(const ReadsView &rv, uint64_t r, int L, uint64_t *A, uint64_t *R, int WP, int lane)
+{
+    const int W = (L + 31) >> 5;
+    const uint64_t *src = rv.words + r * (uint64_t)rv.stride;
+    for (int w = lane; w < WP; w += 32) A[w] = (w >= 1 && w <= W) ? __ldg(src + (w - 1)) : 0ULL;
+    __syncwarp();
+    for (int w = lane; w < WP; w += 32) R[w] = (w >= 1 && w <= W) ? rc_word(A, L, W, w - 1) : 0ULL;
+    __syncwarp();
+}
+
+__device__ __forceinline__ int read_len(const ReadsView &rv, uint64_t r)
+{
+    return rv.uniform_len ? rv.uniform_len : (int)__ldg(rv.len + r);
+}
+
+__device__ __forceinline__ bool grab_chunk(unsigned long long *counter, uint64_t lo, uint64_t hi, int lane,
+                                           uint64_t *begin, uint64_t *end)
+{
+    unsigned long long c = 0;
+    if (lane == 0) c = atomicAdd(counter, (unsigned long long)kChunk);
+    c = __shfl_sync(FULL, c, 0);
+    uint64_t b = lo + c;
+    if (b >= hi) return false;
+    *begin = b;
+    *end = (b + kChunk < hi) ? b + kChunk : hi;
+    return true;
+}
+
+__device__ __forceinline__ void warp_stat_add(unsigned long long *stats, int slot, unsigned long long v)
+{
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(stats + slot, v);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// hash table build: two records per read (prefix k-mer, suffix k-mer), bucket = one 32-byte sector of four slots.
+// Warp per read; quad 0 inserts the prefix record and quad 1 the suffix record cooperatively: each lane of the quad
+// reads one slot of the bucket (one coalesced sector), the quad votes, the first empty lane does the CAS.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int WP = ((rv.max_len + 31) >> 5) + 2;
+    uint64_t *A = smem + (size_t)wib * 2 * WP, *R = A + WP;
+    const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
+    for (uint64_t r = (uint64_t)blockIdx.x * kWarps + wib; r < rv.n; r += nwarps) {
+        if (skip_bits && ((__ldg(skip_bits + (r >> 5)) >> (r & 31)) & 1)) continue; // warp-uniform
+        const int L = read_len(rv, r);
+        stage_read(rv, r, L, A, R, WP, lane);
+        if (lane < 8) {
+            const int quad = lane >> 2, sub = lane & 3;
+            const unsigned qmask = 0xFu << (quad * 4);
+            int fwd;
+            // record 2r = prefix k-mer (j = 0), record 2r+1 = suffix k-mer (j = L-K): HashTable.cpp:430-431
+            const uint64_t h = canon_kmer_hash(A, R, L, quad ? L - K : 0, K, &fwd);
+            const uint64_t val = make_slot(h, fwd, (uint32_t)(2 * r + quad));
+            uint64_t b = bucket_of(h, tv.nbuckets);
+            for (;;) {
+                unsigned long long *slot = reinterpret_cast<unsigned long long *>(tv.slots) + 4 * b + sub;
+                const uint64_t cur = __ldcg(slot); // L2 (coherent) read: slots change under our feet
+                const unsigned empties = (__ballot_sync(qmask, cur == kEmptySlot) >> (quad * 4)) & 0xFu;
+                if (empties) {
+                    const int first = __ffs(empties) - 1;
+                    int ok = 0;
+                    if (sub == first) ok = atomicCAS(slot, (unsigned long long)kEmptySlot, (unsigned long long)val) == kEmptySlot;
+                    ok = __shfl_sync(qmask, ok, quad * 4 + first);
+                    if (ok) break; // otherwise somebody else took it: vote again on the same bucket
+                } else {
+                    b = (b + 1 == tv.nbuckets) ? 0 : b + 1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// search kernels
+// ---------------------------------------------------------------------------------------------------------------
+enum { MODE_CONTAIN = 0, MODE_EDGES = 1 };
+
+// hit record of the edge pass: [55..40 j][39..8 rec][1..0 type]  -> sorts by (j, rec) = the reference's visiting order
+__device__ __forceinline__ uint64_t make_hit(int j, uint32_t rec, int type) { return ((uint64_t)j << 40) | ((uint64_t)rec << 8) | (uint64_t)type; }
+__device__ __forceinline__ int hit_j(uint64_t h) { return (int)(h >> 40); }
+__device__ __forceinline__ uint32_t hit_read(uint64_t h) { return (uint32_t)(h >> 9) & 0x7FFFFFFFu; }
+__device__ __forceinline__ int hit_type(uint64_t h) { return (int)(h & 3); }
+
+struct WarpSmem {
+    uint64_t *A, *R, *hits, *row, *best;
+    int *ctrl; // [0] n hits, [1] slow flag, [2] n row, [3] n best
+};
+
+template <int NW>
+__device__ __forceinline__ bool verify_dovetail(const SearchParams &p, const WarpSmem &s, int L1, int j, int type, uint32_t r2)
+{
+    RegMatcher<NW> m;
+    if (NW == 0) reinterpret_cast<RegMatcher<0> &>(m).stride = p.reads.stride;
+    m.load(p.reads.words, r2);
+    const int L2 = read_len(p.reads, r2);
+    return check_dovetail(s.A, s.R, L1, j, p.K, type, L2, m);
+}
+
+// Exact sequential search of one read (used when MAX_EDGE_PER_KMER can fire or a position has a long candidate list):
+// positions in ascending order, candidates in record order, at most `cap` insertions per position, a read already in
+// the row is skipped without counting (OverlapGraph.cpp:645-670).  The warp walks 8 buckets (32 slots) per step.
+template <int NW>
+__device__ void search_edges_slow(const SearchParams &p, const WarpSmem &s, uint64_t r1, int L1, int lane,
+                                  unsigned long long &n_probes, unsigned long long &n_buckets,
+                                  unsigned long long &n_verified, unsigned long long &n_capfired)
+{
+    const int K = p.K;
+    int nrow = 0;
+    if (lane == 0) s.ctrl[2] = 0;
+    __syncwarp();
+    for (int j = 1; j < L1 - K; j++) {
+        int fq;
+        const uint64_t h = canon_kmer_hash(s.A, s.R, L1, j, K, &fq);
+        const uint32_t tag = slot_tag(h);
+        uint64_t b = bucket_of(h, p.table.nbuckets);
+        int nbest = 0, nvalid = 0;
+        n_probes += (lane == 0);
+        for (;;) {
+            uint64_t bb = b + (lane >> 2);
+            if (bb >= p.table.nbuckets) bb -= p.table.nbuckets;
+            const uint64_t v = __ldg(p.table.slots + 4 * bb + (lane & 3));
+            const unsigned empties = __ballot_sync(FULL, v == kEmptySlot);
+            const int limit = empties ? ((__ffs(empties) - 1) | 3) : 31; // the chain ends in the first bucket with a hole
+            n_buckets += (lane == 0) ? (unsigned long long)((limit >> 2) + 1) : 0ULL;
+            bool valid = false;
+            uint64_t key = 0;
+            if (lane <= limit && v != kEmptySlot && (uint32_t)(v >> 33) == tag) {
+                const uint32_t rec = (uint32_t)v, r2 = rec >> 1;
+                bool seen = (r2 == (uint32_t)r1);
+                for (int k = 0; k < nrow && !seen; k++) seen = (uint32_t)entry_nbr(s.row[k]) == r2;
+                if (!seen) {
+                    const int type = cand_type(rec & 1, (int)((v >> 32) & 1) == fq);
+                    n_verified++;
+                    if (verify_dovetail<NW>(p, s, L1, j, type, r2)) { valid = true; key = ((uint64_t)rec << 2) | (uint64_t)type; }
+                }
+            }
+            unsigned vm = __ballot_sync(FULL, valid);
+            while (vm) { // keep the kBestMax smallest records, sorted (lane 0 owns the list)
+                const int src = __ffs(vm) - 1; vm &= vm - 1;
+                const uint64_t kk = __shfl_sync(FULL, key, src);
+                nvalid++;
+                if (lane == 0) {
+                    int pos = nbest;
+                    if (nbest == kBestMax) { if (kk >= s.best[nbest - 1]) pos = -1; else pos = nbest - 1; }
+                    else nbest++;
+                    if (pos >= 0) {
+                        while (pos > 0 && s.best[pos - 1] > kk) { s.best[pos] = s.best[pos - 1]; pos--; }
+                        s.best[pos] = kk;
+                    }
+                }
+            }
+            if (empties) break;
+            b += 8; if (b >= p.table.nbuckets) b -= p.table.nbuckets;
+        }
+        if (lane == 0) {
+            int ctr = 0, fired = 0;
+            const int row0 = nrow;
+            for (int t = 0; t < nbest; t++) {
+                const uint64_t kk = s.best[t];
+                const uint32_t r2 = (uint32_t)(kk >> 3);
+                bool seen = false;
+                for (int k = row0; k < nrow && !seen; k++) seen = (uint32_t)entry_nbr(s.row[k]) == r2; // same position, other record
+                if (seen) continue;
+                if (ctr >= p.cap) { fired = 1; continue; }
+                int orient, ovl;
+                type_to_edge((int)(kk & 3), L1, K, j, &orient, &ovl);
+                if (nrow < p.rowcap) s.row[nrow] = make_entry(L1 - ovl, r2, orient);
+                nrow++; ctr++;
+            }
+            if (nvalid > nbest && ctr >= p.cap) fired = 1;
+            n_capfired += fired;
+            s.ctrl[2] = nrow;
+        }
+        __syncwarp();
+        nrow = s.ctrl[2];
+    }
+}
+
+template <int NW, int MODE>
+__global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int WP = ((p.reads.max_len + 31) >> 5) + 2;
+    const int K = p.K;
+    // per-warp shared memory carve-up (u64 units)
+    const size_t per_warp = (MODE == MODE_EDGES) ? (size_t)(2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (size_t)(2 * WP);
+    WarpSmem s;
+    s.A = smem + wib * per_warp; s.R = s.A + WP;
+    s.hits = s.R + WP; s.row = s.hits + p.hcap; s.best = s.row + p.rowcap;
+    s.ctrl = reinterpret_cast<int *>(s.best + kBestMax);
+
+    unsigned long long n_queries = 0, n_probes = 0, n_buckets = 0, n_verified = 0, n_hits = 0, n_entries = 0,
+                       n_capfired = 0, n_slow = 0, maxdeg = 0;
+    unsigned long long blk_cur = 0, blk_end = 0; // this warp's reserved slice of the adjacency buffer
+    uint64_t rb, re;
+    while (grab_chunk(p.work_counter, p.q_lo, p.q_hi, lane, &rb, &re)) {
+        for (uint64_t r1 = rb; r1 < re; r1++) {
+            if (MODE == MODE_EDGES && ((__ldg(p.contained_bits + (r1 >> 5)) >> (r1 & 31)) & 1)) continue; // OverlapGraph.cpp:657
+            const int L1 = read_len(p.reads, r1);
+            stage_read(p.reads, r1, L1, s.A, s.R, WP, lane);
+            n_queries += (lane == 0);
+            if (MODE == MODE_EDGES) {
+                if (lane < 4) s.ctrl[lane] = 0;
+                __syncwarp();
+            }
+            // containment: positions [0, L1-K) (OverlapGraph.cpp:401), pruned to those where some read can fit:
+            //   types 0/2 need j + L2 <= L1, types 1/3 need j >= L2 - K, and L2 >= min_len.
+            // edges: positions [1, L1-K) (OverlapGraph.cpp:638)
+            const int jlo = (MODE == MODE_EDGES) ? 1 : 0, jhi = L1 - K;
+            for (int jb = jlo; jb < jhi; jb += 32) {
+                const int j = jb + lane;
+                bool act = j < jhi;
+                if (MODE == MODE_CONTAIN) act = act && (j <= L1 - p.reads.min_len || j >= p.reads.min_len - K);
+                if (act) {
+                    int fq;
+                    const uint64_t h = canon_kmer_hash(s.A, s.R, L1, j, K, &fq);
+                    const uint32_t tag = slot_tag(h);
+                    uint64_t b = bucket_of(h, p.table.nbuckets);
+                    n_probes++;
+                    for (int walked = 0;; walked++) {
+                        if (MODE == MODE_EDGES && walked == kScanLimit) { s.ctrl[1] = 1; break; } // long chain: slow path
+                        uint64_t v[4];
+                        load_bucket(p.table.slots, b, v);
+                        n_buckets++;
+                        bool hole = false;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            if (v[q] == kEmptySlot) { hole = true; continue; }
+                            if ((uint32_t)(v[q] >> 33) != tag) continue;
+                            const uint32_t rec = (uint32_t)v[q], r2 = rec >> 1;
+                            if (r2 == (uint32_t)r1) continue; // OverlapGraph.cpp:421 / :655
+                            const int type = cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq);
+                            if (MODE == MODE_EDGES) {
+                                n_verified++;
+                                if (verify_dovetail<NW>(p, s, L1, j, type, r2)) {
+                                    const int pos = atomicAdd(&s.ctrl[0], 1);
+                                    if (pos < p.hcap) s.hits[pos] = make_hit(j, rec, type);
+                                }
+                            } else {
+                                const int L2 = read_len(p.reads, r2);
+                                // read1 must be longer, or equal and earlier in the file (OverlapGraph.cpp:424, :449)
+                                if (!(L1 > L2 || (L1 == L2 && r1 < r2))) continue;
+                                RegMatcher<NW> m;
+                                if (NW == 0) reinterpret_cast<RegMatcher<0> &>(m).stride = p.reads.stride;
+                                m.load(p.reads.words, r2);
+                                n_verified++;
+                                if (check_contained(s.A, s.R, L1, j, K, type, L2, m)) {
+                                    n_hits++;
+                                    atomicMin(p.best + r2, (unsigned long long)make_ckey(r1, j, rec & 1, type));
+                                }
+                            }
+                        }
+                        if (hole) break;
+                        b = (b + 1 == p.table.nbuckets) ? 0 : b + 1;
+                    }
+                }
+                __syncwarp();
+            }
+            if (MODE != MODE_EDGES) continue;
+
+            // ---- resolve the hits of this read into its adjacency row ------------------------------------------
+            const int n = s.ctrl[0];
+            bool slow = s.ctrl[1] != 0 || n > p.hcap;
+            int nrow = 0;
+            if (!slow) {
+                bool over = false;
+                for (int i0 = 0; i0 < n; i0 += 32) {
+                    const int i = i0 + lane;
+                    const bool have = i < n;
+                    const uint64_t hk = have ? s.hits[i] : 0ULL;
+                    const uint32_t r2 = hit_read(hk);
+                    const int j = hit_j(hk);
+                    bool keep = have;
+                    int cnt = 0;
+                    for (int k = 0; k < n; k++) {
+                        const uint64_t o = s.hits[k];
+                        if (hit_read(o) == r2 && o < hk) keep = false; // an earlier (j, record) already paired r2 (:656)
+                        cnt += hit_j(o) == j;
+                    }
+                    over |= have && cnt > p.cap;
+                    if (keep) {
+                        int orient, ovl;
+                        type_to_edge(hit_type(hk), L1, K, j, &orient, &ovl);
+                        const int pos = atomicAdd(&s.ctrl[2], 1);
+                        s.row[pos] = make_entry(L1 - ovl, r2, orient); // pos < n <= hcap <= rowcap
+                    }
+                }
+                slow = __any_sync(FULL, over); // a position with more than cap partners: redo exactly
+                __syncwarp();
+                nrow = s.ctrl[2];
+                n_hits += (lane == 0) ? (unsigned long long)n : 0ULL;
+            }
+            if (slow) {
+                n_slow += (lane == 0);
+                search_edges_slow<NW>(p, s, r1, L1, lane, n_probes, n_buckets, n_verified, n_capfired);
+                nrow = s.ctrl[2];
+                if (nrow > p.rowcap) nrow = p.rowcap; // cannot happen: rowcap >= cap * positions
+            }
+            if (nrow == 0) continue;
+            // ---- sort by (offset, neighbour, orientation) and append to the global adjacency -------------------
+            // space comes from a warp-private slice reserved kRowBlock entries at a time: one global atomic per ~30
+            // reads instead of one per read (rows need not be contiguous in read order; rowinfo points at them)
+            if (blk_cur + nrow > blk_end) {
+                const unsigned long long want = nrow > kRowBlock ? (unsigned long long)nrow : (unsigned long long)kRowBlock;
+                if (lane == 0) blk_cur = atomicAdd(p.rows_cursor, want);
+                blk_cur = __shfl_sync(FULL, blk_cur, 0);
+                blk_end = blk_cur + want;
+            }
+            const unsigned long long base = blk_cur;
+            blk_cur += nrow;
+            n_entries += (lane == 0) ? (unsigned long long)nrow : 0ULL;
+            if ((unsigned long long)nrow > maxdeg) maxdeg = nrow;
+            if (base + nrow <= p.rows_cap) {
+                for (int i = lane; i < nrow; i += 32) {
+                    const uint64_t e = s.row[i];
+                    int rank = 0;
+                    for (int k = 0; k < nrow; k++) rank += s.row[k] < e;
+                    p.rows[base + rank] = e;
+                }
+                if (lane == 0) p.rowinfo[r1] = make_rowinfo(base, (uint32_t)nrow);
+            } else if (lane == 0) {
+                atomicExch(p.stats + ST_OVERFLOW, 1ULL);
+            }
+            __syncwarp();
+        }
+    }
+    warp_stat_add(p.stats, ST_QUERIES, n_queries);
+    warp_stat_add(p.stats, ST_PROBES, n_probes);
+    warp_stat_add(p.stats, ST_BUCKETS, n_buckets);
+    warp_stat_add(p.stats, ST_VERIFIED, n_verified);
+    warp_stat_add(p.stats, ST_HITS, n_hits);
+    if (MODE == MODE_EDGES) {
+        warp_stat_add(p.stats, ST_ENTRIES, n_entries);
+        warp_stat_add(p.stats, ST_CAP_FIRED, n_capfired);
+        warp_stat_add(p.stats, ST_SLOW_READS, n_slow);
+        for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(FULL, maxdeg, o); if (t > maxdeg) maxdeg = t; }
+        if (lane == 0 && maxdeg) atomicMax(p.stats + ST_MAXDEG, maxdeg);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// containment bookkeeping
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void k_contained_finish(const unsigned long long *best, uint64_t n, uint32_t *bits, unsigned long long *count)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool c = i < n && best[i] != ~0ULL;
+    const unsigned m = __ballot_sync(FULL, c);
+    if ((threadIdx.x & 31) == 0) {
+        if ((i >> 5) < ((n + 31) >> 5)) bits[i >> 5] = m;
+        if (m) atomicAdd(count, (unsigned long long)__popc(m));
+    }
+}
+
+__global__ void k_contained_rows(const unsigned long long *best, ReadsView rv, int K, disco_crow *out, unsigned long long *cursor)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long key = i < rv.n ? best[i] : ~0ULL;
+    const bool c = key != ~0ULL;
+    const unsigned m = __ballot_sync(FULL, c);
+    unsigned long long base = 0;
+    const int lane = threadIdx.x & 31;
+    if (lane == 0 && m) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL, base, 0);
+    if (c) {
+        const uint64_t r1 = key >> 20;
+        const int j = (int)((key >> 4) & 0xFFFF), type = (int)(key & 3);
+        const int L1 = read_len(rv, r1);
+        int orient, ovl;
+        type_to_edge(type, L1, K, j, &orient, &ovl);
+        disco_crow row;
+        row.contained = (uint32_t)i; row.container = (uint32_t)r1; row.orient = (uint32_t)orient; row.start = (uint32_t)(L1 - ovl);
+        out[base + __popc(m & ((1u << lane) - 1))] = row;
+    }
+}
+
+__global__ void k_rebase_rowinfo(uint64_t *rowinfo, uint64_t lo, uint64_t hi, uint64_t base)
+{
+    const uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < hi) {
+        const uint64_t ri = rowinfo[i];
+        if (rowinfo_deg(ri)) rowinfo[i] = make_rowinfo(rowinfo_start(ri) + base, rowinfo_deg(ri));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// transitive reduction, pass 1: Myers marking of every node on the full graph (OverlapGraph.cpp:687-723).
+// Warp per node u; u's row lives in shared memory (neighbour id + orientation + state); for every neighbour v still
+// INPLAY, in ascending offset order, the warp streams v's row (coalesced) and eliminates common neighbours whose
+// orientations chain through v.  The result is the eliminated bit of u's own entries.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    // per warp: ids u32[maxdeg], st u8[maxdeg]  (st: bits 0-1 orientation, bit 2 eliminated)
+    const size_t per_warp = (((size_t)p.maxdeg * 5 + 15) / 16) * 16;
+    uint8_t *basep = reinterpret_cast<uint8_t *>(smem) + wib * per_warp;
+    uint32_t *ids = reinterpret_cast<uint32_t *>(basep);
+    volatile uint8_t *st = basep + (size_t)p.maxdeg * 4;
+    unsigned long long n_rows = 0, n_ent = 0;
+    uint64_t ub, ue;
+    while (grab_chunk(p.work_counter, p.u_lo, p.u_hi, lane, &ub, &ue)) {
+        for (uint64_t u = ub; u < ue; u++) {
+            const uint64_t ri = p.rowinfo[u];
+            const int deg = (int)rowinfo_deg(ri);
+            if (deg == 0) continue;
+            const uint64_t start = rowinfo_start(ri);
+            for (int k = lane; k < deg; k += 32) {
+                const uint64_t e = p.rows[start + k];
+                ids[k] = (uint32_t)entry_nbr(e);
+                st[k] = (uint8_t)entry_orient(e);
+            }
+            __syncwarp();
+            for (int i = 0; i < deg; i++) {
+                const uint8_t si = st[i];
+                if (si & 4) continue; // ELIMINATED neighbours do not eliminate (OverlapGraph.cpp:696)
+                const int t1 = si & 3;
+                const uint64_t vri = p.rowinfo[ids[i]];
+                const int vd = (int)rowinfo_deg(vri);
+                const uint64_t vs = rowinfo_start(vri);
+                n_rows += (lane == 0); n_ent += (lane == 0) ? (unsigned long long)vd : 0ULL;
+                for (int q0 = 0; q0 < vd; q0 += 32) {
+                    const int q = q0 + lane;
+                    bool go = false;
+                    uint32_t w = 0;
+                    if (q < vd) {
+                        const uint64_t e = __ldcg(p.rows + vs + q); // other warps may be setting eliminated bits: ignore them
+                        w = (uint32_t)entry_nbr(e);
+                        go = chain_ok(t1, entry_orient(e));
+                    }
+                    if (__any_sync(FULL, go)) {
+                        for (int k = 0; k < deg; k++)
+                            if (go && ids[k] == w) st[k] = st[k] | 4; // only this lane can hold w == ids[k]
+                    }
+                }
+                __syncwarp();
+            }
+            for (int k = lane; k < deg; k += 32)
+                if (st[k] & 4) p.rows[start + k] |= kElimBit;
+            __syncwarp();
+        }
+    }
+    warp_stat_add(p.stats, ST_ROWS_FETCHED, n_rows);
+    warp_stat_add(p.stats, ST_ENTRIES_FETCHED, n_ent);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// transitive reduction, pass 2: an edge dies when it was eliminated from either endpoint (edge and twin are flagged
+// together in the reference, OverlapGraph.cpp:717-718).  For each surviving entry u->w the warp finds the twin in
+// w's row; the lower id emits the canonical record (OverlapGraph.cpp:808).
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_reduce_emit(ReduceParams p)
+{
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    disco_edge *out = reinterpret_cast<disco_edge *>(p.edges_out);
+    __shared__ disco_edge ebuf_all[kWarps][32]; // kept edges are staged per warp: one global atomic per 32 edges
+    disco_edge *ebuf = ebuf_all[wib];
+    int nbuf = 0;                               // warp-uniform
+    unsigned long long n_rows = 0, n_ent = 0, n_multi = 0, n_one = 0, n_out = 0;
+    uint64_t ub, ue;
+    while (grab_chunk(p.work_counter, p.u_lo, p.u_hi, lane, &ub, &ue)) {
+        for (uint64_t u = ub; u < ue; u++) {
+            const uint64_t ri = p.rowinfo[u];
+            const int deg = (int)rowinfo_deg(ri);
+            if (deg == 0) continue;
+            const uint64_t start = rowinfo_start(ri);
+            const int Lu = read_len(p.reads, u);
+            for (int k0 = 0; k0 < deg; k0 += 32) {
+                const int k = k0 + lane;
+                const uint64_t e = (k < deg) ? p.rows[start + k] : kElimBit;
+                unsigned alive = __ballot_sync(FULL, !(e & kElimBit));
+                while (alive) {
+                    const int src = __ffs(alive) - 1; alive &= alive - 1;
+                    const uint64_t ee = __shfl_sync(FULL, e, src);
+                    const uint64_t w = entry_nbr(ee);
+                    const int orient = entry_orient(ee), offset = entry_offset(ee);
+                    const uint64_t wri = p.rowinfo[w];
+                    const int wd = (int)rowinfo_deg(wri);
+                    const uint64_t ws = rowinfo_start(wri);
+                    const int Lw = read_len(p.reads, w);
+                    n_rows += (lane == 0); n_ent += (lane == 0) ? (unsigned long long)wd : 0ULL;
+                    // twin of u->w as seen from w (OverlapGraph.cpp:617-619)
+                    const int t_orient = twin_orient(orient), t_offset = Lw + offset - Lu;
+                    int found = 0, dead = 0, same = 0;
+                    for (int q0 = 0; q0 < wd; q0 += 32) {
+                        const int q = q0 + lane;
+                        uint64_t te = 0;
+                        bool hit = false;
+                        if (q < wd) { te = p.rows[ws + q]; hit = entry_nbr(te) == u; }
+                        const unsigned hm = __ballot_sync(FULL, hit);
+                        if (hm) {
+                            const uint64_t t = __shfl_sync(FULL, te, __ffs(hm) - 1);
+                            found = 1; dead = (t & kElimBit) != 0;
+                            same = entry_orient(t) == t_orient && entry_offset(t) == t_offset;
+                            break;
+                        }
+                    }
+                    bool emit;
+                    if (found) {
+                        if (!same && u < w) n_multi += (lane == 0);
+                        emit = !dead && u < w; // lower id's overlap is the canonical one
+                    } else {
+                        n_one += (lane == 0);
+                        emit = true;           // the other endpoint cannot see this edge: emit it from here
+                    }
+                    if (emit) { // warp-uniform
+                        if (lane == 0) {
+                            disco_edge o;
+                            if (u < w) { o.src = (uint32_t)u; o.dst = (uint32_t)w; o.offset = (uint32_t)offset; o.orient = (uint32_t)orient; }
+                            else { o.src = (uint32_t)w; o.dst = (uint32_t)u; o.offset = (uint32_t)t_offset; o.orient = (uint32_t)t_orient; }
+                            ebuf[nbuf] = o;
+                            n_out++;
+                        }
+                        nbuf++;
+                        if (nbuf == 32) {
+                            __syncwarp();
+                            unsigned long long pos = 0;
+                            if (lane == 0) pos = atomicAdd(p.edges_cursor, 32ULL);
+                            pos = __shfl_sync(FULL, pos, 0);
+                            if (pos + lane < p.edges_cap) out[pos + lane] = ebuf[lane];
+                            __syncwarp();
+                            nbuf = 0;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (nbuf) {
+        __syncwarp();
+        unsigned long long pos = 0;
+        if (lane == 0) pos = atomicAdd(p.edges_cursor, (unsigned long long)nbuf);
+        pos = __shfl_sync(FULL, pos, 0);
+        if (lane < nbuf && pos + lane < p.edges_cap) out[pos + lane] = ebuf[lane];
+    }
+    warp_stat_add(p.stats, ST_ROWS_FETCHED, n_rows);
+    warp_stat_add(p.stats, ST_ENTRIES_FETCHED, n_ent);
+    warp_stat_add(p.stats, ST_MULTI_OVERLAP, n_multi);
+    warp_stat_add(p.stats, ST_ONE_SIDED, n_one);
+    warp_stat_add(p.stats, ST_EDGES_OUT, n_out);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+static int wp_of(int max_len) { return ((max_len + 31) >> 5) + 2; }
+
+template <typename Kern>
+static cudaError_t persistent_grid(Kern kern, size_t smem, int num_sms, int *grid)
+{
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorInvalidConfiguration;
+    *grid = num_sms * per_sm; // persistent: every CTA resident, work handed out by the atomic counter
+    return cudaSuccess;
+}
+
+cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, const uint32_t *skip_bits,
+                                int num_sms, cudaStream_t s)
+{
+    const size_t smem = (size_t)kWarps * 2 * wp_of(r.max_len) * sizeof(uint64_t);
+    int grid = 0;
+    cudaError_t e = persistent_grid(k_table_insert, smem, num_sms, &grid);
+    if (e != cudaSuccess) return e;
+    const uint64_t need = (r.n + kWarps - 1) / kWarps;
+    if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
+    k_table_insert<<<grid, kThreads, smem, s>>>(r, t, K, skip_bits);
+    return cudaGetLastError();
+}
+
+static size_t search_smem(const SearchParams &p, int mode)
+{
+    const size_t WP = wp_of(p.reads.max_len);
+    const size_t per_warp = (mode == MODE_EDGES) ? (2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (2 * WP);
+    return per_warp * kWarps * sizeof(uint64_t);
+}
+
+bool search_edges_fits(int max_len, int K, int cap)
+{
+    const size_t rowcap = (size_t)cap * (size_t)(max_len - K);
+    const size_t per_warp = 2 * (size_t)wp_of(max_len) + 2 * rowcap + kBestMax + 2;
+    return per_warp * kWarps * sizeof(uint64_t) <= 200 * 1024;
+}
+
+template <int MODE>
+static cudaError_t launch_search(const SearchParams &p, int num_sms, cudaStream_t s)
+{
+    const size_t smem = search_smem(p, MODE);
+    int grid = 0;
+    cudaError_t e;
+#define DISCO_LAUNCH(NWV)                                                            \
+    {                                                                                \
+        e = persistent_grid(k_search<NWV, MODE>, smem, num_sms, &grid);              \
+        if (e != cudaSuccess) return e;                                              \
+        k_search<NWV, MODE><<<grid, kThreads, smem, s>>>(p);                         \
+        break;                                                                       \
+    }
+    switch (p.reads.stride) {
+    case 2: DISCO_LAUNCH(2)
+    case 4: DISCO_LAUNCH(4)
+    case 6: DISCO_LAUNCH(6)
+    case 8: DISCO_LAUNCH(8)
+    case 10: DISCO_LAUNCH(10)
+    case 12: DISCO_LAUNCH(12)
+    case 16: DISCO_LAUNCH(16)
+    default: DISCO_LAUNCH(0)
+    }
+#undef DISCO_LAUNCH
+    return cudaGetLastError();
+}
+
+cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStream_t s) { return launch_search<MODE_CONTAIN>(p, num_sms, s); }
+cudaError_t launch_search_edges(const SearchParams &p, int num_sms, cudaStream_t s) { return launch_search<MODE_EDGES>(p, num_sms, s); }
+
+cudaError_t launch_contained_finish(const unsigned long long *best, uint64_t n, uint32_t *bits, unsigned long long *count, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    const uint64_t blocks = (n + 255) / 256;
+    k_contained_finish<<<(unsigned)blocks, 256, 0, s>>>(best, n, bits, count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_contained_rows(const unsigned long long *best, const ReadsView &r, int K, void *rows_out,
+                                  unsigned long long *cursor, cudaStream_t s)
+{
+    if (r.n == 0) return cudaSuccess;
+    const uint64_t blocks = (r.n + 255) / 256;
+    k_contained_rows<<<(unsigned)blocks, 256, 0, s>>>(best, r, K, reinterpret_cast<disco_crow *>(rows_out), cursor);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s)
+{
+    if (u_hi <= u_lo) return cudaSuccess;
+    const uint64_t blocks = (u_hi - u_lo + 255) / 256;
+    k_rebase_rowinfo<<<(unsigned)blocks, 256, 0, s>>>(rowinfo, u_lo, u_hi, base);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t s)
+{
+    const size_t per_warp = (((size_t)p.maxdeg * 5 + 15) / 16) * 16;
+    const size_t smem = per_warp * kWarps;
+    int grid = 0;
+    cudaError_t e = persistent_grid(k_reduce_mark, smem, num_sms, &grid);
+    if (e != cudaSuccess) return e;
+    k_reduce_mark<<<grid, kThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t s)
+{
+    int grid = 0;
+    cudaError_t e = persistent_grid(k_reduce_emit, 0, num_sms, &grid);
+    if (e != cudaSuccess) return e;
+    k_reduce_emit<<<grid, kThreads, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace disco

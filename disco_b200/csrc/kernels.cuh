@@ -1,0 +1,91 @@
+// kernels.cuh -- parameter blocks and launcher prototypes of the sm_100a kernels (kernels.cu) used by api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace disco {
+
+// per-launch statistics slots (unsigned long long each)
+enum StatSlot {
+    ST_QUERIES = 0,   // reads searched
+    ST_PROBES,        // k-mer look-ups
+    ST_BUCKETS,       // 32-byte buckets read
+    ST_VERIFIED,      // candidate reads fetched + compared
+    ST_HITS,          // verified candidates that passed
+    ST_ENTRIES,       // adjacency entries written (directed)
+    ST_CAP_FIRED,
+    ST_SLOW_READS,
+    ST_MAXDEG,        // atomicMax
+    ST_OVERFLOW,      // adjacency buffer too small (entries needed = rows cursor)
+    ST_ROWS_FETCHED,  // reduction: neighbour rows read
+    ST_ENTRIES_FETCHED,
+    ST_MULTI_OVERLAP,
+    ST_ONE_SIDED,
+    ST_EDGES_OUT,
+    ST_COUNT
+};
+
+struct ReadsView {
+    const uint64_t *words; // n * stride, 16-byte aligned rows
+    const uint16_t *len;   // n
+    uint64_t n;
+    int stride;            // words per read (even)
+    int uniform_len;       // 0, or the common length of every read
+    int min_len, max_len;
+};
+
+struct TableView {
+    uint64_t *slots;   // nbuckets * 4
+    uint64_t nbuckets;
+};
+
+struct SearchParams {
+    ReadsView reads;
+    TableView table;
+    int K;                 // hashStringLength = minOverlap - 1
+    int cap;               // MAX_EDGE_PER_KMER
+    uint64_t q_lo, q_hi;   // query reads [q_lo, q_hi)
+    unsigned long long *work_counter;
+    unsigned long long *stats;
+    // containment pass
+    unsigned long long *best; // n keys, ~0 = not contained
+    // edge pass
+    const uint32_t *contained_bits;
+    uint64_t *rows;
+    uint64_t rows_cap;
+    unsigned long long *rows_cursor;
+    uint64_t *rowinfo;
+    int hcap;    // fast-path hit buffer entries per warp
+    int rowcap;  // row buffer entries per warp  (>= cap * (max_len - K - 1))
+};
+
+struct ReduceParams {
+    ReadsView reads;
+    uint64_t *rows;
+    const uint64_t *rowinfo;
+    uint64_t u_lo, u_hi;
+    unsigned long long *work_counter;
+    unsigned long long *stats;
+    int maxdeg;
+    // emit
+    void *edges_out;       // disco_edge[edges_cap]
+    uint64_t edges_cap;
+    unsigned long long *edges_cursor;
+};
+
+cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, const uint32_t *skip_bits,
+                                int num_sms, cudaStream_t s);
+cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStream_t s);
+cudaError_t launch_search_edges(const SearchParams &p, int num_sms, cudaStream_t s);
+cudaError_t launch_contained_finish(const unsigned long long *best, uint64_t n, uint32_t *bits,
+                                    unsigned long long *count, cudaStream_t s);
+// rows for contained reads: keys -> (contained, container, orient, start), compacted in read order
+cudaError_t launch_contained_rows(const unsigned long long *best, const ReadsView &r, int K, void *rows_out,
+                                  unsigned long long *cursor, cudaStream_t s);
+cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t s);
+cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t s);
+cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s);
+// smem bytes a search / reduce block needs for the given shape (0 = does not fit)
+bool search_edges_fits(int max_len, int K, int cap);
+
+} // namespace disco

@@ -1,0 +1,211 @@
+"""ctypes binding of the C ABI in include/disco_gpu.h (libdisco_gpu.so).
+
+This is the only way Python reaches the kernels; there is no fallback: if the library is missing or no GPU is
+present the calls raise."""
+import ctypes as C
+import os
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libdisco_gpu.so")
+
+EDGE_DTYPE = np.dtype([("src", "<u4"), ("dst", "<u4"), ("offset", "<u4"), ("orient", "<u4")])
+CROW_DTYPE = np.dtype([("contained", "<u4"), ("container", "<u4"), ("orient", "<u4"), ("start", "<u4")])
+
+EXPORTS = [
+    "disco_gpu_create", "disco_gpu_destroy", "disco_gpu_last_error", "disco_gpu_set_stream", "disco_gpu_load_reads",
+    "disco_gpu_load_reads_device", "disco_gpu_build_graph", "disco_gpu_counts", "disco_gpu_get_contained",
+    "disco_gpu_get_edges", "disco_gpu_get_row", "disco_gpu_get_stats", "disco_gpu_begin", "disco_gpu_phase_table",
+    "disco_gpu_phase_contained", "disco_gpu_phase_finish_contained", "disco_gpu_phase_edges", "disco_gpu_phase_reduce",
+    "disco_gpu_dev_contained_keys", "disco_gpu_dev_rowinfo", "disco_gpu_dev_rows", "disco_gpu_rebase_rows",
+    "disco_gpu_adopt_rows", "disco_gpu_set_max_degree", "disco_gpu_sync",
+]
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "n_reads", "n_contained", "n_edges", "raw_directed_edges", "cap_fired", "multi_overlap_pairs", "one_sided_edges",
+        "slow_path_reads", "probes_contained", "probes_edges", "buckets_contained", "buckets_edges",
+        "verified_contained", "verified_edges", "max_degree", "reduce_rows_fetched", "reduce_entries_fetched",
+        "table_buckets", "edge_capacity")] + [(n, C.c_float) for n in (
+            "ms_table_all", "ms_contained", "ms_finish_contained", "ms_table_nc", "ms_edges", "ms_mark", "ms_emit", "ms_total")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class DiscoError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DiscoError(f"{LIB_PATH} not built: run `python -m disco_b200.build` (there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
+        L.disco_gpu_create.argtypes = [C.POINTER(vp), i32]
+        L.disco_gpu_destroy.argtypes = [vp]
+        L.disco_gpu_destroy.restype = None
+        L.disco_gpu_last_error.argtypes = [vp]
+        L.disco_gpu_last_error.restype = C.c_char_p
+        L.disco_gpu_set_stream.argtypes = [vp, vp]
+        L.disco_gpu_load_reads.argtypes = [vp, vp, vp, u64, u32]
+        L.disco_gpu_load_reads_device.argtypes = [vp, vp, vp, u64, u32, u32, u32]
+        L.disco_gpu_build_graph.argtypes = [vp, u32, u32]
+        L.disco_gpu_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+        L.disco_gpu_get_contained.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.disco_gpu_get_edges.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.disco_gpu_get_row.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
+        L.disco_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.disco_gpu_begin.argtypes = [vp, u32, u32]
+        L.disco_gpu_phase_table.argtypes = [vp, i32]
+        L.disco_gpu_phase_contained.argtypes = [vp, u64, u64]
+        L.disco_gpu_phase_finish_contained.argtypes = [vp]
+        L.disco_gpu_phase_edges.argtypes = [vp, u64, u64]
+        L.disco_gpu_phase_reduce.argtypes = [vp, u64, u64]
+        for f in ("disco_gpu_dev_contained_keys", "disco_gpu_dev_rowinfo"):
+            getattr(L, f).argtypes = [vp]
+            getattr(L, f).restype = vp
+        L.disco_gpu_dev_rows.argtypes = [vp, C.POINTER(u64)]
+        L.disco_gpu_dev_rows.restype = vp
+        L.disco_gpu_rebase_rows.argtypes = [vp, u64, u64, u64]
+        L.disco_gpu_adopt_rows.argtypes = [vp, vp, u64]
+        L.disco_gpu_set_max_degree.argtypes = [vp, u64]
+        L.disco_gpu_sync.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+class GpuBuildGraph:
+    """One context = one GPU.  Mirrors the reference call order: load reads (HashTable::insertDataset) then
+    build_graph (OverlapGraph::buildOverlapGraphFromHashTable)."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        self._h = C.c_void_p()
+        rc = self._L.disco_gpu_create(C.byref(self._h), device)
+        if rc:
+            raise DiscoError(f"disco_gpu_create({device}) -> {rc}: {self._L.disco_gpu_last_error(None).decode()}")
+        self.n = 0
+        self._keep = None
+
+    def close(self):
+        if self._h:
+            self._L.disco_gpu_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc:
+            raise DiscoError(f"{what} -> {rc}: {self._L.disco_gpu_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream_handle: int):
+        self._ck(self._L.disco_gpu_set_stream(self._h, C.c_void_p(cuda_stream_handle)), "set_stream")
+
+    def sync(self):
+        self._ck(self._L.disco_gpu_sync(self._h), "sync")
+
+    def load_reads(self, packed: np.ndarray, lens: np.ndarray):
+        """packed uint64[n, wpr] (host, ideally pinned), lens uint16[n]."""
+        assert packed.dtype == np.uint64 and packed.ndim == 2 and packed.flags.c_contiguous
+        assert lens.dtype == np.uint16 and lens.shape == (packed.shape[0],)
+        self._keep = (packed, lens)  # the copy is asynchronous
+        self.n = packed.shape[0]
+        self._ck(self._L.disco_gpu_load_reads(self._h, packed.ctypes.data, lens.ctypes.data, self.n, packed.shape[1]), "load_reads")
+
+    def load_reads_ptr(self, packed_ptr: int, lens_ptr: int, n: int, wpr: int):
+        self.n = n
+        self._ck(self._L.disco_gpu_load_reads(self._h, C.c_void_p(packed_ptr), C.c_void_p(lens_ptr), n, wpr), "load_reads")
+
+    def load_reads_device(self, d_packed_ptr: int, d_lens_ptr: int, n: int, wpr: int, min_len: int, max_len: int):
+        self.n = n
+        self._ck(self._L.disco_gpu_load_reads_device(self._h, C.c_void_p(d_packed_ptr), C.c_void_p(d_lens_ptr), n, wpr,
+                                                     min_len, max_len), "load_reads_device")
+
+    def build_graph(self, min_overlap: int, max_edge_per_kmer: int = 4):
+        self._ck(self._L.disco_gpu_build_graph(self._h, min_overlap, max_edge_per_kmer), "build_graph")
+
+    # phase level
+    def begin(self, min_overlap, max_edge_per_kmer=4):
+        self._ck(self._L.disco_gpu_begin(self._h, min_overlap, max_edge_per_kmer), "begin")
+
+    def phase_table(self, exclude_contained: bool):
+        self._ck(self._L.disco_gpu_phase_table(self._h, int(exclude_contained)), "phase_table")
+
+    def phase_contained(self, lo, hi):
+        self._ck(self._L.disco_gpu_phase_contained(self._h, lo, hi), "phase_contained")
+
+    def phase_finish_contained(self):
+        self._ck(self._L.disco_gpu_phase_finish_contained(self._h), "phase_finish_contained")
+
+    def phase_edges(self, lo, hi):
+        self._ck(self._L.disco_gpu_phase_edges(self._h, lo, hi), "phase_edges")
+
+    def phase_reduce(self, lo, hi):
+        self._ck(self._L.disco_gpu_phase_reduce(self._h, lo, hi), "phase_reduce")
+
+    def dev_contained_keys(self) -> int:
+        return self._L.disco_gpu_dev_contained_keys(self._h)
+
+    def dev_rowinfo(self) -> int:
+        return self._L.disco_gpu_dev_rowinfo(self._h)
+
+    def dev_rows(self):
+        n = C.c_uint64()
+        p = self._L.disco_gpu_dev_rows(self._h, C.byref(n))
+        return p, n.value
+
+    def rebase_rows(self, lo, hi, base):
+        self._ck(self._L.disco_gpu_rebase_rows(self._h, lo, hi, base), "rebase_rows")
+
+    def adopt_rows(self, d_rows_ptr: int, n_entries: int):
+        self._ck(self._L.disco_gpu_adopt_rows(self._h, C.c_void_p(d_rows_ptr), n_entries), "adopt_rows")
+
+    def set_max_degree(self, d: int):
+        self._ck(self._L.disco_gpu_set_max_degree(self._h, d), "set_max_degree")
+
+    # results
+    def counts(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.disco_gpu_counts(self._h, C.byref(a), C.byref(b)), "counts")
+        return a.value, b.value
+
+    def contained(self) -> np.ndarray:
+        nc, _ = self.counts()
+        out = np.zeros(nc, dtype=CROW_DTYPE)
+        w = C.c_uint64()
+        self._ck(self._L.disco_gpu_get_contained(self._h, out.ctypes.data, nc, C.byref(w)), "get_contained")
+        return out[:w.value]
+
+    def edges(self, out: np.ndarray = None) -> np.ndarray:
+        _, ne = self.counts()
+        if out is None:
+            out = np.zeros(ne, dtype=EDGE_DTYPE)
+        w = C.c_uint64()
+        self._ck(self._L.disco_gpu_get_edges(self._h, out.ctypes.data, len(out), C.byref(w)), "get_edges")
+        return out[:w.value]
+
+    def row(self, read: int, capacity: int = 1 << 16) -> np.ndarray:
+        out = np.zeros(capacity, dtype=EDGE_DTYPE)
+        w = C.c_uint64()
+        self._ck(self._L.disco_gpu_get_row(self._h, read, out.ctypes.data, capacity, C.byref(w)), "get_row")
+        return out[:w.value]
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._ck(self._L.disco_gpu_get_stats(self._h, C.byref(s)), "get_stats")
+        return s.as_dict()
+
+
+def sort_edges(e: np.ndarray) -> np.ndarray:
+    return e[np.lexsort((e["orient"], e["offset"], e["dst"], e["src"]))]

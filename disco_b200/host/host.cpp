@@ -1,0 +1,284 @@
+// host.cpp -- host side of the BuildGraph stage: input parsing, the reference read filter, 2-bit packing, output
+// formatting.  Plain C++17 + OpenMP + zlib; see include/disco_host.h for the reference lines each piece restates.
+#include "../../include/disco_host.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <omp.h>
+#include <string>
+#include <vector>
+#include <zlib.h>
+
+namespace {
+thread_local std::string g_err;
+int fail(const std::string &m) { g_err = m; return -1; }
+
+// Dataset.cpp:48-87
+const char *kFilterStrings[] = {
+    "ACACACACACACACACACACACACACACA", "AGAGAGAGAGAGAGAGAGAGAGAGAGAGA", "ATATATATATATATATATATATATATATA",
+    "CGCGCGCGCGCGCGCGCGCGCGCGCGCGC", "CTCTCTCTCTCTCTCTCTCTCTCTCTCTC", "AAGAAGAAGAAGAAGAAGAAGAAGAAGAA",
+    "ATAATAATAATAATAATAATAATAATAAT", "TAATAATAATAATAATAATAATAATAATA", "AACAACAACAACAACAACAACAACAACAA",
+    "ACAACAACAACAACAACAACAACAACAAC", "CAACAACAACAACAACAACAACAACAACA", "AAGAAGAAGAAGAAGAAGAAGAAGAAGAA",
+    "AGAAGAAGAAGAAGAAGAAGAAGAAGAAG", "GAAGAAGAAGAAGAAGAAGAAGAAGAAGA", "TTCTTCTTCTTCTTCTTCTTCTTCTTCTT",
+    "AAATAAATAAATAAATAAATAAATAAATA", "TAAATAAATAAATAAATAAATAAATAAAT", "ATAAATAAATAAATAAATAAATAAATAAA",
+    "AATAAATAAATAAATAAATAAATAAATAA", "AATTAATTAATTAATTAATTAATTAATTA", "ATTAATTAATTAATTAATTAATTAATTAA",
+    "TTAATTAATTAATTAATTAATTAATTAAT", "TAATTAATTAATTAATTAATTAATTAATT", "AAAGAAAGAAAGAAAGAAAGAAAGAAAGA",
+    "AAAGAAAGAAAGAAAGAAAGAAAGAAAGA", "AGAAAGAAAGAAAGAAAGAAAGAAAGAAA", "GAAAGAAAGAAAGAAAGAAAGAAAGAAAG",
+    "TACATACATACATACATACATACATACAT", "ACATACATACATACATACATACATACATA", "CATACATACATACATACATACATACATAC",
+    "ATACATACATACATACATACATACATACA", "GTTTGTTTGTTTGTTTGTTTGTTTGTTTG", "TGTTTGTTTGTTTGTTTGTTTGTTTGTTT",
+    "TTTGTTTGTTTGTTTGTTTGTTTGTTTGT", "AGGGAGGGAGGGAGGGAGGGAGGGAGGGA", "GAGGGAGGGAGGGAGGGAGGGAGGGAGGG",
+    "GGAGGGAGGGAGGGAGGGAGGGAGGGAGG", "GGGAGGGAGGGAGGGAGGGAGGGAGGGAG"};
+const char *kMerStrings[] = {"AC", "AG", "AT", "CG", "CT", "GT", "AAT", "ATA", "TAA", "AAC", "ACA", "CAA", "AAG", "AGA", "GAA", "GGGGCC"};
+constexpr uint64_t kMinReadSize = 30; // Dataset.h:15
+
+uint64_t count_substring(const char *s, uint64_t n, const char *sub, uint64_t m)
+{ // Common.h:171-181: std::string::find from the end of the previous match (non-overlapping)
+    uint64_t cnt = 0, i = 0;
+    while (i + m <= n) {
+        const void *p = memmem(s + i, n - i, sub, m);
+        if (!p) break;
+        cnt++;
+        i = (const char *)p - s + m;
+    }
+    return cnt;
+}
+
+bool test_read(const char *s, uint64_t n)
+{
+    if (n < kMinReadSize) return false;
+    uint64_t cnt[4] = {0, 0, 0, 0};
+    for (uint64_t i = 0; i < n; i++) {
+        const char c = s[i];
+        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return false;
+        cnt[(c >> 1) & 3]++;
+    }
+    uint64_t thr = (uint64_t)((double)n * .7); // Dataset.cpp:415
+    if (cnt[0] >= thr || cnt[1] >= thr || cnt[2] >= thr || cnt[3] >= thr) return false;
+    for (const char *f : kFilterStrings) {
+        const uint64_t len = strlen(f);
+        if (n < len) return false;
+        if (memcmp(f, s, len) == 0 || memcmp(f, s + n - len, len) == 0) return false;
+    }
+    thr = (uint64_t)((double)n * .5); // Dataset.cpp:431
+    for (const char *m : kMerStrings) {
+        const uint64_t ml = strlen(m);
+        if (count_substring(s, n, m, ml) * ml >= thr) return false;
+    }
+    return true;
+}
+
+inline uint64_t code_of(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; } // HashTable.h:16-22
+
+void pack_ascii(const char *s, uint64_t n, uint64_t *out)
+{
+    for (uint64_t i = 0; i < n; i++) out[i >> 5] |= code_of(s[i]) << (62 - 2 * (i & 31)); // HashTable.cpp:458-470
+}
+} // namespace
+
+struct disco_reads {
+    uint32_t min_overlap = 0;
+    int threads = 1;
+    uint64_t records = 0;             // file index of the last record seen
+    std::vector<std::string> seqs;    // accepted, upper-cased
+    std::vector<uint64_t> file_index; // accepted
+    bool finalized = false;
+    uint32_t wpr = 0, min_len = 0, max_len = 0;
+    std::vector<uint64_t> packed;
+    std::vector<uint16_t> len;
+};
+
+namespace {
+// filter a batch of raw records (pointer, length) in parallel, then append the accepted ones in order
+struct RawRec { const char *p; uint64_t n; bool strip_nl; };
+void absorb(disco_reads *r, const std::vector<RawRec> &batch)
+{
+    const size_t m = batch.size();
+    std::vector<std::string> clean(m);
+    std::vector<char> good(m, 0);
+#pragma omp parallel for schedule(dynamic, 256) num_threads(r->threads)
+    for (size_t i = 0; i < m; i++) {
+        std::string &s = clean[i];
+        s.reserve(batch[i].n);
+        for (uint64_t k = 0; k < batch[i].n; k++) {
+            char c = batch[i].p[k];
+            if (batch[i].strip_nl && c == '\n') continue;            // Dataset.cpp:276 removes only '\n'
+            s.push_back((char)toupper((unsigned char)c));           // Dataset.cpp:303-304
+        }
+        good[i] = s.size() > r->min_overlap && s.size() <= 32767 && test_read(s.data(), s.size()); // Dataset.cpp:305
+    }
+    for (size_t i = 0; i < m; i++) {
+        r->records++;
+        if (good[i]) { r->seqs.push_back(std::move(clean[i])); r->file_index.push_back(r->records); }
+    }
+}
+} // namespace
+
+extern "C" {
+
+const char *disco_host_last_error(void) { return g_err.c_str(); }
+
+int disco_host_test_read(const char *seq, uint64_t len) { return test_read(seq, len) ? 1 : 0; }
+
+disco_reads *disco_reads_new(uint32_t min_overlap, int threads)
+{
+    disco_reads *r = new disco_reads();
+    r->min_overlap = min_overlap;
+    r->threads = threads > 0 ? threads : omp_get_max_threads();
+    return r;
+}
+
+void disco_reads_free(disco_reads *r) { delete r; }
+
+int disco_reads_add_records(disco_reads *r, const char *seqs, const uint64_t *off, uint64_t n)
+{
+    if (!r || r->finalized) return fail("reads object already finalized");
+    std::vector<RawRec> batch(n);
+    for (uint64_t i = 0; i < n; i++) batch[i] = RawRec{seqs + off[i], off[i + 1] - off[i], false};
+    absorb(r, batch);
+    return 0;
+}
+
+int disco_reads_add_file(disco_reads *r, const char *path)
+{
+    if (!r || r->finalized) return fail("reads object already finalized");
+    gzFile fp = gzopen(path, "rb"); // transparently reads plain files too
+    if (!fp) return fail(std::string("Unable to open file: ") + path);
+    gzbuffer(fp, 1 << 20);
+    std::string data;
+    {
+        std::vector<char> buf(1 << 24);
+        int got;
+        while ((got = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)got);
+        if (got < 0) { gzclose(fp); return fail(std::string("read error in ") + path); }
+    }
+    gzclose(fp);
+    const uint64_t before = r->records;
+    if (!data.empty()) {
+        const char *b = data.data(), *e = b + data.size();
+        std::vector<RawRec> batch;
+        if (*b == '>') { // FASTA (Dataset.cpp:270-281): header line, then everything up to the next '>'
+            const char *p = b;
+            while (p < e) {
+                const char *nl = (const char *)memchr(p, '\n', e - p);
+                if (!nl) { batch.push_back(RawRec{e, 0, true}); break; } // header without sequence
+                const char *s = nl + 1;
+                const char *nx = (const char *)memchr(s, '>', e - s);
+                if (!nx) nx = e;
+                batch.push_back(RawRec{s, (uint64_t)(nx - s), true});
+                p = nx + (nx < e ? 1 : 0);
+                if (nx == e) break;
+            }
+        } else if (*b == '@') { // FASTQ (Dataset.cpp:282-293): four lines per record, sequence on the second
+            const char *p = b;
+            auto next_line = [&](const char *&ls, const char *&le) { // std::getline semantics
+                if (p >= e) return false;
+                ls = p;
+                const char *nl = (const char *)memchr(p, '\n', e - p);
+                le = nl ? nl : e;
+                p = nl ? nl + 1 : e;
+                return true;
+            };
+            const char *ls, *le;
+            while (next_line(ls, le)) {
+                const char *ss = e, *se = e;
+                if (!next_line(ss, se)) { ss = se = e; }
+                const char *d0, *d1;
+                next_line(d0, d1);
+                next_line(d0, d1);
+                batch.push_back(RawRec{ss, (uint64_t)(se - ss), false});
+            }
+        } else {
+            return fail("Unknown input file format."); // Dataset.cpp:267
+        }
+        absorb(r, batch);
+    }
+    if (r->records <= before) return fail(std::string("File empty. No reads loaded from ") + path); // Dataset.cpp:113-114
+    return 0;
+}
+
+int disco_reads_finalize(disco_reads *r)
+{
+    if (!r) return fail("NULL");
+    if (r->finalized) return 0;
+    const uint64_t n = r->seqs.size();
+    uint32_t mn = 0xFFFFFFFFu, mx = 0;
+    for (const auto &s : r->seqs) { mn = std::min<uint32_t>(mn, (uint32_t)s.size()); mx = std::max<uint32_t>(mx, (uint32_t)s.size()); }
+    if (n == 0) { mn = mx = 0; }
+    r->min_len = mn; r->max_len = mx;
+    r->wpr = std::max<uint32_t>(2, (((mx + 31) / 32) + 1) & ~1u);
+    r->packed.assign(n * (uint64_t)r->wpr, 0);
+    r->len.resize(n);
+#pragma omp parallel for schedule(static) num_threads(r->threads)
+    for (uint64_t i = 0; i < n; i++) {
+        pack_ascii(r->seqs[i].data(), r->seqs[i].size(), r->packed.data() + i * r->wpr);
+        r->len[i] = (uint16_t)r->seqs[i].size();
+    }
+    std::vector<std::string>().swap(r->seqs);
+    r->finalized = true;
+    return 0;
+}
+
+uint64_t disco_reads_count(const disco_reads *r) { return r->finalized ? r->len.size() : r->seqs.size(); }
+uint64_t disco_reads_records(const disco_reads *r) { return r->records; }
+uint32_t disco_reads_words_per_read(const disco_reads *r) { return r->wpr; }
+const uint64_t *disco_reads_packed(const disco_reads *r) { return r->packed.data(); }
+const uint16_t *disco_reads_len(const disco_reads *r) { return r->len.data(); }
+const uint64_t *disco_reads_file_index(const disco_reads *r) { return r->file_index.data(); }
+uint32_t disco_reads_min_len(const disco_reads *r) { return r->min_len; }
+uint32_t disco_reads_max_len(const disco_reads *r) { return r->max_len; }
+
+int disco_host_pack_codes(const uint8_t *codes, const uint64_t *off, uint64_t n, uint32_t wpr, uint64_t *out,
+                          uint16_t *len_out, int threads)
+{
+    if (threads <= 0) threads = omp_get_max_threads();
+    int bad = 0;
+#pragma omp parallel for schedule(static) num_threads(threads) reduction(| : bad)
+    for (uint64_t i = 0; i < n; i++) {
+        const uint64_t L = off[i + 1] - off[i];
+        uint64_t *o = out + i * wpr;
+        for (uint32_t w = 0; w < wpr; w++) o[w] = 0;
+        if (L > 32767 || (L + 31) / 32 > wpr) { bad = 1; continue; }
+        const uint8_t *c = codes + off[i];
+        for (uint64_t k = 0; k < L; k++) o[k >> 5] |= (uint64_t)(c[k] & 3) << (62 - 2 * (k & 31));
+        len_out[i] = (uint16_t)L;
+    }
+    return bad ? fail("read too long for words_per_read") : 0;
+}
+
+int disco_write_pargraph(const char *path, const disco_edge *edges, uint64_t n, const uint64_t *file_index,
+                         const uint16_t *len, int flag, int append)
+{
+    FILE *f = fopen(path, append ? "a" : "w");
+    if (!f) return fail(std::string("Unable to open file: ") + path);
+    std::vector<char> buf(1 << 22);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    for (uint64_t i = 0; i < n; i++) {
+        const disco_edge &e = edges[i];
+        const unsigned long long sl = len[e.src], dl = len[e.dst], off = e.offset, ovl = sl - off;
+        // src dst orient,ovl,0,0,srcLen,offset,srcLen-1,dstLen,0,ovl-1,NA,flag   (OverlapGraph.cpp:811-867)
+        fprintf(f, "%llu\t%llu\t%u,%llu,0,0,%llu,%llu,%llu,%llu,0,%llu,NA,%d\n", (unsigned long long)file_index[e.src],
+                (unsigned long long)file_index[e.dst], e.orient, ovl, sl, off, sl - 1, dl, ovl - 1, flag);
+    }
+    fclose(f);
+    return 0;
+}
+
+int disco_write_contained(const char *path, const disco_crow *rows, uint64_t n, const uint64_t *file_index,
+                          const uint16_t *len, int append)
+{
+    FILE *f = fopen(path, append ? "a" : "w");
+    if (!f) return fail(std::string("Unable to open file: ") + path);
+    std::vector<char> buf(1 << 22);
+    setvbuf(f, buf.data(), _IOFBF, buf.size());
+    for (uint64_t i = 0; i < n; i++) {
+        const disco_crow &r = rows[i];
+        const unsigned long long l2 = len[r.contained], l1 = len[r.container], st = r.start;
+        // contained container orient,L2,0,0,L2,0,L2,L1,start,start+L2   (OverlapGraph.cpp:438-447)
+        fprintf(f, "%llu\t%llu\t%u,%llu,0,0,%llu,0,%llu,%llu,%llu,%llu\n", (unsigned long long)file_index[r.contained],
+                (unsigned long long)file_index[r.container], r.orient, l2, l2, l2, l1, st, st + l2);
+    }
+    fclose(f);
+    return 0;
+}
+
+} // extern "C"

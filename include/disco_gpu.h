@@ -1,0 +1,130 @@
+/*
+ * disco_gpu.h -- C ABI of the B200 BuildGraph hot path (libdisco_gpu.so).
+ *
+ * The reference (abiswas-odu/Disco) has no plugin/FFI seam for this path: buildG is one process and the hot path is
+ * the C++ call chain main.cpp:61-63
+ *     HashTable::insertDataset()                      (src/BuildGraph/src/HashTable.cpp:46)
+ *     OverlapGraph::buildOverlapGraphFromHashTable()  (src/BuildGraph/src/OverlapGraph.cpp:100)
+ *        markContainedReads()                         (OverlapGraph.cpp:333)
+ *        insertAllEdgesOfRead() / markTransitiveEdges() / removeTransitiveEdges()   (:631 / :687 / :731)
+ * This header is the seam a maintainer would cut there (INTEGRATION.md shows the patch): the host keeps parsing,
+ * filtering, numbering and file output; everything between "reads are numbered" and "edges are written" is one
+ * library call.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - read ids are 0-based positions in the caller's accepted-read order (= reference readNumber - 1,
+ *     Dataset.cpp:133-134 after file-order numbering).
+ *   - packed reads use the reference record payload layout (HashTable.cpp:456-477): base i in bits
+ *     [62-2*(i%32), 63-2*(i%32)] of word i/32, A=0 C=1 G=2 T=3, unused bits and words zero.
+ *   - every function returns 0 on success or a negative DISCO_E_* code; disco_gpu_last_error() gives the text.
+ *     Nothing in this library calls exit() or falls back to a CPU path: without a usable GPU every call fails.
+ *   - a context is bound to one device and one stream; it is not thread-safe.
+ */
+#ifndef DISCO_GPU_H_
+#define DISCO_GPU_H_
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DISCO_OK 0
+#define DISCO_E_CUDA (-1)     /* CUDA runtime error (no device, launch failure, ...) */
+#define DISCO_E_ARG (-2)      /* invalid argument / call order */
+#define DISCO_E_NOMEM (-3)    /* device or host allocation failed */
+#define DISCO_E_LIMIT (-4)    /* input exceeds a documented limit */
+
+typedef struct disco_ctx disco_ctx;
+
+/* One kept (transitively reduced) overlap edge, src < dst, written from src's point of view
+ * == one line of <prefix>_<t>_parGraph.txt (OverlapGraph.cpp:808-833). */
+typedef struct {
+    uint32_t src;    /* 0-based read id */
+    uint32_t dst;
+    uint32_t offset; /* overlapOffset = len(src) - overlap length (OverlapGraph.cpp:667) */
+    uint32_t orient; /* 0 u<-<v  1 u<->v  2 u>-<v  3 u>->v (Edge.h:30-34) */
+} disco_edge;
+
+/* One contained / duplicate read == one line of <prefix>_<t>_containedReads.txt (OverlapGraph.cpp:438-447). */
+typedef struct {
+    uint32_t contained; /* 0-based read id */
+    uint32_t container;
+    uint32_t orient;
+    uint32_t start;     /* len(container) - overlapLen : where the contained read starts inside the container */
+} disco_crow;
+
+typedef struct {
+    uint64_t n_reads, n_contained, n_edges;      /* n_edges = kept undirected edges */
+    uint64_t raw_directed_edges;                  /* entries of the unreduced adjacency (both directions) */
+    uint64_t cap_fired;                           /* (read, position) pairs where MAX_EDGE_PER_KMER cut candidates */
+    uint64_t multi_overlap_pairs;                 /* pairs whose endpoints found different overlaps */
+    uint64_t one_sided_edges;                     /* edges found from one endpoint only */
+    uint64_t slow_path_reads;                     /* reads that took the sequential (exact cap) search path */
+    uint64_t probes_contained, probes_edges;      /* k-mer look-ups issued */
+    uint64_t buckets_contained, buckets_edges;    /* 32-byte table buckets read */
+    uint64_t verified_contained, verified_edges;  /* candidate reads fetched and compared */
+    uint64_t max_degree;
+    uint64_t reduce_rows_fetched;                 /* neighbour rows read by the two reduction kernels */
+    uint64_t reduce_entries_fetched;              /* adjacency entries read by the two reduction kernels */
+    uint64_t table_buckets;                       /* size of the hash table in 32-byte buckets */
+    uint64_t edge_capacity;                       /* adjacency entries allocated */
+    /* device time of the last disco_gpu_build_graph(), CUDA events on the context's stream, milliseconds */
+    float ms_table_all, ms_contained, ms_finish_contained, ms_table_nc, ms_edges, ms_mark, ms_emit, ms_total;
+} disco_stats;
+
+/* ---- life cycle ---------------------------------------------------------------------------------------------- */
+int disco_gpu_create(disco_ctx **out, int device);
+void disco_gpu_destroy(disco_ctx *ctx);
+const char *disco_gpu_last_error(const disco_ctx *ctx); /* ctx may be NULL: last error of a failed create */
+/* Run on the caller's stream (a cudaStream_t passed as void*); default is a stream owned by the context. */
+int disco_gpu_set_stream(disco_ctx *ctx, void *cuda_stream);
+
+/* ---- input: replaces the record payload writes of HashTable::insertIntoTable (HashTable.cpp:456-514) --------- */
+/* Host buffers (pinned memory makes the copy asynchronous). len[i] in (min_overlap, 32767]. */
+int disco_gpu_load_reads(disco_ctx *ctx, const uint64_t *packed, const uint16_t *len, uint64_t n_reads,
+                         uint32_t words_per_read);
+/* Same, but the buffers already live in this device's memory. */
+int disco_gpu_load_reads_device(disco_ctx *ctx, const uint64_t *d_packed, const uint16_t *d_len, uint64_t n_reads,
+                                uint32_t words_per_read, uint32_t min_len, uint32_t max_len);
+
+/* ---- the whole hot path: insertDataset + buildOverlapGraphFromHashTable (HashTable.cpp:46, OverlapGraph.cpp:100)
+ * min_overlap = MinOverlap4BuildGraph (main.cpp:170); max_edge_per_kmer = MAX_EDGE_PER_KMER (Common.h:62), 1..8. */
+int disco_gpu_build_graph(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_kmer);
+
+/* ---- results (device -> caller's host buffers) --------------------------------------------------------------- */
+int disco_gpu_counts(disco_ctx *ctx, uint64_t *n_contained, uint64_t *n_edges);
+/* rows sorted by (container, position, record) == emission order of the reference at -t 1 */
+int disco_gpu_get_contained(disco_ctx *ctx, disco_crow *rows, uint64_t capacity, uint64_t *n_written);
+/* edges in device emission order (callers sort if they need a canonical order) */
+int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, uint64_t *n_written);
+/* unreduced adjacency of one read (its own capped search, sorted by offset): for tests of the cap semantics */
+int disco_gpu_get_row(disco_ctx *ctx, uint64_t read, disco_edge *out, uint64_t capacity, uint64_t *n_written);
+int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out);
+
+/* ---- phase-level entry points (multi-GPU: query reads sharded by id, table and reads replicated; mirrors
+ * BuildGraphMPI/src/OverlapGraph.cpp:524-529 and :293-295).  disco_gpu_build_graph() == the sequence
+ *   table(0) -> contained(0,n) -> finish_contained -> table(1) -> edges(0,n) -> reduce(0,n).
+ * Between phases the host exchanges the buffers exposed below with NCCL. ---------------------------------------- */
+int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_kmer);
+int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained);
+int disco_gpu_phase_contained(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi);
+int disco_gpu_phase_finish_contained(disco_ctx *ctx);
+int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi);
+int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi);
+/* device pointers for collectives: containment keys u64[n] (all-reduce MIN), row info u64[n] (all-reduce SUM after
+ * rebase), adjacency entries u64[*n_entries] (all-gather) */
+void *disco_gpu_dev_contained_keys(disco_ctx *ctx);
+void *disco_gpu_dev_rowinfo(disco_ctx *ctx);
+void *disco_gpu_dev_rows(disco_ctx *ctx, uint64_t *n_entries);
+/* Replace the adjacency by a gathered one: rows u64[n_entries] on this device (copied), row info already reduced
+ * in place.  rebase adds `base` to the start of every local row in [u_lo,u_hi) before the exchange. */
+int disco_gpu_rebase_rows(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi, uint64_t base);
+int disco_gpu_adopt_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entries);
+/* largest row length over all ranks (sizes the reduction kernel's shared memory) */
+int disco_gpu_set_max_degree(disco_ctx *ctx, uint64_t max_degree);
+/* wait for everything queued on the context's stream */
+int disco_gpu_sync(disco_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DISCO_GPU_H_ */

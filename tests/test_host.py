@@ -1,0 +1,147 @@
+"""CPU-only tests of the host side (libdisco_host.so) and of the C ABI surface of libdisco_gpu.so."""
+import ctypes
+import gzip
+import os
+import re
+import subprocess
+import numpy as np
+import pytest
+from helpers import GOLDEN, load_golden, oracle_filter, HERE
+from disco_b200 import gpu, host, pack, synth
+
+ROOT = os.path.dirname(HERE)
+
+
+def test_device_primitives_on_host(tmp_path):
+    """dna.cuh (hash, reverse complement, window compare, dovetail / containment geometry) against string code."""
+    exe = tmp_path / "csrc_host_test"
+    subprocess.run(["g++", "-O2", "-std=c++17", "-o", str(exe), os.path.join(HERE, "csrc_host_test.cpp")], check=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
+def _declared(header):
+    txt = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(r"\b(disco_[a-z_]+)\s*\(", txt)))
+
+
+def test_gpu_library_exports_every_declared_symbol():
+    L = ctypes.CDLL(gpu.LIB_PATH)
+    names = _declared("disco_gpu.h")
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(gpu.EXPORTS) == names
+
+
+def test_host_library_exports_every_declared_symbol():
+    L = ctypes.CDLL(host.LIB_PATH)
+    names = _declared("disco_host.h")
+    for n in names:
+        assert hasattr(L, n), n
+    assert sorted(host.EXPORTS) == names
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(gpu.DiscoError):
+        gpu.GpuBuildGraph(0)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: p.split("/")[-1][:-4])
+def test_filter_and_numbering_match_oracle(path):
+    g = load_golden(path)
+    reads, fi = oracle_filter(g["records"], g["min_overlap"])
+    r = host.Reads(g["min_overlap"])
+    r.add_records(g["records"])
+    r.finalize()
+    assert r.records == len(g["records"])
+    assert r.n == len(reads)
+    assert list(r.file_index) == fi
+    assert list(r.lens) == [len(s) for s in reads]
+    want, _ = pack.pack_codes(synth.from_strings(reads).codes, synth.from_strings(reads).off, r.packed.shape[1])
+    assert np.array_equal(r.packed, want)
+
+
+def test_filter_edge_cases():
+    from oracle import oracle
+    rng = np.random.default_rng(0)
+    cases = ["ACGT" * 10, "A" * 21 + "CGT" * 3, "ACGTN" + "ACGT" * 10, "AC" * 20, "AAT" * 14, "GGGGCC" * 6,
+             "ACACACACACACACACACACACACACACA" + "GATTACA" * 5, "GATTACA" * 5 + "GGGAGGGAGGGAGGGAGGGAGGGAGGGAG", "ACGT" * 7 + "A"]
+    for _ in range(300):
+        L = int(rng.integers(25, 80))
+        p = rng.dirichlet([0.3, 0.3, 0.3, 0.3])
+        cases.append("".join(rng.choice(list("ACGT"), size=L, p=p)))
+    for s in cases:
+        assert host.test_read(s) == oracle.test_read(s), s
+
+
+def _write(path, text, gz=False):
+    if gz:
+        with gzip.open(path, "wt") as f:
+            f.write(text)
+    else:
+        with open(path, "w") as f:
+            f.write(text)
+
+
+@pytest.mark.parametrize("gz", [False, True])
+def test_fasta_fastq_parsing(tmp_path, gz):
+    reads = synth.single_genome(50, 80, 10.0, seed=5).strings()
+    recs = reads[:20] + ["ACGTNNNN" * 10] + reads[20:] + ["acgt" + reads[0][4:].lower()]
+    ext = ".gz" if gz else ""
+    fa = str(tmp_path / ("r.fa" + ext))
+    # multi-line FASTA: sequence lines are joined (Dataset.cpp:276)
+    _write(fa, "".join(f">r{i} desc\n{s[:30]}\n{s[30:]}\n" for i, s in enumerate(recs)), gz)
+    fq = str(tmp_path / ("r.fq" + ext))
+    _write(fq, "".join(f"@r{i}\n{s}\n+\n{'I' * len(s)}\n" for i, s in enumerate(recs)), gz)
+    want, fi = oracle_filter(recs, 40)
+    for path in (fa, fq):
+        r = host.Reads(40)
+        r.add_file(path)
+        r.finalize()
+        assert r.records == len(recs)
+        assert list(r.file_index) == fi
+        ref, _ = pack.pack_codes(synth.from_strings(want).codes, synth.from_strings(want).off, r.packed.shape[1])
+        assert np.array_equal(r.packed, ref)
+    # two files: file indices keep counting (Dataset.cpp:109-128)
+    r = host.Reads(40)
+    r.add_file(fa)
+    r.add_file(fq)
+    r.finalize()
+    assert r.records == 2 * len(recs)
+    assert list(r.file_index) == fi + [x + len(recs) for x in fi]
+    with pytest.raises(host.HostError):
+        host.Reads(40).add_file(str(tmp_path / "missing.fa"))
+
+
+def test_pack_codes_matches_numpy():
+    rs = synth.dup_contained(500, 150, 20.0, seed=3)
+    a, la = host.pack_codes(rs.codes, rs.off)
+    b, lb = pack.pack_codes(rs.codes, rs.off, a.shape[1])
+    assert np.array_equal(a, b) and np.array_equal(la, lb)
+
+
+def test_writers_match_reference_format(tmp_path):
+    g = load_golden([p for p in GOLDEN if "fixture_contained_m30" in p][0])
+    # edges / rows of the golden case, expressed in 0-based accepted-read ids
+    reads, fi = oracle_filter(g["records"], 30)
+    pos = {f: i for i, f in enumerate(fi)}
+    lens = np.array([len(s) for s in reads], dtype=np.uint16)
+    edges = np.zeros(len(g["ref_edges"]), dtype=gpu.EDGE_DTYPE)
+    for k, line in enumerate(g["ref_edges"]):
+        a, b, rest = line.split("\t")
+        f = rest.split(",")
+        edges[k] = (pos[int(a)], pos[int(b)], int(f[5]), int(f[0]))
+    rows = np.zeros(len(g["ref_crows"]), dtype=gpu.CROW_DTYPE)
+    for k, line in enumerate(g["ref_crows"]):
+        a, b, rest = line.split("\t")
+        f = rest.split(",")
+        rows[k] = (pos[int(a)], pos[int(b)], int(f[0]), int(f[8]))
+    pg, cr = str(tmp_path / "p_0_parGraph.txt"), str(tmp_path / "p_0_containedReads.txt")
+    host.write_pargraph(pg, edges, np.array(fi), lens, flag=2)
+    host.write_contained(cr, rows, np.array(fi), lens)
+    assert [l.rstrip("\n") for l in open(pg)] == [l + ",2" for l in g["ref_edges"]]
+    assert [l.rstrip("\n") for l in open(cr)] == g["ref_crows"]
