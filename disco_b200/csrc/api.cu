@@ -328,7 +328,7 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
     p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.contained_bits = ctx->d_bits; p.rows_cursor = ctx->d_cursors + CUR_ROWS; p.rowinfo = ctx->d_rowinfo;
-    p.rowcap = rowcap; p.hcap = std::min(rowcap, 192);
+    p.rowcap = rowcap; p.hcap = search_hit_capacity(rowcap);
     // adjacency capacity: start from 48 entries per query read (30x, 150 bp, minOverlap 50 needs ~33), bounded by free
     // memory; the kernel keeps counting on overflow so that one retry with the exact size always succeeds
     if (!ctx->d_rows) {
@@ -376,7 +376,7 @@ int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
     p.reads = ctx->reads; p.rows = ctx->d_rows; p.rowinfo = ctx->d_rowinfo; p.u_lo = u_lo; p.u_hi = u_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.maxdeg = (int)std::max<uint64_t>(ctx->stats.max_degree, 1);
-    if ((size_t)p.maxdeg * 5 * 8 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
+    if ((size_t)p.maxdeg * 5 + 16 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
     CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
     if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_mark(p, ctx->num_sms, ctx->stream));
     int rc = record(ctx, EV_MARK);

@@ -22,6 +22,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 8;      // reads per work-counter grab
 constexpr int kScanLimit = 6;  // buckets a lane may walk on the fast path before the read is deferred to the slow path
 constexpr int kRowBlock = 1024; // adjacency entries a warp reserves per global atomic
+constexpr int kHitCap = 192;    // fast-path hit buffer entries per warp
 constexpr int kBestMax = 16;   // slow path: smallest-record candidates kept per position (>= 2 * cap)
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -119,8 +120,9 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int WP = ((rv.max_len + 31) >> 5) + 2;
     uint64_t *A = smem + (size_t)wib * 2 * WP, *R = A + WP;
-    const uint64_t nwarps = (uint64_t)gridDim.x * kWarps;
-    for (uint64_t r = (uint64_t)blockIdx.x * kWarps + wib; r < rv.n; r += nwarps) {
+    const int wpb = blockDim.x >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * wpb;
+    for (uint64_t r = (uint64_t)blockIdx.x * wpb + wib; r < rv.n; r += nwarps) {
         if (skip_bits && ((__ldg(skip_bits + (r >> 5)) >> (r & 31)) & 1)) continue; // warp-uniform
         const int L = read_len(rv, r);
         stage_read(rv, r, L, A, R, WP, lane);
@@ -628,8 +630,18 @@ __global__ void __launch_bounds__(kThreads) k_reduce_emit(ReduceParams p)
 // ---------------------------------------------------------------------------------------------------------------
 static int wp_of(int max_len) { return ((max_len + 31) >> 5) + 2; }
 
+constexpr size_t kSmemBudget = 200 * 1024; // per block; leaves room for the driver's reservation out of 227 KB
+
+// largest warp count (8, 4, 2, 1) whose shared memory fits the budget; 0 = even one warp does not fit
+static int warps_that_fit(size_t per_warp_bytes)
+{
+    for (int w = kWarps; w >= 1; w >>= 1)
+        if (per_warp_bytes * w <= kSmemBudget) return w;
+    return 0;
+}
+
 template <typename Kern>
-static cudaError_t persistent_grid(Kern kern, size_t smem, int num_sms, int *grid)
+static cudaError_t persistent_grid(Kern kern, size_t smem, int num_sms, int *grid, int threads = kThreads)
 {
     cudaError_t e = cudaSuccess;
     if (smem > 48 * 1024) {
@@ -637,7 +649,7 @@ static cudaError_t persistent_grid(Kern kern, size_t smem, int num_sms, int *gri
         if (e != cudaSuccess) return e;
     }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorInvalidConfiguration;
     *grid = num_sms * per_sm; // persistent: every CTA resident, work handed out by the atomic counter
@@ -647,41 +659,51 @@ static cudaError_t persistent_grid(Kern kern, size_t smem, int num_sms, int *gri
 cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, const uint32_t *skip_bits,
                                 int num_sms, cudaStream_t s)
 {
-    const size_t smem = (size_t)kWarps * 2 * wp_of(r.max_len) * sizeof(uint64_t);
+    const size_t per_warp = 2 * (size_t)wp_of(r.max_len) * sizeof(uint64_t);
+    const int warps = warps_that_fit(per_warp);
+    if (!warps) return cudaErrorInvalidConfiguration;
+    const size_t smem = per_warp * warps;
     int grid = 0;
-    cudaError_t e = persistent_grid(k_table_insert, smem, num_sms, &grid);
+    cudaError_t e = persistent_grid(k_table_insert, smem, num_sms, &grid, warps * 32);
     if (e != cudaSuccess) return e;
-    const uint64_t need = (r.n + kWarps - 1) / kWarps;
+    const uint64_t need = (r.n + warps - 1) / warps;
     if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
-    k_table_insert<<<grid, kThreads, smem, s>>>(r, t, K, skip_bits);
+    k_table_insert<<<grid, warps * 32, smem, s>>>(r, t, K, skip_bits);
     return cudaGetLastError();
 }
 
-static size_t search_smem(const SearchParams &p, int mode)
+static size_t search_smem_per_warp(const SearchParams &p, int mode)
 {
     const size_t WP = wp_of(p.reads.max_len);
     const size_t per_warp = (mode == MODE_EDGES) ? (2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (2 * WP);
-    return per_warp * kWarps * sizeof(uint64_t);
+    return per_warp * sizeof(uint64_t);
 }
 
 bool search_edges_fits(int max_len, int K, int cap)
 {
-    const size_t rowcap = (size_t)cap * (size_t)(max_len - K);
-    const size_t per_warp = 2 * (size_t)wp_of(max_len) + 2 * rowcap + kBestMax + 2;
-    return per_warp * kWarps * sizeof(uint64_t) <= 200 * 1024;
+    SearchParams p{};
+    p.reads.max_len = max_len;
+    p.rowcap = cap * (max_len - K);
+    p.hcap = p.rowcap < kHitCap ? p.rowcap : kHitCap;
+    return warps_that_fit(search_smem_per_warp(p, MODE_EDGES)) > 0;
 }
+int search_hit_capacity(int rowcap) { return rowcap < kHitCap ? rowcap : kHitCap; }
 
 template <int MODE>
 static cudaError_t launch_search(const SearchParams &p, int num_sms, cudaStream_t s)
 {
-    const size_t smem = search_smem(p, MODE);
+    const size_t per_warp = search_smem_per_warp(p, MODE);
+    const int warps = warps_that_fit(per_warp);
+    if (!warps) return cudaErrorInvalidConfiguration;
+    const size_t smem = per_warp * warps;
+    const int threads = warps * 32;
     int grid = 0;
     cudaError_t e;
 #define DISCO_LAUNCH(NWV)                                                            \
     {                                                                                \
-        e = persistent_grid(k_search<NWV, MODE>, smem, num_sms, &grid);              \
+        e = persistent_grid(k_search<NWV, MODE>, smem, num_sms, &grid, threads);     \
         if (e != cudaSuccess) return e;                                              \
-        k_search<NWV, MODE><<<grid, kThreads, smem, s>>>(p);                         \
+        k_search<NWV, MODE><<<grid, threads, smem, s>>>(p);                          \
         break;                                                                       \
     }
     switch (p.reads.stride) {
@@ -729,11 +751,13 @@ cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_h
 cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t s)
 {
     const size_t per_warp = (((size_t)p.maxdeg * 5 + 15) / 16) * 16;
-    const size_t smem = per_warp * kWarps;
+    const int warps = warps_that_fit(per_warp);
+    if (!warps) return cudaErrorInvalidConfiguration;
+    const size_t smem = per_warp * warps;
     int grid = 0;
-    cudaError_t e = persistent_grid(k_reduce_mark, smem, num_sms, &grid);
+    cudaError_t e = persistent_grid(k_reduce_mark, smem, num_sms, &grid, warps * 32);
     if (e != cudaSuccess) return e;
-    k_reduce_mark<<<grid, kThreads, smem, s>>>(p);
+    k_reduce_mark<<<grid, warps * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -87,5 +87,6 @@ cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t 
 cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s);
 // smem bytes a search / reduce block needs for the given shape (0 = does not fit)
 bool search_edges_fits(int max_len, int K, int cap);
+int search_hit_capacity(int rowcap);
 
 } // namespace disco
