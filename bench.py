@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- BuildGraph hot path on B200: reads/s overlap-searched (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads R] [--impl ours|reference]
+
+One step = one pass of the whole hot path (hash table -> contained reads -> hash table of the survivors -> overlap
+search -> transitive reduction) over one batch of synthetic reads of BASELINE config 2's shape (150 bp, 30x,
+single random genome, minOverlap 50).  `value` times the device path with the packed reads already resident in HBM;
+`e2e` times the C-ABI call with HOST buffers (pinned): H2D of the packed reads, the same device path, D2H of the
+contained rows and the reduced edge list.  N > 1: reads sharded by read id, table and reads replicated on every GPU
+(the BuildGraphMPI partitioning); per-GPU work is fixed (weak scaling), no collective on the timed path except the
+containment-key all-reduce and the adjacency all-gather the algorithm needs.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads/sec overlap-searched"
+UNIT = "reads/s"
+MIN_OVERLAP = 50
+READ_LEN = 150
+COVERAGE = 30.0
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_reads(n_reads, seed):
+    from disco_b200 import synth
+    return synth.single_genome(n_reads, READ_LEN, COVERAGE, seed=seed)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_reference(args):
+    """The reference's own OpenMP BuildGraph (oracle/_ref/buildG = unmodified algorithm + the two SURVEY 8c patches),
+    all host cores, on a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    sample = args.ref_reads
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": f"synthetic {sample} x {READ_LEN}bp single-genome reads, {COVERAGE:.0f}x, minOverlap={MIN_OVERLAP} "
+                                   f"(bounded sample of config 2: 10M x 150bp)", "min_overlap": MIN_OVERLAP}}
+    if not oracle.have_ref():
+        try:
+            oracle.build()
+        except Exception:
+            pass
+    if not oracle.have_ref():
+        line["unavailable"] = "oracle/_ref/buildG missing (reference not built in this snapshot)"
+        print(json.dumps(line), flush=True)
+        return
+    rs = make_reads(sample, seed=2)
+    d = tempfile.mkdtemp(prefix="disco_ref_")
+    fa = os.path.join(d, "reads.fa")
+    rs.write_fasta(fa)
+    times = []
+    for it in range(args.warmup + args.steps):
+        pre = os.path.join(d, f"run{it}", "o")
+        r = oracle.run_ref([fa], pre, MIN_OVERLAP, threads=cores, mem_gb=64)
+        t = r["times"].get("buildOverlapGraphFromHashTable", None)
+        t_ins = r["times"].get("insertDataset", 0.0)
+        if t is None:
+            line["unavailable"] = "reference run failed: " + r["log"][-200:].replace("\n", " ")
+            print(json.dumps(line), flush=True)
+            return
+        if it >= args.warmup:
+            times.append(t + t_ins)  # hash table build + graph stage = the same span our step covers
+    ms = 1000.0 * float(np.mean(times))
+    v = sample / (ms / 1000.0)
+    line.update({"value": v, "ms_per_step": ms,
+                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+                                  "sample": f"{sample} reads of the same generator (seed 2); insertDataset + buildOverlapGraphFromHashTable wall time, -t {cores}"},
+                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(sample_reads):
+    """Bounded CPU sample timed beside the GPU run (rank 0, N=1)."""
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    try:
+        if not oracle.have_ref():
+            oracle.build()
+        if not oracle.have_ref():
+            return None
+        rs = make_reads(sample_reads, seed=2)
+        d = tempfile.mkdtemp(prefix="disco_cpu_")
+        fa = os.path.join(d, "reads.fa")
+        rs.write_fasta(fa)
+        r = oracle.run_ref([fa], os.path.join(d, "o"), MIN_OVERLAP, threads=cores, mem_gb=64)
+        t = r["times"]["buildOverlapGraphFromHashTable"] + r["times"].get("insertDataset", 0.0)
+        return {"value": sample_reads / t, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"{sample_reads} reads of the same generator; oracle/_ref/buildG -t {cores}: insertDataset "
+                          f"{r['times'].get('insertDataset', 0.0):.2f}s + buildOverlapGraphFromHashTable {r['times']['buildOverlapGraphFromHashTable']:.2f}s"}
+    except Exception as e:  # never let the baseline leg kill the bench line
+        return {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": f"failed: {e}"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from disco_b200 import gpu, host, multigpu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_total = args.reads * world          # weak scaling: per-GPU query share is fixed
+    rs = make_reads(n_total, seed=2)
+    n = rs.n
+    wpr = 6
+    # pinned host buffers (the reference-facing call takes host memory)
+    h_packed = torch.empty((n, wpr), dtype=torch.int64).pin_memory()
+    h_lens = torch.empty((n,), dtype=torch.int16).pin_memory()
+    host.pack_codes(rs.codes, rs.off, wpr, out=h_packed.numpy().view(np.uint64), lens_out=h_lens.numpy().view(np.uint16))
+    del rs
+    d_packed = h_packed.cuda(non_blocking=True)
+    d_lens = h_lens.cuda(non_blocking=True)
+    stream = torch.cuda.current_stream()
+    g = gpu.GpuBuildGraph(local)
+    g.set_stream(stream.cuda_stream)
+    runner = multigpu.ShardedBuildGraph(g, rank, world) if world > 1 else None
+    lo, hi = (rank * n) // world, ((rank + 1) * n) // world
+
+    def device_step():
+        g.load_reads_device(d_packed.data_ptr(), d_lens.data_ptr(), n, wpr, READ_LEN, READ_LEN)
+        if runner:
+            runner.build_graph(MIN_OVERLAP, 4)
+        else:
+            g.build_graph(MIN_OVERLAP, 4)
+
+    h_edges = None
+    h_crows = None
+
+    def e2e_step():
+        nonlocal h_edges, h_crows
+        g.load_reads_ptr(h_packed.data_ptr(), h_lens.data_ptr(), n, wpr)
+        if runner:
+            runner.build_graph(MIN_OVERLAP, 4)
+        else:
+            g.build_graph(MIN_OVERLAP, 4)
+        nc, ne = g.counts()
+        if h_edges is None or h_edges.shape[0] < ne:
+            h_edges = torch.empty((int(ne * 1.1) + 16, 4), dtype=torch.int32).pin_memory()
+        if h_crows is None or h_crows.shape[0] < nc:
+            h_crows = torch.empty((int(nc * 1.1) + 16, 4), dtype=torch.int32).pin_memory()
+        e = g.edges(out=h_edges.numpy().view(gpu.EDGE_DTYPE).reshape(-1))
+        c = g.contained_into(h_crows.numpy().view(gpu.CROW_DTYPE).reshape(-1))
+        return len(e), len(c)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        out = None
+        for _ in range(steps):
+            out = fn()
+        t1.record(stream)
+        barrier()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, out
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    stats_acc = []
+    with ClockSampler(local) as clk:
+        # per-step loop so that the per-kernel counters of every step can be read (between steps, outside the kernels)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+        t0.record(stream)
+        for _ in range(args.steps):
+            device_step()
+            stats_acc.append(g.stats())
+        t1.record(stream)
+        barrier()
+        ms_total = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n / (ms_step / 1000.0)
+
+    # end to end through host buffers
+    for _ in range(2):
+        e2e_step()
+    ms_e2e, (ne_out, nc_out) = timed(e2e_step, args.steps)
+    ms_e2e /= args.steps
+    h2d = h_packed.numel() * 8 + h_lens.numel() * 2
+    d2h = (ne_out + nc_out) * 16
+
+    st = stats_acc[-1]
+    tot_raw, tot_edges = st["raw_directed_edges"], st["n_edges"]
+    if world > 1:
+        t = torch.tensor([tot_raw, tot_edges], device="cuda", dtype=torch.int64)
+        dist.all_reduce(t)
+        tot_raw, tot_edges = int(t[0]), int(t[1])
+    peak, peak_src = measured_peak()
+    # algorithmic bytes of the dominant kernel (overlap search), SURVEY 8(d):  R + P*S + H*2S + 8*E_raw per read
+    # with R = 40 B packed read, S = 32 B sector, P probes, H candidates fetched (48-byte rows = 2 sectors), all taken
+    # from the kernel's own counters for THIS rank's launch
+    ms_k = float(np.mean([x["ms_edges_kernel"] for x in stats_acc]))
+    alg_bytes = st["queries_edges"] * 40 + st["probes_edges"] * 32 + st["verified_edges"] * 64 + st["raw_directed_edges"] * 8
+    achieved = alg_bytes / (ms_k / 1000.0) / 1e9 if ms_k > 0 else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic_search_edges.json")
+    if os.path.exists(tp):
+        try:
+            tj = json.load(open(tp))
+            if int(tj.get("reads", -1)) == n and world == 1:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+        "data": "synthetic",
+        "config": {"workload": f"synthetic {n} x {READ_LEN}bp single-genome reads ({COVERAGE:.0f}x, both strands, error-free), "
+                               f"minOverlap={MIN_OVERLAP}" + (f", {world} GPUs: queries sharded by read id, table+reads replicated" if world > 1 else " (BASELINE config 2 when --reads 10000000)"),
+                   "reads": n, "reads_per_gpu": args.reads, "read_len": READ_LEN, "min_overlap": MIN_OVERLAP,
+                   "max_edge_per_kmer": 4, "l2": "inputs larger than L2 (packed reads + table > 126 MB), no flush needed"},
+        "e2e": {"value": n / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e},
+        "gpu_launches": int(8 * args.steps),
+        "clocks": clk.summary(),
+        "roofline": {"bound": "hbm", "kernel": "k_search<EDGES>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                     "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": int(alg_bytes)},
+        "edges_per_s": {"raw_directed": tot_raw / (ms_step / 1000.0), "reduced": tot_edges / (ms_step / 1000.0)},
+        "phase_ms": {k: float(np.mean([s[k] for s in stats_acc])) for k in st if k.startswith("ms_")},
+        "counters": {k: int(v) for k, v in st.items() if not k.startswith("ms_")},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        line["cpu_baseline"] = cpu_baseline(args.ref_reads)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    g.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads per GPU (config 2: 10M)")
+    ap.add_argument("--ref-reads", type=int, default=400_000, help="reads in the bounded CPU sample")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,7 +17,8 @@ namespace {
 thread_local std::string g_create_error;
 
 enum Cursor { CUR_WORK = 0, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_COUNT };
-enum Ev { EV_T0 = 0, EV_TABLE_ALL, EV_CONTAINED, EV_FINISH, EV_TABLE_NC, EV_EDGES, EV_MARK, EV_EMIT, EV_COUNT };
+enum Ev { EV_T0 = 0, EV_TABLE_ALL, EV_CONTAINED, EV_FINISH, EV_TABLE_NC, EV_EDGES, EV_MARK, EV_EMIT, EV_EDGES_K0, EV_EDGES_K1,
+          EV_CONT_K0, EV_CONT_K1, EV_COUNT };
 } // namespace
 
 struct disco_ctx {
@@ -41,7 +42,9 @@ struct disco_ctx {
     unsigned long long *d_best = nullptr;
     uint32_t *d_bits = nullptr;
     disco_crow *d_crows = nullptr;
+    uint64_t crows_cap = 0;
     uint64_t n_contained = 0;
+    uint64_t run_n = 0; // reads the run buffers are sized for
     // adjacency
     uint64_t *d_rowinfo = nullptr;
     uint64_t *d_rows = nullptr;
@@ -98,7 +101,7 @@ void free_run_buffers(disco_ctx *c)
 {
     dfree(c->d_slots); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
     dfree(c->d_rowinfo); dfree(c->d_rows); dfree(c->d_edges);
-    c->rows_cap = c->edges_cap = 0;
+    c->rows_cap = c->edges_cap = c->crows_cap = c->run_n = 0;
     c->begun = c->have_contained = c->have_edges = c->have_reduced = false;
 }
 
@@ -117,6 +120,13 @@ int record(disco_ctx *ctx, int which)
 
 int alloc_reads(disco_ctx *ctx, uint64_t n, int min_len, int max_len)
 {
+    // same shape as the resident set (the steady state of a service that processes batch after batch): keep every buffer
+    if (ctx->d_words && n == ctx->reads.n && n > 0 && pick_stride(max_len) == ctx->reads.stride) {
+        ctx->reads.min_len = min_len; ctx->reads.max_len = max_len;
+        ctx->reads.uniform_len = (min_len == max_len) ? max_len : 0;
+        ctx->begun = ctx->have_contained = ctx->have_edges = ctx->have_reduced = false;
+        return DISCO_OK;
+    }
     free_run_buffers(ctx);
     free_reads(ctx);
     if (n == 0) return fail(ctx, DISCO_E_ARG, "no reads");
@@ -243,7 +253,7 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
     if ((uint32_t)ctx->reads.min_len <= min_overlap)
         return fail(ctx, DISCO_E_ARG, "every read must be longer than min_overlap (Dataset.cpp:305): shortest is %d", ctx->reads.min_len);
     CK(cudaSetDevice(ctx->device));
-    free_run_buffers(ctx);
+    ctx->begun = ctx->have_contained = ctx->have_edges = ctx->have_reduced = false;
     ctx->K = (int)min_overlap - 1; // hashStringLength (HashTable.cpp:50)
     ctx->cap = (int)max_edge_per_kmer;
     if (!search_edges_fits(ctx->reads.max_len, ctx->K, ctx->cap))
@@ -251,11 +261,15 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
     const uint64_t n = ctx->reads.n;
     // 2n records, four 8-byte slots per 32-byte bucket, load factor 1/3 (the reference sizes its table at 8n+1
     // index words, HashTable.cpp:53)
-    ctx->nbuckets = std::max<uint64_t>(1024, n + n / 2);
-    CK(cudaMalloc(&ctx->d_slots, ctx->nbuckets * 4 * sizeof(uint64_t)));
-    CK(cudaMalloc(&ctx->d_best, n * sizeof(unsigned long long)));
-    CK(cudaMalloc(&ctx->d_bits, ((n + 31) / 32) * sizeof(uint32_t)));
-    CK(cudaMalloc(&ctx->d_rowinfo, n * sizeof(uint64_t)));
+    if (ctx->run_n != n) {
+        free_run_buffers(ctx);
+        ctx->nbuckets = std::max<uint64_t>(1024, n + n / 2);
+        CK(cudaMalloc(&ctx->d_slots, ctx->nbuckets * 4 * sizeof(uint64_t)));
+        CK(cudaMalloc(&ctx->d_best, n * sizeof(unsigned long long)));
+        CK(cudaMalloc(&ctx->d_bits, ((n + 31) / 32) * sizeof(uint32_t)));
+        CK(cudaMalloc(&ctx->d_rowinfo, n * sizeof(uint64_t)));
+        ctx->run_n = n;
+    }
     CK(cudaMemsetAsync(ctx->d_best, 0xFF, n * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_rowinfo, 0, n * sizeof(uint64_t), ctx->stream));
@@ -292,7 +306,10 @@ int disco_gpu_phase_contained(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
     p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets};
     p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_c; p.best = ctx->d_best;
+    int rc = record(ctx, EV_CONT_K0);
+    if (rc) return rc;
     if (q_hi > q_lo) CK(launch_search_contained(p, ctx->num_sms, ctx->stream));
+    if ((rc = record(ctx, EV_CONT_K1))) return rc;
     return record(ctx, EV_CONTAINED);
 }
 
@@ -306,9 +323,13 @@ int disco_gpu_phase_finish_contained(disco_ctx *ctx)
     CK(cudaMemcpyAsync(&nc, ctx->d_cursors + CUR_NCONTAINED, sizeof nc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->n_contained = nc;
-    dfree(ctx->d_crows);
-    if (nc) {
+    if (nc > ctx->crows_cap) {
+        dfree(ctx->d_crows);
+        ctx->crows_cap = 0;
         CK(cudaMalloc(&ctx->d_crows, nc * sizeof(disco_crow)));
+        ctx->crows_cap = nc;
+    }
+    if (nc) {
         CK(launch_contained_rows(ctx->d_best, ctx->reads, ctx->K, ctx->d_crows, ctx->d_cursors + CUR_CROWS, ctx->stream));
     }
     ctx->have_contained = true;
@@ -345,7 +366,9 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
         CK(cudaMemsetAsync(ctx->d_stats_e, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
         if (attempt) CK(cudaMemsetAsync(ctx->d_rowinfo + q_lo, 0, nq * sizeof(uint64_t), ctx->stream));
         p.rows = ctx->d_rows; p.rows_cap = ctx->rows_cap;
+        { int rc = record(ctx, EV_EDGES_K0); if (rc) return rc; }
         if (nq) CK(launch_search_edges(p, ctx->num_sms, ctx->stream));
+        { int rc = record(ctx, EV_EDGES_K1); if (rc) return rc; }
         unsigned long long cur[2] = {0, 0}, st[ST_COUNT];
         CK(cudaMemcpyAsync(cur, ctx->d_cursors + CUR_WORK, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(st, ctx->d_stats_e, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
@@ -505,6 +528,7 @@ int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out)
     disco_stats &s = ctx->stats;
     s.probes_contained = sc[ST_PROBES]; s.buckets_contained = sc[ST_BUCKETS]; s.verified_contained = sc[ST_VERIFIED];
     s.probes_edges = se[ST_PROBES]; s.buckets_edges = se[ST_BUCKETS]; s.verified_edges = se[ST_VERIFIED];
+    s.queries_contained = sc[ST_QUERIES]; s.queries_edges = se[ST_QUERIES];
     s.cap_fired = se[ST_CAP_FIRED]; s.slow_path_reads = se[ST_SLOW_READS];
     s.multi_overlap_pairs = se[ST_MULTI_OVERLAP]; s.one_sided_edges = se[ST_ONE_SIDED];
     s.reduce_rows_fetched = se[ST_ROWS_FETCHED]; s.reduce_entries_fetched = se[ST_ENTRIES_FETCHED];
@@ -517,6 +541,7 @@ int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out)
     s.ms_finish_contained = ms(EV_CONTAINED, EV_FINISH); s.ms_table_nc = ms(EV_FINISH, EV_TABLE_NC);
     s.ms_edges = ms(EV_TABLE_NC, EV_EDGES); s.ms_mark = ms(EV_EDGES, EV_MARK); s.ms_emit = ms(EV_MARK, EV_EMIT);
     s.ms_total = ms(EV_T0, EV_EMIT);
+    s.ms_edges_kernel = ms(EV_EDGES_K0, EV_EDGES_K1); s.ms_contained_kernel = ms(EV_CONT_K0, EV_CONT_K1);
     *out = s;
     return DISCO_OK;
 }

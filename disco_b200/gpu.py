@@ -27,8 +27,9 @@ class Stats(C.Structure):
         "n_reads", "n_contained", "n_edges", "raw_directed_edges", "cap_fired", "multi_overlap_pairs", "one_sided_edges",
         "slow_path_reads", "probes_contained", "probes_edges", "buckets_contained", "buckets_edges",
         "verified_contained", "verified_edges", "max_degree", "reduce_rows_fetched", "reduce_entries_fetched",
-        "table_buckets", "edge_capacity")] + [(n, C.c_float) for n in (
-            "ms_table_all", "ms_contained", "ms_finish_contained", "ms_table_nc", "ms_edges", "ms_mark", "ms_emit", "ms_total")]
+        "table_buckets", "edge_capacity", "queries_contained", "queries_edges")] + [(n, C.c_float) for n in (
+            "ms_table_all", "ms_contained", "ms_finish_contained", "ms_table_nc", "ms_edges", "ms_mark", "ms_emit", "ms_total",
+            "ms_edges_kernel", "ms_contained_kernel")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -185,6 +186,11 @@ class GpuBuildGraph:
         out = np.zeros(nc, dtype=CROW_DTYPE)
         w = C.c_uint64()
         self._ck(self._L.disco_gpu_get_contained(self._h, out.ctypes.data, nc, C.byref(w)), "get_contained")
+        return out[:w.value]
+
+    def contained_into(self, out: np.ndarray) -> np.ndarray:
+        w = C.c_uint64()
+        self._ck(self._L.disco_gpu_get_contained(self._h, out.ctypes.data, len(out), C.byref(w)), "get_contained")
         return out[:w.value]
 
     def edges(self, out: np.ndarray = None) -> np.ndarray:

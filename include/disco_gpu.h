@@ -67,8 +67,10 @@ typedef struct {
     uint64_t reduce_entries_fetched;              /* adjacency entries read by the two reduction kernels */
     uint64_t table_buckets;                       /* size of the hash table in 32-byte buckets */
     uint64_t edge_capacity;                       /* adjacency entries allocated */
+    uint64_t queries_contained, queries_edges;    /* reads searched by this context's launches */
     /* device time of the last disco_gpu_build_graph(), CUDA events on the context's stream, milliseconds */
     float ms_table_all, ms_contained, ms_finish_contained, ms_table_nc, ms_edges, ms_mark, ms_emit, ms_total;
+    float ms_edges_kernel, ms_contained_kernel; /* the two search kernels alone */
 } disco_stats;
 
 /* ---- life cycle ---------------------------------------------------------------------------------------------- */
