@@ -38,8 +38,8 @@ class BuildGraph:
         try:
             g.load_reads(np.ascontiguousarray(r.packed), np.ascontiguousarray(r.lens))
             g.build_graph(self.min_overlap, self.cap)
-            res.crows = g.contained()
-            res.edges = gpu.sort_edges(g.edges())
+            res.crows = host.sort_contained(g.contained(), res.lens, self.min_overlap)
+            res.edges = host.sort_edges(g.edges())
             res.stats = g.stats()
             self._g = g
         except Exception:

@@ -343,13 +343,11 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
     if (q_lo > q_hi || q_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad query range");
     CK(cudaSetDevice(ctx->device));
     const uint64_t nq = q_hi - q_lo;
-    const int rowcap = ctx->cap * (ctx->reads.max_len - ctx->K);
     SearchParams p{};
     p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets};
     p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.contained_bits = ctx->d_bits; p.rows_cursor = ctx->d_cursors + CUR_ROWS; p.rowinfo = ctx->d_rowinfo;
-    p.rowcap = rowcap; p.hcap = search_hit_capacity(rowcap);
     // adjacency capacity: start from 48 entries per query read (30x, 150 bp, minOverlap 50 needs ~33), bounded by free
     // memory; the kernel keeps counting on overflow so that one retry with the exact size always succeeds
     if (!ctx->d_rows) {
@@ -399,7 +397,7 @@ int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
     p.reads = ctx->reads; p.rows = ctx->d_rows; p.rowinfo = ctx->d_rowinfo; p.u_lo = u_lo; p.u_hi = u_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.maxdeg = (int)std::max<uint64_t>(ctx->stats.max_degree, 1);
-    if ((size_t)p.maxdeg * 5 + 16 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
+    if ((size_t)p.maxdeg * 9 + 16 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
     CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
     if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_mark(p, ctx->num_sms, ctx->stream));
     int rc = record(ctx, EV_MARK);
@@ -460,22 +458,7 @@ int disco_gpu_get_contained(disco_ctx *ctx, disco_crow *rows, uint64_t capacity,
     const uint64_t n = ctx->n_contained;
     if (n) {
         CK(cudaMemcpyAsync(rows, ctx->d_crows, n * sizeof(disco_crow), cudaMemcpyDeviceToHost, ctx->stream));
-        std::vector<uint16_t> len;
-        if (!ctx->reads.uniform_len) {
-            len.resize(ctx->reads.n);
-            CK(cudaMemcpyAsync(len.data(), ctx->d_len, ctx->reads.n * sizeof(uint16_t), cudaMemcpyDeviceToHost, ctx->stream));
-        }
         CK(cudaStreamSynchronize(ctx->stream));
-        // reference emission order at -t 1: container ascending, then k-mer position, then record (prefix before suffix)
-        const int K = ctx->K, UL = ctx->reads.uniform_len;
-        auto key = [&](const disco_crow &r) {
-            const int L1 = UL ? UL : len[r.container];
-            // orient 3/2 <- types 0/2: start = j ; orient 0/1 <- types 1/3: start = L1 - K - j   (OverlapGraph.cpp:428-434)
-            const int j = (r.orient == 3 || r.orient == 2) ? (int)r.start : L1 - K - (int)r.start;
-            const int kind = (r.orient == 3 || r.orient == 1) ? 0 : 1;
-            return std::make_tuple(r.container, j, 2ULL * r.contained + kind);
-        };
-        std::sort(rows, rows + n, [&](const disco_crow &a, const disco_crow &b) { return key(a) < key(b); });
     }
     if (n_written) *n_written = n;
     return DISCO_OK;
@@ -509,6 +492,8 @@ int disco_gpu_get_row(disco_ctx *ctx, uint64_t read, disco_edge *out, uint64_t c
         CK(cudaMemcpyAsync(e.data(), ctx->d_rows + rowinfo_start(ri), deg * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
+    for (auto &x : e) x &= ~kElimBit;
+    std::sort(e.begin(), e.end()); // device rows are unsorted; (offset, neighbour, orientation) is the reference's list order
     for (uint32_t i = 0; i < deg; i++) {
         out[i].src = (uint32_t)read; out[i].dst = (uint32_t)entry_nbr(e[i]);
         out[i].offset = (uint32_t)entry_offset(e[i]); out[i].orient = (uint32_t)entry_orient(e[i]);

@@ -95,10 +95,11 @@ DHD uint64_t canon_kmer_hash(const uint64_t *A, const uint64_t *R, int L, int j,
     const uint64_t *S = fwd ? A : R;
     const int s = fwd ? j : jr;
     uint64_t h = 0x9E3779B97F4A7C15ULL ^ (uint64_t)K;
-    for (int i = 0; i < KW; i++) {
+    for (int i = 0; i < KW; i++) { // one multiply per word, full avalanche once at the end
         uint64_t x = fetch64(S, s + 32 * i);
         if (i == KW - 1) x &= tmask;
-        h = mix64(h ^ x) + 0x632BE59BD9B4E019ULL;
+        h = (h ^ x) * 0xD6E8FEB86659FD93ULL;
+        h ^= h >> 32;
     }
     *fwd_is_canon = fwd;
     return mix64(h);
@@ -148,35 +149,60 @@ struct LoaderMatcher {
     DHD bool operator()(const uint64_t *P, int a, int b, int n) const { return match_window(P, a, s2, b, n); }
 };
 
-// checkOverlap (OverlapGraph.cpp:567-595): dovetail test of query read (A fwd / R rc, length L1) at k-mer position j
-// against candidate s2 (length L2).  The whole overlap -- k-mer included -- is compared, so a fingerprint collision
-// can never produce an edge.
-template <typename Matcher>
-DHD bool check_dovetail(const uint64_t *A, const uint64_t *R, int L1, int j, int K, int type, int L2, const Matcher &m)
+// Window to compare for a candidate: bases [a, a+n) of the query (reverse-complement array when *use_rc) against bases
+// [b, b+n) of the candidate's forward strand.  Returns false when the geometry already rules the candidate out.
+// One parameter set + ONE matcher call keeps a warp converged whatever mix of types its lanes hold.
+//
+// checkOverlap (OverlapGraph.cpp:567-595): dovetail test of the query read (length L1) at k-mer position j against a
+// candidate of length L2.  The whole overlap -- k-mer included -- is compared, so a fingerprint collision can never
+// produce an edge.
+DHD bool dovetail_window(int type, int L1, int j, int K, int L2, int *use_rc, int *a, int *b, int *n)
 {
     if (type == 0 || type == 2) {
         if (L1 - j >= L2) return false; // the overlap must run to the end of read1 and stop inside read2
-        int ov = L1 - j;
-        return type == 0 ? m(A, j, 0, ov)        // s1[j..L1) == s2[0..ov)
-                         : m(R, 0, L2 - ov, ov); // rc(s1)[0..ov) == s2[L2-ov..L2)
+        const int ov = L1 - j;
+        *n = ov;
+        if (type == 0) { *use_rc = 0; *a = j; *b = 0; }      // s1[j..L1) == s2[0..ov)
+        else { *use_rc = 1; *a = 0; *b = L2 - ov; }          // rc(s1)[0..ov) == s2[L2-ov..L2)
+        return true;
     }
     if (L2 - K < j) return false;
-    int ov = K + j;
-    return type == 1 ? m(A, 0, L2 - ov, ov)  // s1[0..ov) == s2[L2-ov..L2)
-                     : m(R, L1 - ov, 0, ov); // rc(s1)[L1-ov..L1) == s2[0..ov)
+    const int ov = K + j;
+    *n = ov;
+    if (type == 1) { *use_rc = 0; *a = 0; *b = L2 - ov; }    // s1[0..ov) == s2[L2-ov..L2)
+    else { *use_rc = 1; *a = L1 - ov; *b = 0; }              // rc(s1)[L1-ov..L1) == s2[0..ov)
+    return true;
 }
 
 // checkOverlapForContainedRead (OverlapGraph.cpp:517-554): is the whole of s2 (or its reverse complement) inside s1,
 // anchored by the k-mer hit at position j?
+DHD bool contained_window(int type, int L1, int j, int K, int L2, int *use_rc, int *a, int *b, int *n)
+{
+    *b = 0; *n = L2;
+    if (type == 0 || type == 2) {
+        if (j + L2 > L1) return false;
+        if (type == 0) { *use_rc = 0; *a = j; } else { *use_rc = 1; *a = L1 - j - L2; }
+        return true;
+    }
+    if (j < L2 - K) return false;
+    if (type == 1) { *use_rc = 0; *a = j - (L2 - K); } else { *use_rc = 1; *a = L1 - j - K; }
+    return true;
+}
+
+template <typename Matcher>
+DHD bool check_dovetail(const uint64_t *A, const uint64_t *R, int L1, int j, int K, int type, int L2, const Matcher &m)
+{
+    int use_rc, a, b, n;
+    if (!dovetail_window(type, L1, j, K, L2, &use_rc, &a, &b, &n)) return false;
+    return m(use_rc ? R : A, a, b, n);
+}
+
 template <typename Matcher>
 DHD bool check_contained(const uint64_t *A, const uint64_t *R, int L1, int j, int K, int type, int L2, const Matcher &m)
 {
-    if (type == 0 || type == 2) {
-        if (j + L2 > L1) return false;
-        return type == 0 ? m(A, j, 0, L2) : m(R, L1 - j - L2, 0, L2);
-    }
-    if (j < L2 - K) return false;
-    return type == 1 ? m(A, j - (L2 - K), 0, L2) : m(R, L1 - j - K, 0, L2);
+    int use_rc, a, b, n;
+    if (!contained_window(type, L1, j, K, L2, &use_rc, &a, &b, &n)) return false;
+    return m(use_rc ? R : A, a, b, n);
 }
 
 // --- hash table slot / CSR entry / key encodings ---------------------------------------------------------------------

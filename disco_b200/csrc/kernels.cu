@@ -22,7 +22,8 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kChunk = 8;      // reads per work-counter grab
 constexpr int kScanLimit = 6;  // buckets a lane may walk on the fast path before the read is deferred to the slow path
 constexpr int kRowBlock = 1024; // adjacency entries a warp reserves per global atomic
-constexpr int kHitCap = 192;    // fast-path hit buffer entries per warp
+constexpr int kHitCap = 128;    // fast-path candidate queue entries per warp (edge pass)
+constexpr int kContainQueue = 64; // candidate queue entries per warp (containment pass, drained every 32 positions)
 constexpr int kBestMax = 16;   // slow path: smallest-record candidates kept per position (>= 2 * cap)
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -158,6 +159,8 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
 // ---------------------------------------------------------------------------------------------------------------
 enum { MODE_CONTAIN = 0, MODE_EDGES = 1 };
 
+__host__ __device__ inline size_t reduce_mark_smem_per_warp(int maxdeg) { return (((size_t)maxdeg * 9 + 15) / 16) * 16; }
+
 // hit record of the edge pass: [55..40 j][39..8 rec][1..0 type]  -> sorts by (j, rec) = the reference's visiting order
 __device__ __forceinline__ uint64_t make_hit(int j, uint32_t rec, int type) { return ((uint64_t)j << 40) | ((uint64_t)rec << 8) | (uint64_t)type; }
 __device__ __forceinline__ int hit_j(uint64_t h) { return (int)(h >> 40); }
@@ -259,6 +262,31 @@ __device__ void search_edges_slow(const SearchParams &p, const WarpSmem &s, uint
     }
 }
 
+// containment test of one queued candidate + the atomicMin that elects the container (OverlapGraph.cpp:421-449)
+template <int NW>
+__device__ __forceinline__ bool contain_one(const SearchParams &p, const WarpSmem &s, uint64_t r1, int L1, uint64_t c)
+{
+    const uint32_t r2 = hit_read(c);
+    const int L2 = read_len(p.reads, r2);
+    // read1 must be longer, or equal and earlier in the file (OverlapGraph.cpp:424, :449)
+    if (!(L1 > L2 || (L1 == L2 && r1 < r2))) return false;
+    RegMatcher<NW> m;
+    if (NW == 0) reinterpret_cast<RegMatcher<0> &>(m).stride = p.reads.stride;
+    m.load(p.reads.words, r2);
+    const int j = hit_j(c), type = hit_type(c);
+    if (!check_contained(s.A, s.R, L1, j, p.K, type, L2, m)) return false;
+    atomicMin(p.best + r2, (unsigned long long)make_ckey(r1, j, (int)((c >> 8) & 1), type));
+    return true;
+}
+
+// Search kernel, both passes.  Per read (one warp):
+//   1. probe   : one lane per k-mer position; canonical fingerprint, one 32-byte bucket load, tag compare; every
+//                tag match is queued in shared memory as (position, record, type)
+//   2. verify  : one lane per queued candidate (lanes fully packed whatever the hit pattern was): 128-bit loads of the
+//                candidate read, one windowed 2-bit compare against the staged query (forward or reverse complement)
+//   3. resolve : (edge pass) first hit per neighbour wins (OverlapGraph.cpp:656) -- checked with a shared-memory
+//                set of neighbour ids; positions with more than `cap` partners send the read to the exact
+//                sequential path; survivors are compacted by ballot and appended to the adjacency
 template <int NW, int MODE>
 __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
 {
@@ -266,12 +294,18 @@ __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int WP = ((p.reads.max_len + 31) >> 5) + 2;
     const int K = p.K;
-    // per-warp shared memory carve-up (u64 units)
-    const size_t per_warp = (MODE == MODE_EDGES) ? (size_t)(2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (size_t)(2 * WP);
+    // per-warp shared memory carve-up (u64 units); must match search_smem_per_warp()
+    const size_t per_warp = (MODE == MODE_EDGES) ? (size_t)(2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (size_t)(2 * WP + p.hcap + 2);
     WarpSmem s;
     s.A = smem + wib * per_warp; s.R = s.A + WP;
-    s.hits = s.R + WP; s.row = s.hits + p.hcap; s.best = s.row + p.rowcap;
-    s.ctrl = reinterpret_cast<int *>(s.best + kBestMax);
+    s.hits = s.R + WP;
+    if (MODE == MODE_EDGES) { s.row = s.hits + p.hcap; s.best = s.row + p.rowcap; s.ctrl = reinterpret_cast<int *>(s.best + kBestMax); }
+    else { s.row = nullptr; s.best = nullptr; s.ctrl = reinterpret_cast<int *>(s.hits + p.hcap); }
+    // fast-path scratch inside the (otherwise idle) row buffer: neighbour-id set + per-position counters
+    uint32_t *hset = (MODE == MODE_EDGES) ? reinterpret_cast<uint32_t *>(s.row) : nullptr;
+    int *cntj = (MODE == MODE_EDGES) ? reinterpret_cast<int *>(s.row) + p.hset : nullptr;
+    const uint32_t hset_mask = (uint32_t)p.hset - 1;
+    const unsigned lt_mask = (1u << lane) - 1;
 
     unsigned long long n_queries = 0, n_probes = 0, n_buckets = 0, n_verified = 0, n_hits = 0, n_entries = 0,
                        n_capfired = 0, n_slow = 0, maxdeg = 0;
@@ -283,14 +317,13 @@ __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
             const int L1 = read_len(p.reads, r1);
             stage_read(p.reads, r1, L1, s.A, s.R, WP, lane);
             n_queries += (lane == 0);
-            if (MODE == MODE_EDGES) {
-                if (lane < 4) s.ctrl[lane] = 0;
-                __syncwarp();
-            }
+            if (lane < 4) s.ctrl[lane] = 0; // [0] queued, [1] needs exact path, [2] row length, [3] some position has > cap candidates
+            __syncwarp();
             // containment: positions [0, L1-K) (OverlapGraph.cpp:401), pruned to those where some read can fit:
             //   types 0/2 need j + L2 <= L1, types 1/3 need j >= L2 - K, and L2 >= min_len.
             // edges: positions [1, L1-K) (OverlapGraph.cpp:638)
             const int jlo = (MODE == MODE_EDGES) ? 1 : 0, jhi = L1 - K;
+            // ---- 1. probe ------------------------------------------------------------------------------------
             for (int jb = jlo; jb < jhi; jb += 32) {
                 const int j = jb + lane;
                 bool act = j < jhi;
@@ -300,9 +333,10 @@ __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
                     const uint64_t h = canon_kmer_hash(s.A, s.R, L1, j, K, &fq);
                     const uint32_t tag = slot_tag(h);
                     uint64_t b = bucket_of(h, p.table.nbuckets);
+                    int pushed = 0;
                     n_probes++;
                     for (int walked = 0;; walked++) {
-                        if (MODE == MODE_EDGES && walked == kScanLimit) { s.ctrl[1] = 1; break; } // long chain: slow path
+                        if (MODE == MODE_EDGES && walked == kScanLimit) { s.ctrl[1] = 1; break; } // long chain: exact path
                         uint64_t v[4];
                         load_bucket(p.table.slots, b, v);
                         n_buckets++;
@@ -311,68 +345,91 @@ __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
                         for (int q = 0; q < 4; q++) {
                             if (v[q] == kEmptySlot) { hole = true; continue; }
                             if ((uint32_t)(v[q] >> 33) != tag) continue;
-                            const uint32_t rec = (uint32_t)v[q], r2 = rec >> 1;
-                            if (r2 == (uint32_t)r1) continue; // OverlapGraph.cpp:421 / :655
-                            const int type = cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq);
-                            if (MODE == MODE_EDGES) {
-                                n_verified++;
-                                if (verify_dovetail<NW>(p, s, L1, j, type, r2)) {
-                                    const int pos = atomicAdd(&s.ctrl[0], 1);
-                                    if (pos < p.hcap) s.hits[pos] = make_hit(j, rec, type);
-                                }
-                            } else {
-                                const int L2 = read_len(p.reads, r2);
-                                // read1 must be longer, or equal and earlier in the file (OverlapGraph.cpp:424, :449)
-                                if (!(L1 > L2 || (L1 == L2 && r1 < r2))) continue;
-                                RegMatcher<NW> m;
-                                if (NW == 0) reinterpret_cast<RegMatcher<0> &>(m).stride = p.reads.stride;
-                                m.load(p.reads.words, r2);
-                                n_verified++;
-                                if (check_contained(s.A, s.R, L1, j, K, type, L2, m)) {
-                                    n_hits++;
-                                    atomicMin(p.best + r2, (unsigned long long)make_ckey(r1, j, rec & 1, type));
-                                }
-                            }
+                            const uint32_t rec = (uint32_t)v[q];
+                            if ((rec >> 1) == (uint32_t)r1) continue; // OverlapGraph.cpp:421 / :655
+                            const uint64_t c = make_hit(j, rec, cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq));
+                            const int pos = atomicAdd(&s.ctrl[0], 1);
+                            if (pos < p.hcap) s.hits[pos] = c;
+                            else if (MODE == MODE_CONTAIN) { n_verified++; n_hits += contain_one<NW>(p, s, r1, L1, c); } // queue full (rare)
+                            pushed++;
                         }
                         if (hole) break;
                         b = (b + 1 == p.table.nbuckets) ? 0 : b + 1;
                     }
+                    if (MODE == MODE_EDGES && pushed > p.cap) s.ctrl[3] = 1;
                 }
                 __syncwarp();
+                if (MODE == MODE_CONTAIN) { // ---- 2. verify, drained after every batch (this pass has no exact path)
+                    const int nc = min(s.ctrl[0], p.hcap);
+                    for (int i = lane; i < nc; i += 32) { n_verified++; n_hits += contain_one<NW>(p, s, r1, L1, s.hits[i]); }
+                    __syncwarp();
+                    if (lane == 0) s.ctrl[0] = 0;
+                    __syncwarp();
+                }
             }
             if (MODE != MODE_EDGES) continue;
 
-            // ---- resolve the hits of this read into its adjacency row ------------------------------------------
-            const int n = s.ctrl[0];
-            bool slow = s.ctrl[1] != 0 || n > p.hcap;
+            const int nc = s.ctrl[0];
+            bool slow = s.ctrl[1] != 0 || nc > p.hcap;
             int nrow = 0;
             if (!slow) {
-                bool over = false;
-                for (int i0 = 0; i0 < n; i0 += 32) {
+                // ---- 2. verify: lane per candidate ------------------------------------------------------------
+                const bool count_pos = s.ctrl[3] != 0; // only reads with a crowded position pay for per-position counts
+                for (int k = lane; k < p.hset; k += 32) hset[k] = 0xFFFFFFFFu;
+                if (count_pos) for (int k = lane; k < jhi; k += 32) cntj[k] = 0;
+                __syncwarp();
+                bool dup = false, over = false;
+                for (int i0 = 0; i0 < nc; i0 += 32) {
                     const int i = i0 + lane;
-                    const bool have = i < n;
-                    const uint64_t hk = have ? s.hits[i] : 0ULL;
-                    const uint32_t r2 = hit_read(hk);
-                    const int j = hit_j(hk);
-                    bool keep = have;
-                    int cnt = 0;
-                    for (int k = 0; k < n; k++) {
-                        const uint64_t o = s.hits[k];
-                        if (hit_read(o) == r2 && o < hk) keep = false; // an earlier (j, record) already paired r2 (:656)
-                        cnt += hit_j(o) == j;
-                    }
-                    over |= have && cnt > p.cap;
-                    if (keep) {
-                        int orient, ovl;
-                        type_to_edge(hit_type(hk), L1, K, j, &orient, &ovl);
-                        const int pos = atomicAdd(&s.ctrl[2], 1);
-                        s.row[pos] = make_entry(L1 - ovl, r2, orient); // pos < n <= hcap <= rowcap
+                    if (i < nc) {
+                        const uint64_t c = s.hits[i];
+                        const uint32_t r2 = hit_read(c);
+                        const bool ok = verify_dovetail<NW>(p, s, L1, hit_j(c), hit_type(c), r2);
+                        if (ok) {
+                            // ---- 3a. first hit per neighbour: insert r2 into the warp's id set
+                            uint32_t hh = (r2 * 0x9E3779B1u) & hset_mask;
+                            for (;;) {
+                                const uint32_t old = atomicCAS(&hset[hh], 0xFFFFFFFFu, r2);
+                                if (old == 0xFFFFFFFFu) break;
+                                if (old == r2) { dup = true; break; }
+                                hh = (hh + 1) & hset_mask;
+                            }
+                            if (count_pos) over |= atomicAdd(&cntj[hit_j(c)], 1) >= p.cap;
+                        } else {
+                            s.hits[i] = ~0ULL;
+                        }
                     }
                 }
+                n_verified += (lane == 0) ? (unsigned long long)nc : 0ULL;
                 slow = __any_sync(FULL, over); // a position with more than cap partners: redo exactly
+                dup = __any_sync(FULL, dup);
                 __syncwarp();
-                nrow = s.ctrl[2];
-                n_hits += (lane == 0) ? (unsigned long long)n : 0ULL;
+                if (!slow && dup) {
+                    // rare (tandem repeats, circular overlaps): a neighbour reached through two positions keeps the
+                    // first one in (position, record) order (OverlapGraph.cpp:656)
+                    unsigned drop = 0;
+                    for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++) {
+                        const int i = i0 + lane;
+                        const uint64_t hk = (i < nc) ? s.hits[i] : ~0ULL;
+                        if (hk == ~0ULL) continue;
+                        const uint32_t r2 = hit_read(hk);
+                        for (int k = 0; k < nc; k++) {
+                            const uint64_t o = s.hits[k];
+                            if (o != ~0ULL && hit_read(o) == r2 && o < hk) { drop |= 1u << rd; break; }
+                        }
+                    }
+                    __syncwarp();
+                    for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++)
+                        if ((drop >> rd) & 1) s.hits[i0 + lane] = ~0ULL;
+                    __syncwarp();
+                }
+                if (!slow) {
+                    for (int i0 = 0; i0 < nc; i0 += 32) {
+                        const int i = i0 + lane;
+                        nrow += __popc(__ballot_sync(FULL, i < nc && s.hits[i] != ~0ULL));
+                    }
+                    n_hits += (lane == 0) ? (unsigned long long)nrow : 0ULL;
+                }
             }
             if (slow) {
                 n_slow += (lane == 0);
@@ -381,9 +438,10 @@ __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
                 if (nrow > p.rowcap) nrow = p.rowcap; // cannot happen: rowcap >= cap * positions
             }
             if (nrow == 0) continue;
-            // ---- sort by (offset, neighbour, orientation) and append to the global adjacency -------------------
-            // space comes from a warp-private slice reserved kRowBlock entries at a time: one global atomic per ~30
-            // reads instead of one per read (rows need not be contiguous in read order; rowinfo points at them)
+            // ---- 3b. append the row to the global adjacency.  Space comes from a warp-private slice reserved
+            // kRowBlock entries at a time: one global atomic per ~30 reads instead of one per read (rows need not be
+            // contiguous in read order; rowinfo points at them).  Rows are stored unsorted: the reduction picks
+            // neighbours in offset order itself.
             if (blk_cur + nrow > blk_end) {
                 const unsigned long long want = nrow > kRowBlock ? (unsigned long long)nrow : (unsigned long long)kRowBlock;
                 if (lane == 0) blk_cur = atomicAdd(p.rows_cursor, want);
@@ -395,11 +453,22 @@ __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
             n_entries += (lane == 0) ? (unsigned long long)nrow : 0ULL;
             if ((unsigned long long)nrow > maxdeg) maxdeg = nrow;
             if (base + nrow <= p.rows_cap) {
-                for (int i = lane; i < nrow; i += 32) {
-                    const uint64_t e = s.row[i];
-                    int rank = 0;
-                    for (int k = 0; k < nrow; k++) rank += s.row[k] < e;
-                    p.rows[base + rank] = e;
+                if (slow) {
+                    for (int i = lane; i < nrow; i += 32) p.rows[base + i] = s.row[i];
+                } else {
+                    int off = 0;
+                    for (int i0 = 0; i0 < nc; i0 += 32) {
+                        const int i = i0 + lane;
+                        const uint64_t hk = (i < nc) ? s.hits[i] : ~0ULL;
+                        const bool valid = hk != ~0ULL;
+                        const unsigned m = __ballot_sync(FULL, valid);
+                        if (valid) {
+                            int orient, ovl;
+                            type_to_edge(hit_type(hk), L1, K, hit_j(hk), &orient, &ovl);
+                            p.rows[base + off + __popc(m & lt_mask)] = make_entry(L1 - ovl, hit_read(hk), orient);
+                        }
+                        off += __popc(m);
+                    }
                 }
                 if (lane == 0) p.rowinfo[r1] = make_rowinfo(base, (uint32_t)nrow);
             } else if (lane == 0) {
@@ -477,11 +546,12 @@ __global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
 {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    // per warp: ids u32[maxdeg], st u8[maxdeg]  (st: bits 0-1 orientation, bit 2 eliminated)
-    const size_t per_warp = (((size_t)p.maxdeg * 5 + 15) / 16) * 16;
+    // per warp: ent u64[maxdeg] (the row; the entry value is also the (offset, id, orientation) sort key),
+    //           st u8[maxdeg]   (bit 0 visited, bit 1 eliminated; 0 = INPLAY and not yet visited)
+    const size_t per_warp = reduce_mark_smem_per_warp(p.maxdeg);
     uint8_t *basep = reinterpret_cast<uint8_t *>(smem) + wib * per_warp;
-    uint32_t *ids = reinterpret_cast<uint32_t *>(basep);
-    volatile uint8_t *st = basep + (size_t)p.maxdeg * 4;
+    uint64_t *ent = reinterpret_cast<uint64_t *>(basep);
+    volatile uint8_t *st = basep + (size_t)p.maxdeg * 8;
     unsigned long long n_rows = 0, n_ent = 0;
     uint64_t ub, ue;
     while (grab_chunk(p.work_counter, p.u_lo, p.u_hi, lane, &ub, &ue)) {
@@ -491,37 +561,51 @@ __global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
             if (deg == 0) continue;
             const uint64_t start = rowinfo_start(ri);
             for (int k = lane; k < deg; k += 32) {
-                const uint64_t e = p.rows[start + k];
-                ids[k] = (uint32_t)entry_nbr(e);
-                st[k] = (uint8_t)entry_orient(e);
+                ent[k] = __ldcg(p.rows + start + k) & ~kElimBit;
+                st[k] = 0;
             }
             __syncwarp();
-            for (int i = 0; i < deg; i++) {
-                const uint8_t si = st[i];
-                if (si & 4) continue; // ELIMINATED neighbours do not eliminate (OverlapGraph.cpp:696)
-                const int t1 = si & 3;
-                const uint64_t vri = p.rowinfo[ids[i]];
+            for (;;) {
+                // "traverse the list of edges according to their overlap offset" (OverlapGraph.cpp:693): rows are
+                // stored unsorted, so pick the smallest (offset, id, orientation) entry that is still INPLAY and
+                // unvisited -- a warp arg-min per visited neighbour (only a handful per node) instead of a sort
+                uint64_t best = ~0ULL;
+                int bk = -1;
+                for (int k = lane; k < deg; k += 32) {
+                    const uint64_t e = ent[k];
+                    if (st[k] == 0 && e < best) { best = e; bk = k; }
+                }
+                for (int o = 16; o; o >>= 1) {
+                    const uint64_t ob = __shfl_xor_sync(FULL, best, o);
+                    const int ok = __shfl_xor_sync(FULL, bk, o);
+                    if (ob < best) { best = ob; bk = ok; }
+                }
+                if (best == ~0ULL) break;
+                if (lane == 0) st[bk] = 1;
+                const int t1 = entry_orient(best);
+                const uint64_t vri = p.rowinfo[entry_nbr(best)];
                 const int vd = (int)rowinfo_deg(vri);
                 const uint64_t vs = rowinfo_start(vri);
                 n_rows += (lane == 0); n_ent += (lane == 0) ? (unsigned long long)vd : 0ULL;
+                __syncwarp();
                 for (int q0 = 0; q0 < vd; q0 += 32) {
                     const int q = q0 + lane;
                     bool go = false;
                     uint32_t w = 0;
                     if (q < vd) {
-                        const uint64_t e = __ldcg(p.rows + vs + q); // other warps may be setting eliminated bits: ignore them
+                        const uint64_t e = __ldcg(p.rows + vs + q); // other warps may be setting eliminated bits: ignored
                         w = (uint32_t)entry_nbr(e);
                         go = chain_ok(t1, entry_orient(e));
                     }
                     if (__any_sync(FULL, go)) {
                         for (int k = 0; k < deg; k++)
-                            if (go && ids[k] == w) st[k] = st[k] | 4; // only this lane can hold w == ids[k]
+                            if (go && (uint32_t)entry_nbr(ent[k]) == w) st[k] = st[k] | 2; // at most one lane holds this w
                     }
                 }
                 __syncwarp();
             }
             for (int k = lane; k < deg; k += 32)
-                if (st[k] & 4) p.rows[start + k] |= kElimBit;
+                if (st[k] & 2) p.rows[start + k] = ent[k] | kElimBit;
             __syncwarp();
         }
     }
@@ -672,26 +756,44 @@ cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, c
     return cudaGetLastError();
 }
 
+static int pow2_at_least(int x) { int v = 1; while (v < x) v <<= 1; return v; }
+
+// fills hcap / hset / rowcap for a launch: rowcap is the worst-case row (cap entries per position) and is also
+// large enough to hold the fast path's scratch (id set of hset u32 + one int counter per position)
+static void size_search(SearchParams &p, int mode)
+{
+    const int positions = p.reads.max_len - p.K;
+    if (mode == MODE_EDGES) {
+        const int worst = p.cap * positions;
+        p.hcap = worst < kHitCap ? worst : kHitCap;
+        p.hset = pow2_at_least(2 * p.hcap);
+        const int scratch = (p.hset + positions + 2 + 1) / 2; // u64 units
+        p.rowcap = worst > scratch ? worst : scratch;
+    } else {
+        p.hcap = kContainQueue; p.hset = 0; p.rowcap = 0;
+    }
+}
+
 static size_t search_smem_per_warp(const SearchParams &p, int mode)
 {
     const size_t WP = wp_of(p.reads.max_len);
-    const size_t per_warp = (mode == MODE_EDGES) ? (2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (2 * WP);
+    const size_t per_warp = (mode == MODE_EDGES) ? (2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (2 * WP + p.hcap + 2);
     return per_warp * sizeof(uint64_t);
 }
 
 bool search_edges_fits(int max_len, int K, int cap)
 {
     SearchParams p{};
-    p.reads.max_len = max_len;
-    p.rowcap = cap * (max_len - K);
-    p.hcap = p.rowcap < kHitCap ? p.rowcap : kHitCap;
+    p.reads.max_len = max_len; p.K = K; p.cap = cap;
+    size_search(p, MODE_EDGES);
     return warps_that_fit(search_smem_per_warp(p, MODE_EDGES)) > 0;
 }
-int search_hit_capacity(int rowcap) { return rowcap < kHitCap ? rowcap : kHitCap; }
 
 template <int MODE>
-static cudaError_t launch_search(const SearchParams &p, int num_sms, cudaStream_t s)
+static cudaError_t launch_search(const SearchParams &p_in, int num_sms, cudaStream_t s)
 {
+    SearchParams p = p_in;
+    size_search(p, MODE);
     const size_t per_warp = search_smem_per_warp(p, MODE);
     const int warps = warps_that_fit(per_warp);
     if (!warps) return cudaErrorInvalidConfiguration;
@@ -750,7 +852,7 @@ cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_h
 
 cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t s)
 {
-    const size_t per_warp = (((size_t)p.maxdeg * 5 + 15) / 16) * 16;
+    const size_t per_warp = reduce_mark_smem_per_warp(p.maxdeg);
     const int warps = warps_that_fit(per_warp);
     if (!warps) return cudaErrorInvalidConfiguration;
     const size_t smem = per_warp * warps;

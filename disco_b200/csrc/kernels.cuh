@@ -55,8 +55,10 @@ struct SearchParams {
     uint64_t rows_cap;
     unsigned long long *rows_cursor;
     uint64_t *rowinfo;
-    int hcap;    // fast-path hit buffer entries per warp
-    int rowcap;  // row buffer entries per warp  (>= cap * (max_len - K - 1))
+    // shared-memory shape, filled in by the launcher
+    int hcap;    // candidate queue entries per warp
+    int hset;    // neighbour-id set slots (u32, power of two)
+    int rowcap;  // row buffer entries per warp (>= cap * (max_len - K), also holds the fast path's scratch)
 };
 
 struct ReduceParams {
@@ -87,6 +89,5 @@ cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t 
 cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s);
 // smem bytes a search / reduce block needs for the given shape (0 = does not fit)
 bool search_edges_fits(int max_len, int K, int cap);
-int search_hit_capacity(int rowcap);
 
 } // namespace disco

@@ -10,7 +10,7 @@ EXPORTS = ["disco_host_last_error", "disco_host_test_read", "disco_reads_new", "
            "disco_reads_add_records", "disco_reads_finalize", "disco_reads_count", "disco_reads_records",
            "disco_reads_words_per_read", "disco_reads_packed", "disco_reads_len", "disco_reads_file_index",
            "disco_reads_min_len", "disco_reads_max_len", "disco_host_pack_codes", "disco_write_pargraph",
-           "disco_write_contained"]
+           "disco_write_contained", "disco_host_sort_contained", "disco_host_sort_edges"]
 
 _lib = None
 
@@ -47,6 +47,8 @@ def lib():
         L.disco_host_pack_codes.argtypes = [vp, vp, u64, u32, vp, vp, i32]
         L.disco_write_pargraph.argtypes = [C.c_char_p, vp, u64, vp, vp, i32, i32]
         L.disco_write_contained.argtypes = [C.c_char_p, vp, u64, vp, vp, i32]
+        L.disco_host_sort_contained.argtypes = [vp, u64, vp, u32]
+        L.disco_host_sort_edges.argtypes = [vp, u64]
         _lib = L
     return _lib
 
@@ -151,3 +153,17 @@ def write_contained(path, rows, file_index, lens, append=False):
     fi = np.ascontiguousarray(file_index, dtype=np.uint64)
     ln = np.ascontiguousarray(lens, dtype=np.uint16)
     _ck(lib().disco_write_contained(path.encode(), rows.ctypes.data, len(rows), fi.ctypes.data, ln.ctypes.data, int(append)))
+
+
+def sort_contained(rows: np.ndarray, lens: np.ndarray, min_overlap: int) -> np.ndarray:
+    """In place: the reference's -t 1 emission order (container, position, record)."""
+    rows = np.ascontiguousarray(rows)
+    ln = np.ascontiguousarray(lens, dtype=np.uint16)
+    _ck(lib().disco_host_sort_contained(rows.ctypes.data, len(rows), ln.ctypes.data, min_overlap))
+    return rows
+
+
+def sort_edges(edges: np.ndarray) -> np.ndarray:
+    edges = np.ascontiguousarray(edges)
+    _ck(lib().disco_host_sort_edges(edges.ctypes.data, len(edges)))
+    return edges

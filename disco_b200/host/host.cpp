@@ -245,6 +245,42 @@ int disco_host_pack_codes(const uint8_t *codes, const uint64_t *off, uint64_t n,
     return bad ? fail("read too long for words_per_read") : 0;
 }
 
+int disco_host_sort_contained(disco_crow *rows, uint64_t n, const uint16_t *len, uint32_t min_overlap)
+{
+    const int K = (int)min_overlap - 1;
+    std::vector<std::pair<uint64_t, uint64_t>> keys(n); // (container, position | record) , index
+    std::vector<uint64_t> k2(n);
+#pragma omp parallel for schedule(static)
+    for (uint64_t i = 0; i < n; i++) {
+        const disco_crow &r = rows[i];
+        const int L1 = len[r.container];
+        // orient 3/2 <- types 0/2: start = j ; orient 0/1 <- types 1/3: start = L1 - K - j   (OverlapGraph.cpp:428-434)
+        const uint64_t j = (r.orient == 3 || r.orient == 2) ? r.start : (uint64_t)(L1 - K - (int)r.start);
+        const uint64_t kind = (r.orient == 3 || r.orient == 1) ? 0 : 1;
+        keys[i] = {((uint64_t)r.container << 16) | j, i};
+        k2[i] = 2ULL * r.contained + kind;
+    }
+    std::sort(keys.begin(), keys.end(), [&](const std::pair<uint64_t, uint64_t> &a, const std::pair<uint64_t, uint64_t> &b) {
+        if (a.first != b.first) return a.first < b.first;
+        return k2[a.second] < k2[b.second];
+    });
+    std::vector<disco_crow> out(n);
+    for (uint64_t i = 0; i < n; i++) out[i] = rows[keys[i].second];
+    std::copy(out.begin(), out.end(), rows);
+    return 0;
+}
+
+int disco_host_sort_edges(disco_edge *edges, uint64_t n)
+{
+    std::sort(edges, edges + n, [](const disco_edge &a, const disco_edge &b) {
+        if (a.src != b.src) return a.src < b.src;
+        if (a.dst != b.dst) return a.dst < b.dst;
+        if (a.offset != b.offset) return a.offset < b.offset;
+        return a.orient < b.orient;
+    });
+    return 0;
+}
+
 int disco_write_pargraph(const char *path, const disco_edge *edges, uint64_t n, const uint64_t *file_index,
                          const uint16_t *len, int flag, int append)
 {

@@ -94,7 +94,7 @@ int disco_gpu_build_graph(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edg
 
 /* ---- results (device -> caller's host buffers) --------------------------------------------------------------- */
 int disco_gpu_counts(disco_ctx *ctx, uint64_t *n_contained, uint64_t *n_edges);
-/* rows sorted by (container, position, record) == emission order of the reference at -t 1 */
+/* rows in device order; the host library's sort helper (disco_host.h) restores the reference's -t 1 emission order */
 int disco_gpu_get_contained(disco_ctx *ctx, disco_crow *rows, uint64_t capacity, uint64_t *n_written);
 /* edges in device emission order (callers sort if they need a canonical order) */
 int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, uint64_t *n_written);

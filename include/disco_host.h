@@ -47,6 +47,13 @@ uint32_t disco_reads_max_len(const disco_reads *r);
 int disco_host_pack_codes(const uint8_t *codes, const uint64_t *off, uint64_t n, uint32_t words_per_read,
                           uint64_t *out, uint16_t *len_out, int threads);
 
+/* Sort contained rows into the reference's emission order at -t 1: container ascending, then k-mer position, then
+ * record (prefix before suffix) -- rows of one container end up consecutive, which SimplifyGraph expects
+ * (SimplifyGraph/src/DataSet.cpp:316-335).  min_overlap as given to the GPU run. */
+int disco_host_sort_contained(disco_crow *rows, uint64_t n, const uint16_t *len, uint32_t min_overlap);
+/* Sort edges by (src, dst, offset, orient): the canonical order used when files must be reproducible. */
+int disco_host_sort_edges(disco_edge *edges, uint64_t n);
+
 /* flag = trailing mark field of every line (2 = both endpoints finalised in this file, OverlapGraph.cpp:826-833) */
 int disco_write_pargraph(const char *path, const disco_edge *edges, uint64_t n, const uint64_t *file_index,
                          const uint16_t *len, int flag, int append);
