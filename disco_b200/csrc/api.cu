@@ -151,7 +151,10 @@ int copy_reads(disco_ctx *ctx, const uint64_t *packed, const uint16_t *len, uint
     const size_t width = (size_t)std::min<int>((int)wpr, stride) * sizeof(uint64_t);
     if (width < (size_t)stride * sizeof(uint64_t))
         CK(cudaMemsetAsync(ctx->d_words, 0, n * (uint64_t)stride * sizeof(uint64_t), ctx->stream));
-    CK(cudaMemcpy2DAsync(ctx->d_words, (size_t)stride * sizeof(uint64_t), packed, (size_t)wpr * sizeof(uint64_t), width, n, kind, ctx->stream));
+    if ((int)wpr == stride) // same pitch on both sides: one flat copy (a pitched copy of 10M 48-byte rows is far slower)
+        CK(cudaMemcpyAsync(ctx->d_words, packed, n * (uint64_t)stride * sizeof(uint64_t), kind, ctx->stream));
+    else
+        CK(cudaMemcpy2DAsync(ctx->d_words, (size_t)stride * sizeof(uint64_t), packed, (size_t)wpr * sizeof(uint64_t), width, n, kind, ctx->stream));
     CK(cudaMemcpyAsync(ctx->d_len, len, n * sizeof(uint16_t), kind, ctx->stream));
     return DISCO_OK;
 }
@@ -184,6 +187,8 @@ int disco_gpu_create(disco_ctx **out, int device)
     if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(e, "cudaGetDeviceProperties");
     if (prop.major < 10) { fail(nullptr, DISCO_E_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor); delete ctx; return DISCO_E_CUDA; }
     ctx->num_sms = prop.multiProcessorCount;
+    // the path is random 32-byte sectors: do not let L2 pull in the neighbouring sectors of every miss
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(e, "cudaStreamCreate");
     ctx->own_stream = true;
     for (auto &ev : ctx->ev) if ((e = cudaEventCreate(&ev)) != cudaSuccess) return bail(e, "cudaEventCreate");
@@ -259,11 +264,18 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
     if (!search_edges_fits(ctx->reads.max_len, ctx->K, ctx->cap))
         return fail(ctx, DISCO_E_LIMIT, "max read length %d with min_overlap %u needs more shared memory per warp than one SM has", ctx->reads.max_len, min_overlap);
     const uint64_t n = ctx->reads.n;
-    // 2n records, four 8-byte slots per 32-byte bucket, load factor 1/3 (the reference sizes its table at 8n+1
-    // index words, HashTable.cpp:53)
+    // 2n records, four 8-byte slots per 32-byte bucket (the reference sizes its table at 8n+1 index words,
+    // HashTable.cpp:53)
     if (ctx->run_n != n) {
         free_run_buffers(ctx);
-        ctx->nbuckets = std::max<uint64_t>(1024, n + n / 2);
+        {   // load factor 1/6 (3n buckets) keeps ~99.5% of the look-ups to a single 32-byte sector; fall back to 1/3 when
+            // that would take more than a tenth of the free memory
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            uint64_t nb = 3 * n;
+            if (nb * 32 > free_b / 10) nb = n + n / 2;
+            ctx->nbuckets = std::max<uint64_t>(1024, nb);
+        }
         CK(cudaMalloc(&ctx->d_slots, ctx->nbuckets * 4 * sizeof(uint64_t)));
         CK(cudaMalloc(&ctx->d_best, n * sizeof(unsigned long long)));
         CK(cudaMalloc(&ctx->d_bits, ((n + 31) / 32) * sizeof(uint32_t)));
@@ -397,7 +409,7 @@ int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
     p.reads = ctx->reads; p.rows = ctx->d_rows; p.rowinfo = ctx->d_rowinfo; p.u_lo = u_lo; p.u_hi = u_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.maxdeg = (int)std::max<uint64_t>(ctx->stats.max_degree, 1);
-    if ((size_t)p.maxdeg * 9 + 16 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
+    if ((size_t)p.maxdeg * 25 + 512 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
     CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
     if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_mark(p, ctx->num_sms, ctx->stream));
     int rc = record(ctx, EV_MARK);

@@ -3,7 +3,6 @@
 // Packed layout = the reference's record payload (src/BuildGraph/src/HashTable.cpp:456-477):
 //   base i of a read lives in bits [62-2*(i%32), 63-2*(i%32)] of 64-bit word i/32 (MSB first), A=0 C=1 G=2 T=3
 //   (HashTable.h:16-22); unused tail bits are 0.
-// A "padded" array P holds a read for random base-offset access: P[0] = 0, P[1..W] = words, P[W+1] = 0.
 #pragma once
 #include <stdint.h>
 
@@ -38,15 +37,30 @@ DHD uint64_t revcomp64(uint64_t x)
     return ((y >> 1) & 0x5555555555555555ULL) | ((y & 0x5555555555555555ULL) << 1);
 }
 
-// 32 bases starting at base position p (p >= -32) of a padded array; positions outside the read give 0 bits
-// as long as the caller's array has one zero word in front and one behind.
-DHD uint64_t fetch64(const uint64_t *P, int p)
+// ---- padded read arrays --------------------------------------------------------------------------------------------
+// A padded array P holds a read for random base-offset access as 32-bit half-words in BASE ORDER (16 bases each):
+//   P[2k] = high half, P[2k+1] = low half of padded word k;  padded word 0 = 0, words 1..W = the read, word W+1 = 0.
+// 32-bit granularity lets every unaligned fetch be two single-instruction funnel shifts (SHF) instead of 64-bit
+// shift/or sequences.
+DHD uint32_t fsl32(uint32_t lo, uint32_t hi, int s) // upper 32 bits of (hi:lo) << s, 0 <= s < 32
 {
-    int q = p + 32;
-    int idx = q >> 5, sh = (q & 31) * 2;
-    uint64_t hi = P[idx];
-    if (sh == 0) return hi;
-    return (hi << sh) | (P[idx + 1] >> (64 - sh));
+#ifdef __CUDA_ARCH__
+    return __funnelshift_l(lo, hi, s);
+#else
+    return s ? (hi << s) | (lo >> (32 - s)) : hi;
+#endif
+}
+DHD uint64_t pword(const uint32_t *P, int k) { return ((uint64_t)P[2 * k] << 32) | P[2 * k + 1]; }
+DHD void pstore(uint32_t *P, int k, uint64_t w) { P[2 * k] = (uint32_t)(w >> 32); P[2 * k + 1] = (uint32_t)w; }
+DHD int padded_u32(int words) { return 2 * (words + 2); }
+
+// 32 bases starting at base position p (-32 <= p < 32*W) of a padded array; positions outside the read give 0 bits
+DHD uint64_t fetch64(const uint32_t *P, int p)
+{
+    const int q = p + 32;
+    const int i = q >> 4, s = (q & 15) * 2;
+    const uint32_t w0 = P[i], w1 = P[i + 1], w2 = P[i + 2];
+    return ((uint64_t)fsl32(w1, w0, s) << 32) | fsl32(w2, w1, s);
 }
 
 // mask selecting bases [lo, hi) of a word, 0 <= lo < hi <= 32
@@ -57,14 +71,14 @@ DHD uint64_t base_mask(int lo, int hi)
     return m;
 }
 
-// word w (0-based) of the reverse complement of a read of L bases / W words held in padded array A
-// (A[1..W] = forward words).  Z[i] = revcomp64(A[W - i]) spells [32W-L pad T's][rc(read)]; shift the pad out.
-DHD uint64_t rc_word(const uint64_t *A, int L, int W, int w)
+// word w (0-based) of the reverse complement of a read of L bases / W words held in padded array A.
+// Z[i] = revcomp64(word W-1-i) spells [32W-L pad T's][rc(read)]; shift the pad out.
+DHD uint64_t rc_word(const uint32_t *A, int L, int W, int w)
 {
     int sh = (32 * W - L) * 2;
-    uint64_t z0 = revcomp64(A[W - w]);
+    uint64_t z0 = revcomp64(pword(A, W - w));
     if (sh == 0) return z0;
-    uint64_t z1 = (w + 1 < W) ? revcomp64(A[W - w - 1]) : 0ULL;
+    uint64_t z1 = (w + 1 < W) ? revcomp64(pword(A, W - w - 1)) : 0ULL;
     return (z0 << sh) | (z1 >> (64 - sh));
 }
 
@@ -80,7 +94,7 @@ DHD uint64_t mix64(uint64_t h)
 // L = read length).  Canonical form = the smaller of the k-mer and its reverse complement in packed (lexicographic)
 // order -- the role getHashIndex()'s min() plays in the reference (HashTable.cpp:383-391).  *fwd_is_canon tells
 // which one won (ties -- reverse palindromes -- count as forward, matching the reference's "if / else if" typing).
-DHD uint64_t canon_kmer_hash(const uint64_t *A, const uint64_t *R, int L, int j, int K, int *fwd_is_canon)
+DHD uint64_t canon_kmer_hash(const uint32_t *A, const uint32_t *R, int L, int j, int K, int *fwd_is_canon)
 {
     const int KW = (K + 31) >> 5;
     const int tail = K - 32 * (KW - 1);
@@ -92,7 +106,7 @@ DHD uint64_t canon_kmer_hash(const uint64_t *A, const uint64_t *R, int L, int j,
         if (i == KW - 1) { x &= tmask; y &= tmask; }
         if (x != y) { fwd = x < y; break; }
     }
-    const uint64_t *S = fwd ? A : R;
+    const uint32_t *S = fwd ? A : R;
     const int s = fwd ? j : jr;
     uint64_t h = 0x9E3779B97F4A7C15ULL ^ (uint64_t)K;
     for (int i = 0; i < KW; i++) { // one multiply per word, full avalanche once at the end
@@ -108,7 +122,7 @@ DHD uint64_t canon_kmer_hash(const uint64_t *A, const uint64_t *R, int L, int j,
 // Compare n bases: padded array P (query side) from base a, against plain word array s2 (candidate, forward strand)
 // from base b.  Returns true when all n bases agree.
 template <typename WordLoader>
-DHD bool match_window(const uint64_t *P, int a, WordLoader s2, int b, int n)
+DHD bool match_window(const uint32_t *P, int a, WordLoader s2, int b, int n)
 {
     if (n <= 0) return true;
     const int wlo = b >> 5, whi = (b + n - 1) >> 5;
@@ -146,7 +160,7 @@ DHD void type_to_edge(int type, int L1, int K, int j, int *orient, int *ovl)
 template <typename WordLoader>
 struct LoaderMatcher {
     WordLoader s2;
-    DHD bool operator()(const uint64_t *P, int a, int b, int n) const { return match_window(P, a, s2, b, n); }
+    DHD bool operator()(const uint32_t *P, int a, int b, int n) const { return match_window(P, a, s2, b, n); }
 };
 
 // Window to compare for a candidate: bases [a, a+n) of the query (reverse-complement array when *use_rc) against bases
@@ -190,7 +204,7 @@ DHD bool contained_window(int type, int L1, int j, int K, int L2, int *use_rc, i
 }
 
 template <typename Matcher>
-DHD bool check_dovetail(const uint64_t *A, const uint64_t *R, int L1, int j, int K, int type, int L2, const Matcher &m)
+DHD bool check_dovetail(const uint32_t *A, const uint32_t *R, int L1, int j, int K, int type, int L2, const Matcher &m)
 {
     int use_rc, a, b, n;
     if (!dovetail_window(type, L1, j, K, L2, &use_rc, &a, &b, &n)) return false;
@@ -198,7 +212,7 @@ DHD bool check_dovetail(const uint64_t *A, const uint64_t *R, int L1, int j, int
 }
 
 template <typename Matcher>
-DHD bool check_contained(const uint64_t *A, const uint64_t *R, int L1, int j, int K, int type, int L2, const Matcher &m)
+DHD bool check_contained(const uint32_t *A, const uint32_t *R, int L1, int j, int K, int type, int L2, const Matcher &m)
 {
     int use_rc, a, b, n;
     if (!contained_window(type, L1, j, K, L2, &use_rc, &a, &b, &n)) return false;

@@ -19,7 +19,7 @@ namespace disco {
 #define FULL 0xffffffffu
 constexpr int kThreads = 256;  // 8 warps per block
 constexpr int kWarps = kThreads / 32;
-constexpr int kChunk = 8;      // reads per work-counter grab
+constexpr int kChunk = 16;     // reads per work-counter grab
 constexpr int kScanLimit = 6;  // buckets a lane may walk on the fast path before the read is deferred to the slow path
 constexpr int kRowBlock = 1024; // adjacency entries a warp reserves per global atomic
 constexpr int kHitCap = 128;    // fast-path candidate queue entries per warp (edge pass)
@@ -50,14 +50,28 @@ struct RegMatcher {
             v[2 * i] = q.x; v[2 * i + 1] = q.y;
         }
     }
-    __device__ __forceinline__ bool operator()(const uint64_t *P, int a, int b, int n) const
+    // bases [a, a+n) of padded array P against bases [b, b+n) of the candidate.  The query window is unaligned by a
+    // constant amount for every candidate word, so each word costs two funnel shifts; only the first and last word
+    // need a mask.
+    __device__ __forceinline__ bool operator()(const uint32_t *P, int a, int b, int n) const
     {
+        const int q0 = a - b + 32;           // query base (in padded coordinates) facing candidate base 0
+        const int i0 = q0 >> 4, sh = (q0 & 15) * 2;
+        const int wlo = b >> 5, whi = (b + n - 1) >> 5;
+        const uint64_t head = ~0ULL >> (2 * (b & 31));
+        const int tb = (b + n) & 31;
+        const uint64_t tail = tb ? ~(~0ULL >> (2 * tb)) : ~0ULL;
         uint64_t diff = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) {
-            int lo = b - 32 * w; if (lo < 0) lo = 0;
-            int hi = b + n - 32 * w; if (hi > 32) hi = 32;
-            if (lo < hi) diff |= (fetch64(P, a + 32 * w - b) ^ v[w]) & base_mask(lo, hi);
+            if (w >= wlo && w <= whi) {
+                const uint32_t *q = P + (i0 + 2 * w);
+                const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+                uint64_t x = (((uint64_t)fsl32(w1, w0, sh) << 32) | fsl32(w2, w1, sh)) ^ v[w];
+                if (w == wlo) x &= head;
+                if (w == whi) x &= tail;
+                diff |= x;
+            }
         }
         return diff == 0;
     }
@@ -72,17 +86,32 @@ struct RegMatcher<0> {
     LoaderMatcher<GlobalLoader> m;
     int stride;
     __device__ __forceinline__ void load(const uint64_t *words, uint64_t r) { m.s2.p = words + r * (uint64_t)stride; }
-    __device__ __forceinline__ bool operator()(const uint64_t *P, int a, int b, int n) const { return m(P, a, b, n); }
+    __device__ __forceinline__ bool operator()(const uint32_t *P, int a, int b, int n) const { return m(P, a, b, n); }
 };
 
-// stage read r into the warp's padded arrays A (forward) and R (reverse complement); WP = words(max_len) + 2
-__device__ __forceinline__ void stage_read(const ReadsView &rv, uint64_t r, int L, uint64_t *A, uint64_t *R, int WP, int lane)
+// stage read r into the warp's padded arrays A (forward) and R (reverse complement); WP = words(max_len) + 2 padded
+// words per array (stored as base-ordered 32-bit halves, see dna.cuh)
+__device__ __forceinline__ void stage_read(const ReadsView &rv, uint64_t r, int L, uint32_t *A, uint32_t *R, int WP, int lane)
 {
     const int W = (L + 31) >> 5;
     const uint64_t *src = rv.words + r * (uint64_t)rv.stride;
-    for (int w = lane; w < WP; w += 32) A[w] = (w >= 1 && w <= W) ? __ldg(src + (w - 1)) : 0ULL;
+    for (int w = lane; w < WP; w += 32) pstore(A, w, (w >= 1 && w <= W) ? __ldg(src + (w - 1)) : 0ULL);
     __syncwarp();
-    for (int w = lane; w < WP; w += 32) R[w] = (w >= 1 && w <= W) ? rc_word(A, L, W, w - 1) : 0ULL;
+    for (int w = lane; w < WP; w += 32) pstore(R, w, (w >= 1 && w <= W) ? rc_word(A, L, W, w - 1) : 0ULL);
+    __syncwarp();
+}
+
+// same, with the forward words already in registers (lane w holds word w; reads of up to 32 words = 1024 bases)
+__device__ __forceinline__ void stage_read_pre(uint64_t myword, int L, uint32_t *A, uint32_t *R, int WP, int lane)
+{
+    const int W = (L + 31) >> 5;
+    for (int w0 = 0; w0 < WP; w0 += 32) { // uniform trip count: the shuffle needs every lane
+        const int w = w0 + lane;
+        const uint64_t x = __shfl_sync(FULL, myword, (w - 1) & 31);
+        if (w < WP) pstore(A, w, (w >= 1 && w <= W) ? x : 0ULL);
+    }
+    __syncwarp();
+    for (int w = lane; w < WP; w += 32) pstore(R, w, (w >= 1 && w <= W) ? rc_word(A, L, W, w - 1) : 0ULL);
     __syncwarp();
 }
 
@@ -120,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int WP = ((rv.max_len + 31) >> 5) + 2;
-    uint64_t *A = smem + (size_t)wib * 2 * WP, *R = A + WP;
+    uint32_t *A = reinterpret_cast<uint32_t *>(smem + (size_t)wib * 2 * WP), *R = A + 2 * WP;
     const int wpb = blockDim.x >> 5;
     const uint64_t nwarps = (uint64_t)gridDim.x * wpb;
     for (uint64_t r = (uint64_t)blockIdx.x * wpb + wib; r < rv.n; r += nwarps) {
@@ -159,7 +188,11 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
 // ---------------------------------------------------------------------------------------------------------------
 enum { MODE_CONTAIN = 0, MODE_EDGES = 1 };
 
-__host__ __device__ inline size_t reduce_mark_smem_per_warp(int maxdeg) { return (((size_t)maxdeg * 9 + 15) / 16) * 16; }
+__host__ __device__ inline int reduce_mark_hset(int maxdeg) { int v = 64; while (v < 2 * maxdeg) v <<= 1; return v; }
+__host__ __device__ inline size_t reduce_mark_smem_per_warp(int maxdeg)
+{
+    return (((size_t)maxdeg * 9 + (size_t)reduce_mark_hset(maxdeg) * 4 + 15) / 16) * 16;
+}
 
 // hit record of the edge pass: [55..40 j][39..8 rec][1..0 type]  -> sorts by (j, rec) = the reference's visiting order
 __device__ __forceinline__ uint64_t make_hit(int j, uint32_t rec, int type) { return ((uint64_t)j << 40) | ((uint64_t)rec << 8) | (uint64_t)type; }
@@ -168,7 +201,8 @@ __device__ __forceinline__ uint32_t hit_read(uint64_t h) { return (uint32_t)(h >
 __device__ __forceinline__ int hit_type(uint64_t h) { return (int)(h & 3); }
 
 struct WarpSmem {
-    uint64_t *A, *R, *hits, *row, *best;
+    uint32_t *A, *R;
+    uint64_t *hits, *row, *best;
     int *ctrl; // [0] n hits, [1] slow flag, [2] n row, [3] n best
 };
 
@@ -288,7 +322,7 @@ __device__ __forceinline__ bool contain_one(const SearchParams &p, const WarpSme
 //                set of neighbour ids; positions with more than `cap` partners send the read to the exact
 //                sequential path; survivors are compacted by ballot and appended to the adjacency
 template <int NW, int MODE>
-__global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
+__global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 3 : 1) k_search(SearchParams p)
 {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -297,8 +331,8 @@ __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
     // per-warp shared memory carve-up (u64 units); must match search_smem_per_warp()
     const size_t per_warp = (MODE == MODE_EDGES) ? (size_t)(2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (size_t)(2 * WP + p.hcap + 2);
     WarpSmem s;
-    s.A = smem + wib * per_warp; s.R = s.A + WP;
-    s.hits = s.R + WP;
+    s.A = reinterpret_cast<uint32_t *>(smem + wib * per_warp); s.R = s.A + 2 * WP;
+    s.hits = smem + wib * per_warp + 2 * WP;
     if (MODE == MODE_EDGES) { s.row = s.hits + p.hcap; s.best = s.row + p.rowcap; s.ctrl = reinterpret_cast<int *>(s.best + kBestMax); }
     else { s.row = nullptr; s.best = nullptr; s.ctrl = reinterpret_cast<int *>(s.hits + p.hcap); }
     // fast-path scratch inside the (otherwise idle) row buffer: neighbour-id set + per-position counters
@@ -310,12 +344,21 @@ __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
     unsigned long long n_queries = 0, n_probes = 0, n_buckets = 0, n_verified = 0, n_hits = 0, n_entries = 0,
                        n_capfired = 0, n_slow = 0, maxdeg = 0;
     unsigned long long blk_cur = 0, blk_end = 0; // this warp's reserved slice of the adjacency buffer
+    const bool use_pre = p.reads.stride <= 32;
+    uint64_t pre_for = ~0ULL, pre_word = 0;
     uint64_t rb, re;
     while (grab_chunk(p.work_counter, p.q_lo, p.q_hi, lane, &rb, &re)) {
         for (uint64_t r1 = rb; r1 < re; r1++) {
             if (MODE == MODE_EDGES && ((__ldg(p.contained_bits + (r1 >> 5)) >> (r1 & 31)) & 1)) continue; // OverlapGraph.cpp:657
             const int L1 = read_len(p.reads, r1);
-            stage_read(p.reads, r1, L1, s.A, s.R, WP, lane);
+            if (use_pre) {
+                // the words of this read were requested while the previous one was processed
+                const uint64_t mine = (pre_for == r1) ? pre_word : ((lane < p.reads.stride) ? __ldg(p.reads.words + r1 * (uint64_t)p.reads.stride + lane) : 0ULL);
+                if (r1 + 1 < re) { pre_for = r1 + 1; pre_word = (lane < p.reads.stride) ? __ldg(p.reads.words + (r1 + 1) * (uint64_t)p.reads.stride + lane) : 0ULL; }
+                stage_read_pre(mine, L1, s.A, s.R, WP, lane);
+            } else {
+                stage_read(p.reads, r1, L1, s.A, s.R, WP, lane);
+            }
             n_queries += (lane == 0);
             if (lane < 4) s.ctrl[lane] = 0; // [0] queued, [1] needs exact path, [2] row length, [3] some position has > cap candidates
             __syncwarp();
@@ -341,17 +384,29 @@ __global__ void __launch_bounds__(kThreads) k_search(SearchParams p)
                         load_bucket(p.table.slots, b, v);
                         n_buckets++;
                         bool hole = false;
+                        unsigned mbits = 0;
 #pragma unroll
-                        for (int q = 0; q < 4; q++) {
-                            if (v[q] == kEmptySlot) { hole = true; continue; }
-                            if ((uint32_t)(v[q] >> 33) != tag) continue;
-                            const uint32_t rec = (uint32_t)v[q];
-                            if ((rec >> 1) == (uint32_t)r1) continue; // OverlapGraph.cpp:421 / :655
-                            const uint64_t c = make_hit(j, rec, cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq));
-                            const int pos = atomicAdd(&s.ctrl[0], 1);
-                            if (pos < p.hcap) s.hits[pos] = c;
-                            else if (MODE == MODE_CONTAIN) { n_verified++; n_hits += contain_one<NW>(p, s, r1, L1, c); } // queue full (rare)
-                            pushed++;
+                        for (int q = 0; q < 4; q++) { // branch-free classification of the four slots
+                            const bool empty = v[q] == kEmptySlot;
+                            hole |= empty;
+                            // not this read itself: OverlapGraph.cpp:421 / :655
+                            const bool match = !empty && (uint32_t)(v[q] >> 33) == tag && ((uint32_t)v[q] >> 1) != (uint32_t)r1;
+                            mbits |= (unsigned)match << q;
+                        }
+                        if (mbits) {
+                            const int cnt = __popc(mbits);
+                            int pos = atomicAdd(&s.ctrl[0], cnt);
+                            pushed += cnt;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                if ((mbits >> q) & 1) {
+                                    const uint32_t rec = (uint32_t)v[q];
+                                    const uint64_t c = make_hit(j, rec, cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq));
+                                    if (pos < p.hcap) s.hits[pos] = c;
+                                    else if (MODE == MODE_CONTAIN) { n_verified++; n_hits += contain_one<NW>(p, s, r1, L1, c); } // queue full (rare)
+                                    pos++;
+                                }
+                            }
                         }
                         if (hole) break;
                         b = (b + 1 == p.table.nbuckets) ? 0 : b + 1;
@@ -547,11 +602,14 @@ __global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     // per warp: ent u64[maxdeg] (the row; the entry value is also the (offset, id, orientation) sort key),
-    //           st u8[maxdeg]   (bit 0 visited, bit 1 eliminated; 0 = INPLAY and not yet visited)
+    //           hs  u32[hset]   (open-addressing set: neighbour id -> position in ent, sized 2x the row),
+    //           st  u8[maxdeg]  (bit 0 visited, bit 1 eliminated; 0 = INPLAY and not yet visited)
+    const int hcap = reduce_mark_hset(p.maxdeg);
     const size_t per_warp = reduce_mark_smem_per_warp(p.maxdeg);
     uint8_t *basep = reinterpret_cast<uint8_t *>(smem) + wib * per_warp;
     uint64_t *ent = reinterpret_cast<uint64_t *>(basep);
-    volatile uint8_t *st = basep + (size_t)p.maxdeg * 8;
+    uint32_t *hs = reinterpret_cast<uint32_t *>(basep + (size_t)p.maxdeg * 8);
+    volatile uint8_t *st = basep + (size_t)p.maxdeg * 8 + (size_t)hcap * 4;
     unsigned long long n_rows = 0, n_ent = 0;
     uint64_t ub, ue;
     while (grab_chunk(p.work_counter, p.u_lo, p.u_hi, lane, &ub, &ue)) {
@@ -560,9 +618,17 @@ __global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
             const int deg = (int)rowinfo_deg(ri);
             if (deg == 0) continue;
             const uint64_t start = rowinfo_start(ri);
+            int hsz = 64;
+            while (hsz < 2 * deg) hsz <<= 1; // <= hcap
+            const uint32_t hmask = (uint32_t)hsz - 1;
+            for (int k = lane; k < hsz; k += 32) hs[k] = 0xFFFFFFFFu;
+            __syncwarp();
             for (int k = lane; k < deg; k += 32) {
-                ent[k] = __ldcg(p.rows + start + k) & ~kElimBit;
+                const uint64_t e = __ldcg(p.rows + start + k) & ~kElimBit;
+                ent[k] = e;
                 st[k] = 0;
+                uint32_t h = ((uint32_t)entry_nbr(e) * 0x9E3779B1u) >> 7 & hmask;
+                while (atomicCAS(&hs[h], 0xFFFFFFFFu, (uint32_t)k) != 0xFFFFFFFFu) h = (h + 1) & hmask;
             }
             __syncwarp();
             for (;;) {
@@ -588,18 +654,17 @@ __global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
                 const uint64_t vs = rowinfo_start(vri);
                 n_rows += (lane == 0); n_ent += (lane == 0) ? (unsigned long long)vd : 0ULL;
                 __syncwarp();
-                for (int q0 = 0; q0 < vd; q0 += 32) {
-                    const int q = q0 + lane;
-                    bool go = false;
-                    uint32_t w = 0;
-                    if (q < vd) {
-                        const uint64_t e = __ldcg(p.rows + vs + q); // other warps may be setting eliminated bits: ignored
-                        w = (uint32_t)entry_nbr(e);
-                        go = chain_ok(t1, entry_orient(e));
-                    }
-                    if (__any_sync(FULL, go)) {
-                        for (int k = 0; k < deg; k++)
-                            if (go && (uint32_t)entry_nbr(ent[k]) == w) st[k] = st[k] | 2; // at most one lane holds this w
+                for (int q = lane; q < vd; q += 32) {
+                    const uint64_t e = __ldcg(p.rows + vs + q); // other warps may be setting eliminated bits: ignored
+                    if (!chain_ok(t1, entry_orient(e))) continue;
+                    // is w also a neighbour of u?  (markedNodes->find(read3), OverlapGraph.cpp:701)
+                    const uint32_t w = (uint32_t)entry_nbr(e);
+                    uint32_t h = (w * 0x9E3779B1u) >> 7 & hmask;
+                    for (;;) {
+                        const uint32_t k = hs[h];
+                        if (k == 0xFFFFFFFFu) break;
+                        if ((uint32_t)entry_nbr(ent[k]) == w) { st[k] = st[k] | 2; break; } // ELIMINATED
+                        h = (h + 1) & hmask;
                     }
                 }
                 __syncwarp();

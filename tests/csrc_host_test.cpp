@@ -26,10 +26,10 @@ static std::vector<uint64_t> pack(const std::string &s)
     }
     return w;
 }
-static std::vector<uint64_t> padded(const std::vector<uint64_t> &w)
+static std::vector<uint32_t> padded(const std::vector<uint64_t> &w)
 {
-    std::vector<uint64_t> p(w.size() + 2, 0);
-    for (size_t i = 0; i < w.size(); i++) p[i + 1] = w[i];
+    std::vector<uint32_t> p(padded_u32((int)w.size()), 0);
+    for (size_t i = 0; i < w.size(); i++) pstore(p.data(), (int)i + 1, w[i]);
     return p;
 }
 #define CHECK(c) do { if (!(c)) { printf("FAIL %s:%d %s\n", __FILE__, __LINE__, #c); exit(1); } } while (0)
@@ -67,10 +67,10 @@ int main()
         std::string s = rnd_read(L), r = rc(s);
         auto A = padded(pack(s));
         int W = (L + 31) / 32;
-        std::vector<uint64_t> R(W + 2, 0);
-        for (int w = 0; w < W; w++) R[w + 1] = rc_word(A.data(), L, W, w);
+        std::vector<uint32_t> R(padded_u32(W), 0);
+        for (int w = 0; w < W; w++) pstore(R.data(), w + 1, rc_word(A.data(), L, W, w));
         auto Rref = padded(pack(r));
-        for (int w = 0; w < W + 2; w++) CHECK(R[w] == Rref[w]);
+        CHECK(R == Rref);
         for (int p = -32; p < L; p++) {
             uint64_t x = fetch64(A.data(), p);
             for (int b = 0; b < 32; b++) {
