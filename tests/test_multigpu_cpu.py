@@ -1,0 +1,119 @@
+"""world_size-2 gloo test (CPU) of the multi-GPU host logic in disco_b200/multigpu.py: the range partition, the
+unsigned all-reduce(MIN) of containment keys and the variable-length adjacency exchange, driven through a fake context
+that exposes CPU tensors where the real one exposes device buffers."""
+import os
+import sys
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+N = 1000
+SENT = -1  # all ones
+
+
+def _keys_for(rank, lo, hi):
+    rng = np.random.default_rng(100 + rank)
+    k = np.full(N, SENT, dtype=np.int64)
+    idx = np.arange(N)
+    # a rank can mark ANY read contained (its queries cover reads everywhere); include large (bit 50) and tiny keys
+    sel = rng.random(N) < 0.3
+    k[sel] = (rng.integers(lo, max(hi, lo + 1), size=int(sel.sum())).astype(np.int64) << 20) | rng.integers(0, 1 << 19, size=int(sel.sum()))
+    return k
+
+
+def _rows_for(rank, lo, hi):
+    rng = np.random.default_rng(200 + rank)
+    deg = rng.integers(0, 6, size=hi - lo)
+    rows = rng.integers(1, 1 << 40, size=int(deg.sum())).astype(np.int64)
+    start = np.concatenate([[0], np.cumsum(deg)[:-1]])
+    info = np.zeros(N, dtype=np.int64)
+    info[lo:hi] = np.where(deg > 0, (start << 20) | deg, 0)
+    return rows, info, int(deg.max()) if len(deg) else 0
+
+
+class FakeCtx:
+    def __init__(self, rank, world):
+        self.n = N
+        self.rank, self.world = rank, world
+        self.log = []
+
+    def begin(self, m, cap): self.log.append("begin")
+    def phase_table(self, ex): self.log.append(f"table{int(ex)}")
+    def phase_contained(self, lo, hi):
+        self.keys = torch.from_numpy(_keys_for(self.rank, lo, hi))
+        self.log.append("contained")
+    def phase_finish_contained(self): self.log.append("finish")
+    def phase_edges(self, lo, hi):
+        rows, info, md = _rows_for(self.rank, lo, hi)
+        self.rows, self.rowinfo, self.maxdeg = torch.from_numpy(rows), torch.from_numpy(info), md
+        self.log.append("edges")
+    def stats(self): return {"max_degree": self.maxdeg}
+    def rebase_rows(self, lo, hi, base):
+        seg = self.rowinfo[lo:hi]
+        nz = (seg & 0xFFFFF) != 0
+        seg[nz] += base << 20
+    def set_max_degree(self, d): self.final_maxdeg = d
+    def phase_reduce(self, lo, hi): self.log.append("reduce")
+    def sync(self): pass
+
+
+class FakeTensors:
+    def __init__(self, g): self.g = g
+    def keys(self): return self.g.keys
+    def rowinfo(self): return self.g.rowinfo
+    def rows(self): return self.g.rows
+    def adopt_rows(self, t): self.g.adopted = t.clone()
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from disco_b200 import multigpu
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = FakeCtx(rank, world)
+    multigpu.ShardedBuildGraph(g, rank, world, tensors=FakeTensors(g)).build_graph(50, 4)
+    q.put((rank, g.keys.numpy().copy(), g.rowinfo.numpy().copy(), g.adopted.numpy().copy(), g.final_maxdeg, g.log))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_exchange_gloo(world):
+    sys.path.insert(0, ROOT)
+    from disco_b200 import multigpu
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # expected: unsigned min of keys, rows concatenated in rank order, row info rebased
+    parts = [multigpu.partition(N, r, world) for r in range(world)]
+    assert parts[0][0] == 0 and parts[-1][1] == N and all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+    keys = np.stack([_keys_for(r, *parts[r]) for r in range(world)]).view(np.uint64).min(axis=0).view(np.int64)
+    rows, infos, mds = zip(*[_rows_for(r, *parts[r]) for r in range(world)])
+    cat = np.concatenate(rows)
+    for rank, k, info, adopted, md, log in res:
+        assert np.array_equal(k, keys)
+        assert np.array_equal(adopted, cat)
+        assert md == max(mds)
+        assert log == ["begin", "table0", "contained", "finish", "table1", "edges", "reduce"]
+        # every row info entry must point at that read's own row inside the gathered array
+        base = 0
+        for r in range(world):
+            lo, hi = parts[r]
+            loc = infos[r][lo:hi]
+            for i in range(lo, hi):
+                d = int(loc[i - lo] & 0xFFFFF)
+                assert int(info[i] & 0xFFFFF) == d
+                if d:
+                    s0, s1 = int(loc[i - lo] >> 20), int(info[i] >> 20)
+                    assert s1 == s0 + base
+                    assert np.array_equal(adopted[s1:s1 + d], rows[r][s0:s0 + d])
+            base += len(rows[r])
