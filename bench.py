@@ -181,7 +181,7 @@ def run_ours(args):
     n_total = args.reads * world          # weak scaling: per-GPU query share is fixed
     rs = make_reads(n_total, seed=2)
     n = rs.n
-    wpr = 6
+    wpr = 8
     # pinned host buffers (the reference-facing call takes host memory)
     h_packed = torch.empty((n, wpr), dtype=torch.int64).pin_memory()
     h_lens = torch.empty((n,), dtype=torch.int16).pin_memory()

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -38,6 +39,8 @@ struct disco_ctx {
     // table
     uint64_t *d_slots = nullptr;
     uint64_t nbuckets = 0;
+    uint32_t *d_filter = nullptr;
+    uint64_t filter_bits = 0;
     // containment
     unsigned long long *d_best = nullptr;
     uint32_t *d_bits = nullptr;
@@ -92,14 +95,16 @@ void dfree(T *&p)
 int pick_stride(int max_len)
 {
     const int W = (max_len + 31) / 32;
-    const int regs[] = {2, 4, 6, 8, 10, 12, 16};
+    // power-of-two rows (16..128 bytes) never straddle a 64-byte DRAM fetch / 128-byte line: one random access per
+    // candidate read
+    const int regs[] = {2, 4, 8, 16};
     for (int s : regs) if (W <= s) return s;
     return (W + 1) & ~1; // long reads: generic (global-walking) matcher, still 16-byte aligned rows
 }
 
 void free_run_buffers(disco_ctx *c)
 {
-    dfree(c->d_slots); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
+    dfree(c->d_slots); dfree(c->d_filter); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
     dfree(c->d_rowinfo); dfree(c->d_rows); dfree(c->d_edges);
     c->rows_cap = c->edges_cap = c->crows_cap = c->run_n = 0;
     c->begun = c->have_contained = c->have_edges = c->have_reduced = false;
@@ -277,6 +282,16 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
             ctx->nbuckets = std::max<uint64_t>(1024, nb);
         }
         CK(cudaMalloc(&ctx->d_slots, ctx->nbuckets * 4 * sizeof(uint64_t)));
+        // presence filter: 16 bits per record, at most 64 MB so that it stays resident in the 126 MB L2; pointless
+        // once it has fewer bits than records
+        ctx->filter_bits = 1ULL << 16;
+        while (ctx->filter_bits < 32 * n && ctx->filter_bits < (1ULL << 29)) ctx->filter_bits <<= 1;
+        if (const char *e = getenv("DISCO_FILTER_LOG2")) { // tuning knob: 0 disables the filter
+            const int lg = atoi(e);
+            ctx->filter_bits = lg >= 10 && lg <= 33 ? (1ULL << lg) : 0;
+        }
+        if (ctx->filter_bits < 2 * n) ctx->filter_bits = 0;
+        if (ctx->filter_bits) CK(cudaMalloc(&ctx->d_filter, ctx->filter_bits / 8));
         CK(cudaMalloc(&ctx->d_best, n * sizeof(unsigned long long)));
         CK(cudaMalloc(&ctx->d_bits, ((n + 31) / 32) * sizeof(uint32_t)));
         CK(cudaMalloc(&ctx->d_rowinfo, n * sizeof(uint64_t)));
@@ -303,7 +318,8 @@ int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained)
     if (exclude_contained && !ctx->have_contained) return fail(ctx, DISCO_E_ARG, "containment pass not finished");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_slots, 0xFF, ctx->nbuckets * 4 * sizeof(uint64_t), ctx->stream));
-    TableView tv{ctx->d_slots, ctx->nbuckets};
+    if (ctx->d_filter) CK(cudaMemsetAsync(ctx->d_filter, 0, ctx->filter_bits / 8, ctx->stream));
+    TableView tv{ctx->d_slots, ctx->nbuckets, ctx->d_filter, (uint32_t)(ctx->filter_bits ? ctx->filter_bits - 1 : 0)};
     CK(launch_table_insert(ctx->reads, tv, ctx->K, exclude_contained ? ctx->d_bits : nullptr, ctx->num_sms, ctx->stream));
     return record(ctx, exclude_contained ? EV_TABLE_NC : EV_TABLE_ALL);
 }
@@ -315,7 +331,7 @@ int disco_gpu_phase_contained(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
     SearchParams p{};
-    p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets};
+    p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets, ctx->d_filter, (uint32_t)(ctx->filter_bits ? ctx->filter_bits - 1 : 0)};
     p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_c; p.best = ctx->d_best;
     int rc = record(ctx, EV_CONT_K0);
@@ -356,7 +372,7 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
     CK(cudaSetDevice(ctx->device));
     const uint64_t nq = q_hi - q_lo;
     SearchParams p{};
-    p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets};
+    p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets, ctx->d_filter, (uint32_t)(ctx->filter_bits ? ctx->filter_bits - 1 : 0)};
     p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.contained_bits = ctx->d_bits; p.rows_cursor = ctx->d_cursors + CUR_ROWS; p.rowinfo = ctx->d_rowinfo;

@@ -37,6 +37,8 @@ struct ReadsView {
 struct TableView {
     uint64_t *slots;   // nbuckets * 4
     uint64_t nbuckets;
+    uint32_t *filter;  // presence bitmap over a second slice of the k-mer hash, small enough to stay in L2 (or null)
+    uint32_t filter_mask; // bits - 1 (power of two)
 };
 
 struct SearchParams {

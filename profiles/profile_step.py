@@ -7,7 +7,7 @@ from disco_b200 import gpu, host, synth
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 10_000_000
 warm = int(sys.argv[2]) if len(sys.argv) > 2 else 1
 rs = synth.single_genome(n, 150, 30.0, seed=2)
-packed, lens = host.pack_codes(rs.codes, rs.off, 6)
+packed, lens = host.pack_codes(rs.codes, rs.off, 8)
 g = gpu.GpuBuildGraph(0)
 g.load_reads(packed, lens)
 for _ in range(warm + 1):
