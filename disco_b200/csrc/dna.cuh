@@ -100,20 +100,44 @@ DHD uint64_t canon_kmer_hash(const uint32_t *A, const uint32_t *R, int L, int j,
     const int tail = K - 32 * (KW - 1);
     const uint64_t tmask = base_mask(0, tail);
     const int jr = L - j - K; // the k-mer's reverse complement starts here in rc(read)
-    int fwd = 1;
-    for (int i = 0; i < KW; i++) {
-        uint64_t x = fetch64(A, j + 32 * i), y = fetch64(R, jr + 32 * i);
-        if (i == KW - 1) { x &= tmask; y &= tmask; }
-        if (x != y) { fwd = x < y; break; }
-    }
-    const uint32_t *S = fwd ? A : R;
-    const int s = fwd ? j : jr;
     uint64_t h = 0x9E3779B97F4A7C15ULL ^ (uint64_t)K;
-    for (int i = 0; i < KW; i++) { // one multiply per word, full avalanche once at the end
-        uint64_t x = fetch64(S, s + 32 * i);
-        if (i == KW - 1) x &= tmask;
-        h = (h ^ x) * 0xD6E8FEB86659FD93ULL;
-        h ^= h >> 32;
+    int fwd = 1;
+    if (KW <= 4) {
+        // common case (K <= 128): both strands in registers, decide, then hash the winner -- no second fetch
+        uint64_t x[4], y[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (i < KW) {
+                x[i] = fetch64(A, j + 32 * i); y[i] = fetch64(R, jr + 32 * i);
+                if (i == KW - 1) { x[i] &= tmask; y[i] &= tmask; }
+            } else { x[i] = 0; y[i] = 0; }
+        }
+        bool decided = false;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!decided && x[i] != y[i]) { fwd = x[i] < y[i]; decided = true; }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (i < KW) { // one multiply per word, full avalanche once at the end
+                h = (h ^ (fwd ? x[i] : y[i])) * 0xD6E8FEB86659FD93ULL;
+                h ^= h >> 32;
+            }
+        }
+    } else {
+        for (int i = 0; i < KW; i++) {
+            uint64_t x = fetch64(A, j + 32 * i), y = fetch64(R, jr + 32 * i);
+            if (i == KW - 1) { x &= tmask; y &= tmask; }
+            if (x != y) { fwd = x < y; break; }
+        }
+        const uint32_t *S = fwd ? A : R;
+        const int s = fwd ? j : jr;
+        for (int i = 0; i < KW; i++) {
+            uint64_t x = fetch64(S, s + 32 * i);
+            if (i == KW - 1) x &= tmask;
+            h = (h ^ x) * 0xD6E8FEB86659FD93ULL;
+            h ^= h >> 32;
+        }
     }
     *fwd_is_canon = fwd;
     return mix64(h);

@@ -62,13 +62,15 @@ __device__ __forceinline__ bool filter_test(const TableView &t, uint64_t h, uint
     return (w >> (bit & 31)) & 1;
 }
 
-// candidate read held in registers (NW = words per read = the device stride, even)
+// candidate read held in registers: NW = words loaded (even, >= words of the longest read); the row stride in memory
+// may be larger (power of two)
 template <int NW>
 struct RegMatcher {
     uint64_t v[NW];
+    int stride;
     __device__ __forceinline__ void load(const uint64_t *words, uint64_t r)
     {
-        const uint64_t *p = words + r * NW;
+        const uint64_t *p = words + r * (uint64_t)stride;
         const uint64_t pol = policy_evict_first();
 #pragma unroll
         for (int i = 0; i < NW / 2; i++) // 128-bit loads, rows are 16-byte aligned
@@ -77,8 +79,8 @@ struct RegMatcher {
     }
     // bases [a, a+n) of padded array P against bases [b, b+n) of the candidate.  The query window is unaligned by a
     // constant amount for every candidate word, so each word costs two funnel shifts; only the first and last word
-    // need a mask.
-    __device__ __forceinline__ bool operator()(const uint32_t *P, int a, int b, int n) const
+    // need a mask.  Branch-free: words outside [wlo, whi] are fetched from a clamped address and masked to zero.
+    __device__ __forceinline__ bool operator()(const uint32_t *P, int a, int b, int n, int p_u32) const
     {
         const int q0 = a - b + 32;           // query base (in padded coordinates) facing candidate base 0
         const int i0 = q0 >> 4, sh = (q0 & 15) * 2;
@@ -89,14 +91,14 @@ struct RegMatcher {
         uint64_t diff = 0;
 #pragma unroll
         for (int w = 0; w < NW; w++) {
-            if (w >= wlo && w <= whi) {
-                const uint32_t *q = P + (i0 + 2 * w);
-                const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
-                uint64_t x = (((uint64_t)fsl32(w1, w0, sh) << 32) | fsl32(w2, w1, sh)) ^ v[w];
-                if (w == wlo) x &= head;
-                if (w == whi) x &= tail;
-                diff |= x;
-            }
+            int i = i0 + 2 * w;
+            i = max(0, min(i, p_u32 - 3));
+            const uint32_t w0 = P[i], w1 = P[i + 1], w2 = P[i + 2];
+            uint64_t x = (((uint64_t)fsl32(w1, w0, sh) << 32) | fsl32(w2, w1, sh)) ^ v[w];
+            uint64_t m = (w >= wlo && w <= whi) ? ~0ULL : 0ULL;
+            if (w == wlo) m &= head;
+            if (w == whi) m &= tail;
+            diff |= x & m;
         }
         return diff == 0;
     }
@@ -111,7 +113,7 @@ struct RegMatcher<0> {
     LoaderMatcher<GlobalLoader> m;
     int stride;
     __device__ __forceinline__ void load(const uint64_t *words, uint64_t r) { m.s2.p = words + r * (uint64_t)stride; }
-    __device__ __forceinline__ bool operator()(const uint32_t *P, int a, int b, int n) const { return m(P, a, b, n); }
+    __device__ __forceinline__ bool operator()(const uint32_t *P, int a, int b, int n, int) const { return m(P, a, b, n); }
 };
 
 // stage read r into the warp's padded arrays A (forward) and R (reverse complement); WP = words(max_len) + 2 padded
@@ -217,6 +219,15 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
 // ---------------------------------------------------------------------------------------------------------------
 enum { MODE_CONTAIN = 0, MODE_EDGES = 1 };
 
+// u64 words of shared memory one warp of k_search needs: A, R (WP each), position list (npos hashes + npos u32),
+// candidate queue, and for the edge pass the row buffer, the slow path's best list and 4 control ints
+__host__ __device__ inline size_t search_words_per_warp(int WP, int npos, int hcap, int rowcap, int mode)
+{
+    size_t w = 2 * (size_t)WP + (size_t)npos + ((size_t)npos + 1) / 2 + (size_t)hcap + 2;
+    if (mode == MODE_EDGES) w += (size_t)rowcap + kBestMax;
+    return w;
+}
+
 __host__ __device__ inline int reduce_mark_hset(int maxdeg) { int v = 64; while (v < 2 * maxdeg) v <<= 1; return v; }
 __host__ __device__ inline size_t reduce_mark_smem_per_warp(int maxdeg)
 {
@@ -231,6 +242,9 @@ __device__ __forceinline__ int hit_type(uint64_t h) { return (int)(h & 3); }
 
 struct WarpSmem {
     uint32_t *A, *R;
+    int p_u32; // 32-bit words in each padded array
+    uint64_t *ph;   // hashes of the positions that passed the presence filter
+    uint32_t *pj;   // their (position << 1 | canonical-is-forward)
     uint64_t *hits, *row, *best;
     int *ctrl; // [0] n hits, [1] slow flag, [2] n row, [3] n best
 };
@@ -239,10 +253,12 @@ template <int NW>
 __device__ __forceinline__ bool verify_dovetail(const SearchParams &p, const WarpSmem &s, int L1, int j, int type, uint32_t r2)
 {
     RegMatcher<NW> m;
-    if (NW == 0) reinterpret_cast<RegMatcher<0> &>(m).stride = p.reads.stride;
+    m.stride = p.reads.stride;
     m.load(p.reads.words, r2);
     const int L2 = read_len(p.reads, r2);
-    return check_dovetail(s.A, s.R, L1, j, p.K, type, L2, m);
+    int use_rc, a, b, n;
+    if (!dovetail_window(type, L1, j, p.K, L2, &use_rc, &a, &b, &n)) return false;
+    return m(use_rc ? s.R : s.A, a, b, n, s.p_u32);
 }
 
 // Exact sequential search of one read (used when MAX_EDGE_PER_KMER can fire or a position has a long candidate list):
@@ -250,8 +266,7 @@ __device__ __forceinline__ bool verify_dovetail(const SearchParams &p, const War
 // the row is skipped without counting (OverlapGraph.cpp:645-670).  The warp walks 8 buckets (32 slots) per step.
 template <int NW>
 __device__ void search_edges_slow(const SearchParams &p, const WarpSmem &s, uint64_t r1, int L1, int lane,
-                                  unsigned long long &n_probes, unsigned long long &n_buckets,
-                                  unsigned long long &n_verified, unsigned long long &n_capfired)
+                                  unsigned &n_probes, unsigned &n_buckets, unsigned &n_verified, unsigned &n_capfired)
 {
     const int K = p.K;
     int nrow = 0;
@@ -270,7 +285,7 @@ __device__ void search_edges_slow(const SearchParams &p, const WarpSmem &s, uint
             const uint64_t v = __ldg(p.table.slots + 4 * bb + (lane & 3));
             const unsigned empties = __ballot_sync(FULL, v == kEmptySlot);
             const int limit = empties ? ((__ffs(empties) - 1) | 3) : 31; // the chain ends in the first bucket with a hole
-            n_buckets += (lane == 0) ? (unsigned long long)((limit >> 2) + 1) : 0ULL;
+            n_buckets += (lane == 0) ? (unsigned)((limit >> 2) + 1) : 0u;
             bool valid = false;
             uint64_t key = 0;
             if (lane <= limit && v != kEmptySlot && (uint32_t)(v >> 33) == tag) {
@@ -334,44 +349,52 @@ __device__ __forceinline__ bool contain_one(const SearchParams &p, const WarpSme
     // read1 must be longer, or equal and earlier in the file (OverlapGraph.cpp:424, :449)
     if (!(L1 > L2 || (L1 == L2 && r1 < r2))) return false;
     RegMatcher<NW> m;
-    if (NW == 0) reinterpret_cast<RegMatcher<0> &>(m).stride = p.reads.stride;
+    m.stride = p.reads.stride;
     m.load(p.reads.words, r2);
     const int j = hit_j(c), type = hit_type(c);
-    if (!check_contained(s.A, s.R, L1, j, p.K, type, L2, m)) return false;
+    int use_rc, a, b, n;
+    if (!contained_window(type, L1, j, p.K, L2, &use_rc, &a, &b, &n)) return false;
+    if (!m(use_rc ? s.R : s.A, a, b, n, s.p_u32)) return false;
     atomicMin(p.best + r2, (unsigned long long)make_ckey(r1, j, (int)((c >> 8) & 1), type));
     return true;
 }
 
 // Search kernel, both passes.  Per read (one warp):
-//   1. probe   : one lane per k-mer position; canonical fingerprint, one 32-byte bucket load, tag compare; every
-//                tag match is queued in shared memory as (position, record, type)
-//   2. verify  : one lane per queued candidate (lanes fully packed whatever the hit pattern was): 128-bit loads of the
-//                candidate read, one windowed 2-bit compare against the staged query (forward or reverse complement)
+//   1a. hash   : one lane per k-mer position: canonical fingerprint, presence-filter bit (L2 resident); positions that
+//                pass are ballot-compacted into a list and their table bucket is prefetched into L2
+//   1b. probe  : one lane per listed position (lanes packed): one 32-byte bucket load, branch-free tag compare; every
+//                tag match is queued as (position, record, type) and the candidate read is prefetched
+//   2. verify  : one lane per queued candidate: 128-bit loads of the candidate read, one windowed 2-bit compare
+//                against the staged query (forward or reverse complement)
 //   3. resolve : (edge pass) first hit per neighbour wins (OverlapGraph.cpp:656) -- checked with a shared-memory
 //                set of neighbour ids; positions with more than `cap` partners send the read to the exact
 //                sequential path; survivors are compacted by ballot and appended to the adjacency
 template <int NW, int MODE>
-__global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 3 : 1) k_search(SearchParams p)
+__global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_search(SearchParams p)
 {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int WP = ((p.reads.max_len + 31) >> 5) + 2;
     const int K = p.K;
     // per-warp shared memory carve-up (u64 units); must match search_smem_per_warp()
-    const size_t per_warp = (MODE == MODE_EDGES) ? (size_t)(2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (size_t)(2 * WP + p.hcap + 2);
+    const size_t per_warp = search_words_per_warp(WP, p.npos, p.hcap, p.rowcap, MODE);
     WarpSmem s;
-    s.A = reinterpret_cast<uint32_t *>(smem + wib * per_warp); s.R = s.A + 2 * WP;
-    s.hits = smem + wib * per_warp + 2 * WP;
+    uint64_t *w0 = smem + wib * per_warp;
+    s.A = reinterpret_cast<uint32_t *>(w0); s.R = s.A + 2 * WP; s.p_u32 = 2 * WP;
+    s.ph = w0 + 2 * WP;
+    s.pj = reinterpret_cast<uint32_t *>(s.ph + p.npos);
+    s.hits = s.ph + p.npos + (p.npos + 1) / 2;
     if (MODE == MODE_EDGES) { s.row = s.hits + p.hcap; s.best = s.row + p.rowcap; s.ctrl = reinterpret_cast<int *>(s.best + kBestMax); }
     else { s.row = nullptr; s.best = nullptr; s.ctrl = reinterpret_cast<int *>(s.hits + p.hcap); }
     // fast-path scratch inside the (otherwise idle) row buffer: neighbour-id set + per-position counters
     uint32_t *hset = (MODE == MODE_EDGES) ? reinterpret_cast<uint32_t *>(s.row) : nullptr;
     int *cntj = (MODE == MODE_EDGES) ? reinterpret_cast<int *>(s.row) + p.hset : nullptr;
-    const uint32_t hset_mask = (uint32_t)p.hset - 1;
     const unsigned lt_mask = (1u << lane) - 1;
+    const uint64_t nbuckets = p.table.nbuckets;
+    const int hcap = p.hcap, cap = p.cap;
 
-    unsigned long long n_queries = 0, n_probes = 0, n_buckets = 0, n_verified = 0, n_hits = 0, n_entries = 0,
-                       n_capfired = 0, n_slow = 0, maxdeg = 0;
+    unsigned n_queries = 0, n_probes = 0, n_buckets = 0, n_verified = 0, n_hits = 0, n_capfired = 0, n_slow = 0, maxdeg = 0;
+    unsigned long long n_entries = 0;
     unsigned long long blk_cur = 0, blk_end = 0; // this warp's reserved slice of the adjacency buffer
     const bool use_pre = p.reads.stride <= 32;
     uint64_t pre_for = ~0ULL, pre_word = 0;
@@ -396,20 +419,41 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 3 : 1) k_searc
             //   types 0/2 need j + L2 <= L1, types 1/3 need j >= L2 - K, and L2 >= min_len.
             // edges: positions [1, L1-K) (OverlapGraph.cpp:638)
             const int jlo = (MODE == MODE_EDGES) ? 1 : 0, jhi = L1 - K;
-            // ---- 1. probe ------------------------------------------------------------------------------------
+            // ---- 1a. hash + presence filter -------------------------------------------------------------------
+            int np = 0;
             for (int jb = jlo; jb < jhi; jb += 32) {
                 const int j = jb + lane;
                 bool act = j < jhi;
                 if (MODE == MODE_CONTAIN) act = act && (j <= L1 - p.reads.min_len || j >= p.reads.min_len - K);
+                uint64_t h = 0;
+                int fq = 0;
+                bool pass = false;
                 if (act) {
-                    int fq;
-                    const uint64_t h = canon_kmer_hash(s.A, s.R, L1, j, K, &fq);
-                    const uint32_t tag = slot_tag(h);
-                    uint64_t b = bucket_of(h, p.table.nbuckets);
-                    int pushed = 0;
+                    h = canon_kmer_hash(s.A, s.R, L1, j, K, &fq);
                     n_probes++;
                     // most positions match no record at all: the L2-resident presence bit answers that without DRAM
-                    if (filter_test(p.table, h, pol_keep))
+                    pass = filter_test(p.table, h, pol_keep);
+                    if (pass) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table.slots + 4 * bucket_of(h, nbuckets)));
+                }
+                const unsigned m = __ballot_sync(FULL, pass);
+                if (pass) {
+                    const int pos = np + __popc(m & lt_mask);
+                    s.ph[pos] = h;
+                    s.pj[pos] = ((uint32_t)j << 1) | (uint32_t)fq;
+                }
+                np += __popc(m);
+            }
+            __syncwarp();
+            // ---- 1b. probe: one lane per surviving position -----------------------------------------------------
+            for (int i0 = 0; i0 < np; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < np) {
+                    const uint64_t h = s.ph[i];
+                    const uint32_t jf = s.pj[i];
+                    const int j = (int)(jf >> 1), fq = (int)(jf & 1);
+                    const uint32_t tag = slot_tag(h);
+                    uint64_t b = bucket_of(h, nbuckets);
+                    int pushed = 0;
                     for (int walked = 0;; walked++) {
                         if (MODE == MODE_EDGES && walked == kScanLimit) { s.ctrl[1] = 1; break; } // long chain: exact path
                         uint64_t v[4];
@@ -434,21 +478,23 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 3 : 1) k_searc
                                 if ((mbits >> q) & 1) {
                                     const uint32_t rec = (uint32_t)v[q];
                                     const uint64_t c = make_hit(j, rec, cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq));
-                                    if (pos < p.hcap) s.hits[pos] = c;
-                                    else if (MODE == MODE_CONTAIN) { n_verified++; n_hits += contain_one<NW>(p, s, r1, L1, c); } // queue full (rare)
+                                    if (pos < hcap) {
+                                        s.hits[pos] = c;
+                                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.reads.words + (uint64_t)(rec >> 1) * (uint64_t)p.reads.stride));
+                                    } else if (MODE == MODE_CONTAIN) { n_verified++; n_hits += contain_one<NW>(p, s, r1, L1, c); } // queue full (rare)
                                     pos++;
                                 }
                             }
                         }
                         if (hole) break;
-                        b = (b + 1 == p.table.nbuckets) ? 0 : b + 1;
+                        b = (b + 1 == nbuckets) ? 0 : b + 1;
                     }
-                    if (MODE == MODE_EDGES && pushed > p.cap) s.ctrl[3] = 1;
+                    if (MODE == MODE_EDGES && pushed > cap) s.ctrl[3] = 1;
                 }
                 __syncwarp();
-                if (MODE == MODE_CONTAIN) { // ---- 2. verify, drained after every batch (this pass has no exact path)
-                    const int nc = min(s.ctrl[0], p.hcap);
-                    for (int i = lane; i < nc; i += 32) { n_verified++; n_hits += contain_one<NW>(p, s, r1, L1, s.hits[i]); }
+                if (MODE == MODE_CONTAIN) { // ---- 2. verify, drained after every round (this pass has no exact path)
+                    const int nc = min(s.ctrl[0], hcap);
+                    for (int k = lane; k < nc; k += 32) { n_verified++; n_hits += contain_one<NW>(p, s, r1, L1, s.hits[k]); }
                     __syncwarp();
                     if (lane == 0) s.ctrl[0] = 0;
                     __syncwarp();
@@ -457,12 +503,15 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 3 : 1) k_searc
             if (MODE != MODE_EDGES) continue;
 
             const int nc = s.ctrl[0];
-            bool slow = s.ctrl[1] != 0 || nc > p.hcap;
+            bool slow = s.ctrl[1] != 0 || nc > hcap;
             int nrow = 0;
             if (!slow) {
                 // ---- 2. verify: lane per candidate ------------------------------------------------------------
                 const bool count_pos = s.ctrl[3] != 0; // only reads with a crowded position pay for per-position counts
-                for (int k = lane; k < p.hset; k += 32) hset[k] = 0xFFFFFFFFu;
+                int hsz = 64;
+                while (hsz < 2 * nc) hsz <<= 1;         // <= p.hset
+                const uint32_t hm = (uint32_t)hsz - 1;
+                for (int k = lane; k < hsz; k += 32) hset[k] = 0xFFFFFFFFu;
                 if (count_pos) for (int k = lane; k < jhi; k += 32) cntj[k] = 0;
                 __syncwarp();
                 bool dup = false, over = false;
@@ -474,20 +523,20 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 3 : 1) k_searc
                         const bool ok = verify_dovetail<NW>(p, s, L1, hit_j(c), hit_type(c), r2);
                         if (ok) {
                             // ---- 3a. first hit per neighbour: insert r2 into the warp's id set
-                            uint32_t hh = (r2 * 0x9E3779B1u) & hset_mask;
+                            uint32_t hh = (r2 * 0x9E3779B1u) >> 7 & hm;
                             for (;;) {
                                 const uint32_t old = atomicCAS(&hset[hh], 0xFFFFFFFFu, r2);
                                 if (old == 0xFFFFFFFFu) break;
                                 if (old == r2) { dup = true; break; }
-                                hh = (hh + 1) & hset_mask;
+                                hh = (hh + 1) & hm;
                             }
-                            if (count_pos) over |= atomicAdd(&cntj[hit_j(c)], 1) >= p.cap;
+                            if (count_pos) over |= atomicAdd(&cntj[hit_j(c)], 1) >= cap;
                         } else {
                             s.hits[i] = ~0ULL;
                         }
                     }
                 }
-                n_verified += (lane == 0) ? (unsigned long long)nc : 0ULL;
+                n_verified += (lane == 0) ? (unsigned)nc : 0u;
                 slow = __any_sync(FULL, over); // a position with more than cap partners: redo exactly
                 dup = __any_sync(FULL, dup);
                 __syncwarp();
@@ -515,7 +564,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 3 : 1) k_searc
                         const int i = i0 + lane;
                         nrow += __popc(__ballot_sync(FULL, i < nc && s.hits[i] != ~0ULL));
                     }
-                    n_hits += (lane == 0) ? (unsigned long long)nrow : 0ULL;
+                    n_hits += (lane == 0) ? (unsigned)nrow : 0u;
                 }
             }
             if (slow) {
@@ -538,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 3 : 1) k_searc
             const unsigned long long base = blk_cur;
             blk_cur += nrow;
             n_entries += (lane == 0) ? (unsigned long long)nrow : 0ULL;
-            if ((unsigned long long)nrow > maxdeg) maxdeg = nrow;
+            if ((unsigned)nrow > maxdeg) maxdeg = nrow;
             if (base + nrow <= p.rows_cap) {
                 if (slow) {
                     for (int i = lane; i < nrow; i += 32) p.rows[base + i] = s.row[i];
@@ -573,8 +622,8 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 3 : 1) k_searc
         warp_stat_add(p.stats, ST_ENTRIES, n_entries);
         warp_stat_add(p.stats, ST_CAP_FIRED, n_capfired);
         warp_stat_add(p.stats, ST_SLOW_READS, n_slow);
-        for (int o = 16; o; o >>= 1) { unsigned long long t = __shfl_xor_sync(FULL, maxdeg, o); if (t > maxdeg) maxdeg = t; }
-        if (lane == 0 && maxdeg) atomicMax(p.stats + ST_MAXDEG, maxdeg);
+        for (int o = 16; o; o >>= 1) { unsigned t = __shfl_xor_sync(FULL, maxdeg, o); if (t > maxdeg) maxdeg = t; }
+        if (lane == 0 && maxdeg) atomicMax(p.stats + ST_MAXDEG, (unsigned long long)maxdeg);
     }
 }
 
@@ -860,6 +909,7 @@ static int pow2_at_least(int x) { int v = 1; while (v < x) v <<= 1; return v; }
 static void size_search(SearchParams &p, int mode)
 {
     const int positions = p.reads.max_len - p.K;
+    p.npos = positions;
     if (mode == MODE_EDGES) {
         const int worst = p.cap * positions;
         p.hcap = worst < kHitCap ? worst : kHitCap;
@@ -873,9 +923,7 @@ static void size_search(SearchParams &p, int mode)
 
 static size_t search_smem_per_warp(const SearchParams &p, int mode)
 {
-    const size_t WP = wp_of(p.reads.max_len);
-    const size_t per_warp = (mode == MODE_EDGES) ? (2 * WP + p.hcap + p.rowcap + kBestMax + 2) : (2 * WP + p.hcap + 2);
-    return per_warp * sizeof(uint64_t);
+    return search_words_per_warp(wp_of(p.reads.max_len), p.npos, p.hcap, p.rowcap, mode) * sizeof(uint64_t);
 }
 
 bool search_edges_fits(int max_len, int K, int cap)
@@ -905,11 +953,14 @@ static cudaError_t launch_search(const SearchParams &p_in, int num_sms, cudaStre
         k_search<NWV, MODE><<<grid, threads, smem, s>>>(p);                          \
         break;                                                                       \
     }
-    switch (p.reads.stride) {
-    case 2: DISCO_LAUNCH(2)
-    case 4: DISCO_LAUNCH(4)
-    case 8: DISCO_LAUNCH(8)
-    case 16: DISCO_LAUNCH(16)
+    const int words = (p.reads.max_len + 31) / 32; // registers hold an even number of words >= this
+    switch (words <= 16 ? (words + 1) / 2 : 0) {
+    case 1: DISCO_LAUNCH(2)
+    case 2: DISCO_LAUNCH(4)
+    case 3: DISCO_LAUNCH(6)
+    case 4: DISCO_LAUNCH(8)
+    case 5: case 6: DISCO_LAUNCH(12)
+    case 7: case 8: DISCO_LAUNCH(16)
     default: DISCO_LAUNCH(0)
     }
 #undef DISCO_LAUNCH

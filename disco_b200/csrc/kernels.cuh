@@ -58,6 +58,7 @@ struct SearchParams {
     unsigned long long *rows_cursor;
     uint64_t *rowinfo;
     // shared-memory shape, filled in by the launcher
+    int npos;    // k-mer positions of the longest read (max_len - K)
     int hcap;    // candidate queue entries per warp
     int hset;    // neighbour-id set slots (u32, power of two)
     int rowcap;  // row buffer entries per warp (>= cap * (max_len - K), also holds the fast path's scratch)
