@@ -215,6 +215,156 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Lane-per-read variants (short reads): 32 reads per warp step, each lane owns private padded arrays in shared memory
+// (odd 32-bit stride -> conflict-free), so hashing runs with all 32 lanes busy.
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline int lane_array_u32(int max_len) { return 2 * (((max_len + 31) >> 5) + 2) + 1; } // one padded array, odd
+
+// stage this lane's read r (or nothing when !valid) into its private arrays
+__device__ __forceinline__ void stage_lane(const ReadsView &rv, uint64_t r, bool valid, int L, uint32_t *A, uint32_t *R, int WP)
+{
+    const int W = (L + 31) >> 5;
+    if (valid) {
+        const uint64_t *src = rv.words + r * (uint64_t)rv.stride;
+        pstore(A, 0, 0ULL); pstore(R, 0, 0ULL);
+        for (int w = 1; w <= W; w++) pstore(A, w, __ldg(src + (w - 1)));
+        for (int w = W + 1; w < WP; w++) { pstore(A, w, 0ULL); pstore(R, w, 0ULL); }
+        for (int w = 1; w <= W; w++) pstore(R, w, rc_word(A, L, W, w - 1));
+    }
+}
+
+// Table build, 32 reads per warp step.  Each lane hashes the prefix and suffix k-mer of its read; the 64 records are
+// then inserted eight at a time, one record per quad, cooperatively (four lanes read the four slots of the bucket --
+// one sector --, vote, the first empty lane does the CAS).
+__global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int WP = ((rv.max_len + 31) >> 5) + 2;
+    const int AU = lane_array_u32(rv.max_len);
+    uint32_t *base = reinterpret_cast<uint32_t *>(smem) + (size_t)wib * 64 * AU;
+    uint32_t *A = base + (size_t)lane * 2 * AU, *R = A + AU;
+    const int wpb = blockDim.x >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * wpb;
+    const int quad = lane >> 2, sub = lane & 3;
+    const unsigned qmask = 0xFu << (quad * 4);
+    for (uint64_t r0 = ((uint64_t)blockIdx.x * wpb + wib) * 32; r0 < rv.n; r0 += nwarps * 32) {
+        const uint64_t r = r0 + lane;
+        bool valid = r < rv.n;
+        if (valid && skip_bits) valid = !((__ldg(skip_bits + (r >> 5)) >> (r & 31)) & 1);
+        const int L = valid ? read_len(rv, r) : 0;
+        stage_lane(rv, r, valid, L, A, R, WP);
+        uint64_t h0 = 0, h1 = 0;
+        int f0 = 0, f1 = 0;
+        if (valid) {
+            // record 2r = prefix k-mer (j = 0), record 2r+1 = suffix k-mer (j = L-K): HashTable.cpp:430-431
+            h0 = canon_kmer_hash(A, R, L, 0, K, &f0);
+            h1 = canon_kmer_hash(A, R, L, L - K, K, &f1);
+            if (tv.filter) {
+                uint32_t bit = (uint32_t)(h0 >> 13) & tv.filter_mask;
+                atomicOr(tv.filter + (bit >> 5), 1u << (bit & 31));
+                bit = (uint32_t)(h1 >> 13) & tv.filter_mask;
+                atomicOr(tv.filter + (bit >> 5), 1u << (bit & 31));
+            }
+        }
+        const uint64_t v0 = make_slot(h0, f0, (uint32_t)(2 * r)), v1 = make_slot(h1, f1, (uint32_t)(2 * r + 1));
+        for (int t = 0; t < 8; t++) { // records t*8 .. t*8+7, one per quad
+            const int rec = t * 8 + quad, owner = rec >> 1;
+            // (select after the shuffle: the source lane would evaluate the selector with its own record index)
+            const uint64_t ha = __shfl_sync(FULL, h0, owner), hb = __shfl_sync(FULL, h1, owner);
+            const uint64_t va = __shfl_sync(FULL, v0, owner), vb = __shfl_sync(FULL, v1, owner);
+            const uint64_t hh = (rec & 1) ? hb : ha, val = (rec & 1) ? vb : va;
+            const int ok_rec = __shfl_sync(FULL, (int)valid, owner);
+            if (!ok_rec) continue; // uniform within the quad
+            uint64_t b = bucket_of(hh, tv.nbuckets);
+            for (;;) {
+                unsigned long long *slot = reinterpret_cast<unsigned long long *>(tv.slots) + 4 * b + sub;
+                const uint64_t cur = __ldcg(slot); // L2 (coherent) read: slots change under our feet
+                const unsigned empties = (__ballot_sync(qmask, cur == kEmptySlot) >> (quad * 4)) & 0xFu;
+                if (empties) {
+                    const int first = __ffs(empties) - 1;
+                    int ok = 0;
+                    if (sub == first) ok = atomicCAS(slot, (unsigned long long)kEmptySlot, (unsigned long long)val) == kEmptySlot;
+                    ok = __shfl_sync(qmask, ok, quad * 4 + first);
+                    if (ok) break; // otherwise somebody else took it: vote again on the same bucket
+                } else {
+                    b = (b + 1 == tv.nbuckets) ? 0 : b + 1;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Containment pass when every read has the same length L: the only feasible position is j = 0 (types 0/2 need
+// j + L <= L; types 1/3 need j >= L - K, outside [0, L-K)), i.e. contained == exact duplicate, forward or reverse
+// complement, of an earlier read (OverlapGraph.cpp:449).  One probe per read, so a lane per read; the compare is
+// word-aligned (whole read against the candidate).
+template <int NW>
+__global__ void __launch_bounds__(kThreads) k_contain_uniform(SearchParams p)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int L = p.reads.uniform_len, K = p.K;
+    const int W = (L + 31) >> 5, WP = W + 2;
+    const int AU = lane_array_u32(p.reads.max_len);
+    uint32_t *base = reinterpret_cast<uint32_t *>(smem) + (size_t)wib * 64 * AU;
+    uint32_t *A = base + (size_t)lane * 2 * AU, *R = A + AU;
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    const int wpb = blockDim.x >> 5;
+    const uint64_t nwarps = (uint64_t)gridDim.x * wpb;
+    unsigned n_queries = 0, n_probes = 0, n_buckets = 0, n_verified = 0, n_hits = 0;
+    for (uint64_t r0 = p.q_lo + ((uint64_t)blockIdx.x * wpb + wib) * 32; r0 < p.q_hi; r0 += nwarps * 32) {
+        const uint64_t r1 = r0 + lane;
+        const bool valid = r1 < p.q_hi;
+        stage_lane(p.reads, r1, valid, L, A, R, WP);
+        if (!valid) continue;
+        n_queries++; n_probes++;
+        int fq;
+        const uint64_t h = canon_kmer_hash(A, R, L, 0, K, &fq);
+        if (!filter_test(p.table, h, pol_keep)) continue; // cannot happen for a read in the table; kept for symmetry
+        const uint32_t tag = slot_tag(h);
+        uint64_t b = bucket_of(h, p.table.nbuckets);
+        for (;;) {
+            uint64_t v[4];
+            load_bucket(p.table.slots, b, v, pol_stream);
+            n_buckets++;
+            bool hole = false;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                if (v[q] == kEmptySlot) { hole = true; continue; }
+                if ((uint32_t)(v[q] >> 33) != tag) continue;
+                const uint32_t rec = (uint32_t)v[q], r2 = rec >> 1;
+                // equal lengths: read1 covers read2 only when it comes first in the file (OverlapGraph.cpp:449)
+                if (!(r1 < r2)) continue;
+                const int type = cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq);
+                if (type == 1 || type == 3) continue; // suffix-anchored types need j >= L - K
+                RegMatcher<NW> m;
+                m.stride = p.reads.stride;
+                m.load(p.reads.words, r2);
+                n_verified++;
+                const uint32_t *S = (type == 0) ? A : R; // type 0: s1 == s2 ; type 2: rc(s1) == s2
+                uint64_t diff = 0;
+#pragma unroll
+                for (int w = 0; w < NW; w++)
+                    if (w < W) diff |= pword(S, w + 1) ^ m.v[w];
+                if (diff == 0) {
+                    n_hits++;
+                    atomicMin(p.best + r2, (unsigned long long)make_ckey(r1, 0, rec & 1, type));
+                }
+            }
+            if (hole) break;
+            b = (b + 1 == p.table.nbuckets) ? 0 : b + 1;
+        }
+    }
+    warp_stat_add(p.stats, ST_QUERIES, n_queries);
+    warp_stat_add(p.stats, ST_PROBES, n_probes);
+    warp_stat_add(p.stats, ST_BUCKETS, n_buckets);
+    warp_stat_add(p.stats, ST_VERIFIED, n_verified);
+    warp_stat_add(p.stats, ST_HITS, n_hits);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // search kernels
 // ---------------------------------------------------------------------------------------------------------------
 enum { MODE_CONTAIN = 0, MODE_EDGES = 1 };
@@ -886,9 +1036,24 @@ static cudaError_t persistent_grid(Kern kern, size_t smem, int num_sms, int *gri
     return cudaSuccess;
 }
 
+constexpr size_t kLaneSmemPerWarp = 12 * 1024; // lane-per-read kernels are used while 32 private array pairs fit in this
+
 cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, const uint32_t *skip_bits,
                                 int num_sms, cudaStream_t s)
 {
+    {
+        const size_t per_warp = (size_t)64 * lane_array_u32(r.max_len) * sizeof(uint32_t);
+        if (per_warp <= kLaneSmemPerWarp) {
+            const size_t smem = per_warp * kWarps;
+            int grid = 0;
+            cudaError_t e = persistent_grid(k_table_insert_lanes, smem, num_sms, &grid);
+            if (e != cudaSuccess) return e;
+            const uint64_t need = (r.n + kWarps * 32 - 1) / (kWarps * 32);
+            if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
+            k_table_insert_lanes<<<grid, kThreads, smem, s>>>(r, t, K, skip_bits);
+            return cudaGetLastError();
+        }
+    }
     const size_t per_warp = 2 * (size_t)wp_of(r.max_len) * sizeof(uint64_t);
     const int warps = warps_that_fit(per_warp);
     if (!warps) return cudaErrorInvalidConfiguration;
@@ -967,7 +1132,34 @@ static cudaError_t launch_search(const SearchParams &p_in, int num_sms, cudaStre
     return cudaGetLastError();
 }
 
-cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStream_t s) { return launch_search<MODE_CONTAIN>(p, num_sms, s); }
+cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStream_t s)
+{
+    const size_t per_warp = (size_t)64 * lane_array_u32(p.reads.max_len) * sizeof(uint32_t);
+    const int words = (p.reads.max_len + 31) / 32;
+    if (p.reads.uniform_len && per_warp <= kLaneSmemPerWarp && words <= 16) {
+        const size_t smem = per_warp * kWarps;
+        int grid = 0;
+        cudaError_t e;
+#define DISCO_LAUNCH_CU(NWV)                                                         \
+    {                                                                                \
+        e = persistent_grid(k_contain_uniform<NWV>, smem, num_sms, &grid);           \
+        if (e != cudaSuccess) return e;                                              \
+        k_contain_uniform<NWV><<<grid, kThreads, smem, s>>>(p);                      \
+        break;                                                                       \
+    }
+        switch ((words + 1) / 2) {
+        case 1: DISCO_LAUNCH_CU(2)
+        case 2: DISCO_LAUNCH_CU(4)
+        case 3: DISCO_LAUNCH_CU(6)
+        case 4: DISCO_LAUNCH_CU(8)
+        case 5: case 6: DISCO_LAUNCH_CU(12)
+        default: DISCO_LAUNCH_CU(16)
+        }
+#undef DISCO_LAUNCH_CU
+        return cudaGetLastError();
+    }
+    return launch_search<MODE_CONTAIN>(p, num_sms, s);
+}
 cudaError_t launch_search_edges(const SearchParams &p, int num_sms, cudaStream_t s) { return launch_search<MODE_EDGES>(p, num_sms, s); }
 
 cudaError_t launch_contained_finish(const unsigned long long *best, uint64_t n, uint32_t *bits, unsigned long long *count, cudaStream_t s)
