@@ -93,7 +93,7 @@ def make_reads(n_reads, seed):
     return synth.single_genome(n_reads, READ_LEN, COVERAGE, seed=seed)
 
 
-def make_packed_on_gpu(n_reads, seed, device, wpr):
+def make_packed_on_gpu(n_reads, seed, device, wpr, workload="single"):
     """Same shape as synth.single_genome (uniform-random genome, uniform starts, strand ~ Bernoulli(1/2), error-free),
     generated and 2-bit packed with torch on the device so that the 8-GPU runs (80M reads per rank) start in seconds.
     Data generation is outside every timed region."""
@@ -102,6 +102,11 @@ def make_packed_on_gpu(n_reads, seed, device, wpr):
     g.manual_seed(seed)
     glen = max(READ_LEN + 1, int(round(n_reads * READ_LEN / COVERAGE)))
     genome = torch.randint(0, 4, (glen,), dtype=torch.uint8, device=device, generator=g)
+    n_genomes = 200 if workload == "metagenome" else 1       # config 3 shape: log-normal abundances, sigma = 1
+    gl = glen // n_genomes
+    if n_genomes > 1:
+        ab = torch.exp(torch.randn((n_genomes,), device=device, generator=g))
+        ab = ab / ab.sum()
     out = torch.zeros((n_reads, wpr), dtype=torch.int64, device=device)
     words = (READ_LEN + 31) // 32
     shifts = (62 - 2 * torch.arange(32, device=device, dtype=torch.int64))
@@ -109,7 +114,11 @@ def make_packed_on_gpu(n_reads, seed, device, wpr):
     step = 1 << 20
     for lo in range(0, n_reads, step):
         m = min(step, n_reads - lo)
-        starts = torch.randint(0, glen - READ_LEN + 1, (m,), device=device, generator=g, dtype=torch.int64)
+        if n_genomes > 1:
+            which = torch.multinomial(ab, m, replacement=True, generator=g)
+            starts = which * gl + torch.randint(0, gl - READ_LEN + 1, (m,), device=device, generator=g, dtype=torch.int64)
+        else:
+            starts = torch.randint(0, glen - READ_LEN + 1, (m,), device=device, generator=g, dtype=torch.int64)
         flip = torch.rand((m,), device=device, generator=g) < 0.5
         codes = genome[starts[:, None] + ar[None, :]]
         codes = torch.where(flip[:, None], 3 - codes.flip(1), codes).to(torch.int64)
@@ -207,7 +216,7 @@ def run_ours(args):
     n_total = args.reads * world          # weak scaling: per-GPU query share is fixed
     n = n_total
     wpr = 8                               # 64-byte rows
-    d_packed, d_lens = make_packed_on_gpu(n, 2, torch.device("cuda", local), wpr)
+    d_packed, d_lens = make_packed_on_gpu(n, 2, torch.device("cuda", local), wpr, args.workload)
     # pinned host copies (the reference-facing call takes host memory)
     h_packed = torch.empty((n, wpr), dtype=torch.int64).pin_memory()
     h_lens = torch.empty((n,), dtype=torch.int16).pin_memory()
@@ -322,7 +331,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
-        "config": {"workload": f"synthetic {n} x {READ_LEN}bp single-genome reads ({COVERAGE:.0f}x, both strands, error-free), "
+        "config": {"workload": f"synthetic {n} x {READ_LEN}bp {'single-genome' if args.workload == 'single' else '200-genome log-normal metagenome'} reads ({COVERAGE:.0f}x mean, both strands, error-free), "
                                f"minOverlap={MIN_OVERLAP}" + (f", {world} GPUs: queries sharded by read id, table+reads replicated" if world > 1 else " (BASELINE config 2 when --reads 10000000)"),
                    "reads": n, "reads_per_gpu": args.reads, "read_len": READ_LEN, "min_overlap": MIN_OVERLAP,
                    "max_edge_per_kmer": 4, "l2": "inputs larger than L2 (packed reads + table > 126 MB), no flush needed"},
@@ -355,6 +364,8 @@ def main():
     ap.add_argument("--ref-reads", type=int, default=400_000, help="reads in the bounded CPU sample")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="single", choices=["single", "metagenome"],
+                    help="single = BASELINE config 2 (headline); metagenome = config 3 shape (200 genomes, log-normal abundance)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -94,53 +94,68 @@ DHD uint64_t mix64(uint64_t h)
 // L = read length).  Canonical form = the smaller of the k-mer and its reverse complement in packed (lexicographic)
 // order -- the role getHashIndex()'s min() plays in the reference (HashTable.cpp:383-391).  *fwd_is_canon tells
 // which one won (ties -- reverse palindromes -- count as forward, matching the reference's "if / else if" typing).
+// final avalanche of the per-word multiply/xorshift chain (one multiply: the chain already mixed every word)
+DHD uint64_t finish_hash(uint64_t h)
+{
+    h ^= h >> 31; h *= 0xff51afd7ed558ccdULL;
+    h ^= h >> 29;
+    return h;
+}
+
+// K-mer of KW words (KW static): both strands in registers, decide, hash the winner
+template <int KW>
+DHD uint64_t canon_kmer_hash_kw(const uint32_t *A, const uint32_t *R, int j, int jr, uint64_t tmask, uint64_t seed, int *fwd_is_canon)
+{
+    uint64_t x[KW], y[KW];
+#pragma unroll
+    for (int i = 0; i < KW; i++) { x[i] = fetch64(A, j + 32 * i); y[i] = fetch64(R, jr + 32 * i); }
+    x[KW - 1] &= tmask; y[KW - 1] &= tmask;
+    bool fwd = true, decided = false;
+#pragma unroll
+    for (int i = 0; i < KW; i++) {
+        if (!decided && x[i] != y[i]) { fwd = x[i] < y[i]; decided = true; }
+    }
+    uint64_t h = seed;
+#pragma unroll
+    for (int i = 0; i < KW; i++) { // one multiply per word
+        h = (h ^ (fwd ? x[i] : y[i])) * 0xD6E8FEB86659FD93ULL;
+        h ^= h >> 32;
+    }
+    *fwd_is_canon = fwd;
+    return finish_hash(h);
+}
+
 DHD uint64_t canon_kmer_hash(const uint32_t *A, const uint32_t *R, int L, int j, int K, int *fwd_is_canon)
 {
     const int KW = (K + 31) >> 5;
     const int tail = K - 32 * (KW - 1);
     const uint64_t tmask = base_mask(0, tail);
     const int jr = L - j - K; // the k-mer's reverse complement starts here in rc(read)
-    uint64_t h = 0x9E3779B97F4A7C15ULL ^ (uint64_t)K;
+    const uint64_t seed = 0x9E3779B97F4A7C15ULL ^ (uint64_t)K;
+    switch (KW) { // uniform branch; the common sizes run fully unrolled in registers
+    case 1: return canon_kmer_hash_kw<1>(A, R, j, jr, tmask, seed, fwd_is_canon);
+    case 2: return canon_kmer_hash_kw<2>(A, R, j, jr, tmask, seed, fwd_is_canon);
+    case 3: return canon_kmer_hash_kw<3>(A, R, j, jr, tmask, seed, fwd_is_canon);
+    case 4: return canon_kmer_hash_kw<4>(A, R, j, jr, tmask, seed, fwd_is_canon);
+    default: break;
+    }
     int fwd = 1;
-    if (KW <= 4) {
-        // common case (K <= 128): both strands in registers, decide, then hash the winner -- no second fetch
-        uint64_t x[4], y[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (i < KW) {
-                x[i] = fetch64(A, j + 32 * i); y[i] = fetch64(R, jr + 32 * i);
-                if (i == KW - 1) { x[i] &= tmask; y[i] &= tmask; }
-            } else { x[i] = 0; y[i] = 0; }
-        }
-        bool decided = false;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (!decided && x[i] != y[i]) { fwd = x[i] < y[i]; decided = true; }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (i < KW) { // one multiply per word, full avalanche once at the end
-                h = (h ^ (fwd ? x[i] : y[i])) * 0xD6E8FEB86659FD93ULL;
-                h ^= h >> 32;
-            }
-        }
-    } else {
-        for (int i = 0; i < KW; i++) {
-            uint64_t x = fetch64(A, j + 32 * i), y = fetch64(R, jr + 32 * i);
-            if (i == KW - 1) { x &= tmask; y &= tmask; }
-            if (x != y) { fwd = x < y; break; }
-        }
-        const uint32_t *S = fwd ? A : R;
-        const int s = fwd ? j : jr;
-        for (int i = 0; i < KW; i++) {
-            uint64_t x = fetch64(S, s + 32 * i);
-            if (i == KW - 1) x &= tmask;
-            h = (h ^ x) * 0xD6E8FEB86659FD93ULL;
-            h ^= h >> 32;
-        }
+    for (int i = 0; i < KW; i++) {
+        uint64_t x = fetch64(A, j + 32 * i), y = fetch64(R, jr + 32 * i);
+        if (i == KW - 1) { x &= tmask; y &= tmask; }
+        if (x != y) { fwd = x < y; break; }
+    }
+    const uint32_t *S = fwd ? A : R;
+    const int s = fwd ? j : jr;
+    uint64_t h = seed;
+    for (int i = 0; i < KW; i++) {
+        uint64_t x = fetch64(S, s + 32 * i);
+        if (i == KW - 1) x &= tmask;
+        h = (h ^ x) * 0xD6E8FEB86659FD93ULL;
+        h ^= h >> 32;
     }
     *fwd_is_canon = fwd;
-    return mix64(h);
+    return finish_hash(h);
 }
 
 // Compare n bases: padded array P (query side) from base a, against plain word array s2 (candidate, forward strand)

@@ -12,6 +12,7 @@
 // an atomic work counter (persistent grid sized from the SM count).
 #include "dna.cuh"
 #include "kernels.cuh"
+#include <cstdlib>
 #include "../../include/disco_gpu.h"
 
 namespace disco {
@@ -594,6 +595,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
                 np += __popc(m);
             }
             __syncwarp();
+            if (p.dbg & 2) continue;
             // ---- 1b. probe: one lane per surviving position -----------------------------------------------------
             for (int i0 = 0; i0 < np; i0 += 32) {
                 const int i = i0 + lane;
@@ -651,6 +653,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
                 }
             }
             if (MODE != MODE_EDGES) continue;
+            if (p.dbg & 4) continue;
 
             const int nc = s.ctrl[0];
             bool slow = s.ctrl[1] != 0 || nc > hcap;
@@ -1104,6 +1107,7 @@ static cudaError_t launch_search(const SearchParams &p_in, int num_sms, cudaStre
 {
     SearchParams p = p_in;
     size_search(p, MODE);
+    p.dbg = getenv("DISCO_DBG") ? atoi(getenv("DISCO_DBG")) : 0;
     const size_t per_warp = search_smem_per_warp(p, MODE);
     const int warps = warps_that_fit(per_warp);
     if (!warps) return cudaErrorInvalidConfiguration;

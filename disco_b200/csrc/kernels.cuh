@@ -58,6 +58,7 @@ struct SearchParams {
     unsigned long long *rows_cursor;
     uint64_t *rowinfo;
     // shared-memory shape, filled in by the launcher
+    int dbg;     // timing ablations (env DISCO_DBG, results are then wrong): 1 no compare, 2 stop after hashing, 4 stop after probing
     int npos;    // k-mer positions of the longest read (max_len - K)
     int hcap;    // candidate queue entries per warp
     int hset;    // neighbour-id set slots (u32, power of two)
