@@ -17,7 +17,7 @@ using namespace disco;
 namespace {
 thread_local std::string g_create_error;
 
-enum Cursor { CUR_WORK = 0, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_COUNT };
+enum Cursor { CUR_WORK = 0, CUR_WORK2, CUR_WORK3, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_COUNT };
 enum Ev { EV_T0 = 0, EV_TABLE_ALL, EV_CONTAINED, EV_FINISH, EV_TABLE_NC, EV_EDGES, EV_MARK, EV_EMIT, EV_EDGES_K0, EV_EDGES_K1,
           EV_CONT_K0, EV_CONT_K1, EV_COUNT };
 } // namespace
@@ -388,7 +388,7 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
         ctx->rows_cap = want;
     }
     for (int attempt = 0;; attempt++) {
-        CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, 2 * sizeof(unsigned long long), ctx->stream)); // + CUR_ROWS
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, 4 * sizeof(unsigned long long), ctx->stream)); // 3 work counters + CUR_ROWS
         CK(cudaMemsetAsync(ctx->d_stats_e, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
         if (attempt) CK(cudaMemsetAsync(ctx->d_rowinfo + q_lo, 0, nq * sizeof(uint64_t), ctx->stream));
         p.rows = ctx->d_rows; p.rows_cap = ctx->rows_cap;
@@ -396,7 +396,7 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
         if (nq) CK(launch_search_edges(p, ctx->num_sms, ctx->stream));
         { int rc = record(ctx, EV_EDGES_K1); if (rc) return rc; }
         unsigned long long cur[2] = {0, 0}, st[ST_COUNT];
-        CK(cudaMemcpyAsync(cur, ctx->d_cursors + CUR_WORK, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(cur, ctx->d_cursors + CUR_WORK3, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream)); // [1] = CUR_ROWS
         CK(cudaMemcpyAsync(st, ctx->d_stats_e, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         ctx->rows_used = cur[1];

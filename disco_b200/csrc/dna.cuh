@@ -293,9 +293,12 @@ DHD bool chain_ok(int t1, int t2)
     return (((t1 == 0) | (t1 == 2)) & ((t2 == 0) | (t2 == 1))) | (((t1 == 1) | (t1 == 3)) & ((t2 == 2) | (t2 == 3)));
 }
 
-// row info: [63..20 first entry][19..0 degree]
+// row info: [63 exact-path pending][62 crowded position][61..20 first entry][19..0 degree]
+// (the two flag bits only live between the kernels of the edge pass; finished rows have them clear)
+constexpr uint64_t kInfoExact = 1ULL << 63;   // redo this read with the exact sequential search
+constexpr uint64_t kInfoCrowded = 1ULL << 62; // some position has more than `cap` tag matches: count per position
 DHD uint64_t make_rowinfo(uint64_t start, uint32_t deg) { return (start << 20) | deg; }
-DHD uint64_t rowinfo_start(uint64_t ri) { return ri >> 20; }
+DHD uint64_t rowinfo_start(uint64_t ri) { return (ri >> 20) & ((1ULL << 42) - 1); }
 DHD uint32_t rowinfo_deg(uint64_t ri) { return (uint32_t)(ri & 0xFFFFF); }
 
 // containment key: smallest (container, j, record kind) wins == the reference's sequential -t 1 attribution

@@ -781,6 +781,318 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Edge pass as three kernels (default).  The fused kernel above needs 64+ registers and 5 KB of shared memory per
+// warp, which caps it at 32 warps per SM while most of its time is memory latency; split, each part is small:
+//   k_edges_probe  : stage, hash, presence filter, bucket probe  -> tag matches parked in the read's (provisional)
+//                    adjacency row in global memory                                   (40 registers, 48 warps / SM)
+//   k_edges_verify : stage, load the parked candidates, lane-per-candidate overlap compare, first-hit-per-neighbour,
+//                    compact the survivors in place                                   (no table code)
+//   k_edges_exact  : the few reads flagged for the exact sequential search (cap may fire, long chains, > hcap
+//                    candidates)
+// ---------------------------------------------------------------------------------------------------------------
+__host__ __device__ inline size_t probe_words_per_warp(int WP, int npos, int hcap) { return 2 * (size_t)WP + (size_t)npos + ((size_t)npos + 1) / 2 + (size_t)hcap + 2; }
+__host__ __device__ inline size_t verify_words_per_warp(int WP, int npos, int hcap, int hset) { return 2 * (size_t)WP + (size_t)hcap + ((size_t)hset + (size_t)npos + 1) / 2 + 2; }
+__host__ __device__ inline size_t exact_words_per_warp(int WP, int rowcap) { return 2 * (size_t)WP + (size_t)rowcap + kBestMax + 2; }
+
+__global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int WP = ((p.reads.max_len + 31) >> 5) + 2;
+    const int K = p.K;
+    uint64_t *w0 = smem + wib * probe_words_per_warp(WP, p.npos, p.hcap);
+    uint32_t *A = reinterpret_cast<uint32_t *>(w0), *R = A + 2 * WP;
+    uint64_t *ph = w0 + 2 * WP;
+    uint32_t *pj = reinterpret_cast<uint32_t *>(ph + p.npos);
+    uint64_t *hits = ph + p.npos + (p.npos + 1) / 2;
+    int *ctrl = reinterpret_cast<int *>(hits + p.hcap);
+    const unsigned lt_mask = (1u << lane) - 1;
+    const uint64_t nbuckets = p.table.nbuckets;
+    const int hcap = p.hcap, cap = p.cap;
+    unsigned n_queries = 0, n_probes = 0, n_buckets = 0;
+    unsigned long long blk_cur = 0, blk_end = 0; // this warp's reserved slice of the adjacency buffer
+    const bool use_pre = p.reads.stride <= 32;
+    uint64_t pre_for = ~0ULL, pre_word = 0;
+    const uint64_t pol_stream = policy_evict_first(), pol_keep = policy_evict_last();
+    uint64_t rb, re;
+    while (grab_chunk(p.work_counter, p.q_lo, p.q_hi, lane, &rb, &re)) {
+        for (uint64_t r1 = rb; r1 < re; r1++) {
+            if ((__ldg(p.contained_bits + (r1 >> 5)) >> (r1 & 31)) & 1) continue; // OverlapGraph.cpp:657
+            const int L1 = read_len(p.reads, r1);
+            if (use_pre) {
+                const uint64_t mine = (pre_for == r1) ? pre_word : ((lane < p.reads.stride) ? __ldg(p.reads.words + r1 * (uint64_t)p.reads.stride + lane) : 0ULL);
+                if (r1 + 1 < re) { pre_for = r1 + 1; pre_word = (lane < p.reads.stride) ? __ldg(p.reads.words + (r1 + 1) * (uint64_t)p.reads.stride + lane) : 0ULL; }
+                stage_read_pre(mine, L1, A, R, WP, lane);
+            } else {
+                stage_read(p.reads, r1, L1, A, R, WP, lane);
+            }
+            n_queries += (lane == 0);
+            if (lane < 4) ctrl[lane] = 0; // [0] queued, [1] needs exact path, [3] some position has > cap candidates
+            __syncwarp();
+            const int jhi = L1 - K; // positions [1, L1-K) (OverlapGraph.cpp:638)
+            // ---- hash + presence filter: passing positions ballot-compacted, their bucket prefetched into L2
+            int np = 0;
+            for (int jb = 1; jb < jhi; jb += 32) {
+                const int j = jb + lane;
+                uint64_t h = 0;
+                int fq = 0;
+                bool pass = false;
+                if (j < jhi) {
+                    h = canon_kmer_hash(A, R, L1, j, K, &fq);
+                    n_probes++;
+                    pass = filter_test(p.table, h, pol_keep);
+                    if (pass) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table.slots + 4 * bucket_of(h, nbuckets)));
+                }
+                const unsigned m = __ballot_sync(FULL, pass);
+                if (pass) {
+                    const int pos = np + __popc(m & lt_mask);
+                    ph[pos] = h;
+                    pj[pos] = ((uint32_t)j << 1) | (uint32_t)fq;
+                }
+                np += __popc(m);
+            }
+            __syncwarp();
+            // ---- probe: one lane per surviving position
+            for (int i0 = 0; i0 < np; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < np) {
+                    const uint64_t h = ph[i];
+                    const uint32_t jf = pj[i];
+                    const int j = (int)(jf >> 1), fq = (int)(jf & 1);
+                    const uint32_t tag = slot_tag(h);
+                    uint64_t b = bucket_of(h, nbuckets);
+                    int pushed = 0;
+                    for (int walked = 0;; walked++) {
+                        if (walked == kScanLimit) { ctrl[1] = 1; break; } // long chain: exact path
+                        uint64_t v[4];
+                        load_bucket(p.table.slots, b, v, pol_stream);
+                        n_buckets++;
+                        bool hole = false;
+                        unsigned mbits = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) { // branch-free classification of the four slots
+                            const bool empty = v[q] == kEmptySlot;
+                            hole |= empty;
+                            const bool match = !empty && (uint32_t)(v[q] >> 33) == tag && ((uint32_t)v[q] >> 1) != (uint32_t)r1; // :655
+                            mbits |= (unsigned)match << q;
+                        }
+                        if (mbits) {
+                            const int cnt = __popc(mbits);
+                            int pos = atomicAdd(&ctrl[0], cnt);
+                            pushed += cnt;
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                if ((mbits >> q) & 1) {
+                                    const uint32_t rec = (uint32_t)v[q];
+                                    if (pos < hcap) hits[pos] = make_hit(j, rec, cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq));
+                                    pos++;
+                                }
+                            }
+                        }
+                        if (hole) break;
+                        b = (b + 1 == nbuckets) ? 0 : b + 1;
+                    }
+                    if (pushed > cap) ctrl[3] = 1;
+                }
+            }
+            __syncwarp();
+            // ---- park the candidates in the read's row (the verify kernel compacts the survivors in place)
+            const int nc = ctrl[0];
+            if (ctrl[1] != 0 || nc > hcap) {
+                if (lane == 0) p.rowinfo[r1] = kInfoExact;
+            } else if (nc > 0) {
+                if (blk_cur + nc > blk_end) {
+                    const unsigned long long want = nc > kRowBlock ? (unsigned long long)nc : (unsigned long long)kRowBlock;
+                    if (lane == 0) blk_cur = atomicAdd(p.rows_cursor, want);
+                    blk_cur = __shfl_sync(FULL, blk_cur, 0);
+                    blk_end = blk_cur + want;
+                }
+                const unsigned long long base = blk_cur;
+                blk_cur += nc;
+                if (base + nc <= p.rows_cap) {
+                    for (int i = lane; i < nc; i += 32) p.rows[base + i] = hits[i];
+                    if (lane == 0) p.rowinfo[r1] = make_rowinfo(base, (uint32_t)nc) | (ctrl[3] ? kInfoCrowded : 0ULL);
+                } else if (lane == 0) {
+                    atomicExch(p.stats + ST_OVERFLOW, 1ULL);
+                }
+            }
+            __syncwarp();
+        }
+    }
+    warp_stat_add(p.stats, ST_QUERIES, n_queries);
+    warp_stat_add(p.stats, ST_PROBES, n_probes);
+    warp_stat_add(p.stats, ST_BUCKETS, n_buckets);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges_verify(SearchParams p)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int WP = ((p.reads.max_len + 31) >> 5) + 2;
+    const int K = p.K;
+    WarpSmem s;
+    uint64_t *w0 = smem + wib * verify_words_per_warp(WP, p.npos, p.hcap, p.hset);
+    s.A = reinterpret_cast<uint32_t *>(w0); s.R = s.A + 2 * WP; s.p_u32 = 2 * WP;
+    s.hits = w0 + 2 * WP;
+    uint32_t *hset = reinterpret_cast<uint32_t *>(s.hits + p.hcap);
+    int *cntj = reinterpret_cast<int *>(hset + p.hset);
+    s.ctrl = reinterpret_cast<int *>(w0 + verify_words_per_warp(WP, p.npos, p.hcap, p.hset) - 2);
+    s.row = nullptr; s.best = nullptr; s.ph = nullptr; s.pj = nullptr;
+    const unsigned lt_mask = (1u << lane) - 1;
+    const int cap = p.cap;
+    unsigned n_verified = 0, n_hits = 0, maxdeg = 0;
+    unsigned long long n_entries = 0;
+    uint64_t rb, re;
+    while (grab_chunk(p.work_counter + 1, p.q_lo, p.q_hi, lane, &rb, &re)) {
+        for (uint64_t r1 = rb; r1 < re; r1++) {
+            const uint64_t ri = p.rowinfo[r1];
+            const int nc = (int)rowinfo_deg(ri);
+            if ((ri & kInfoExact) || nc == 0) continue;
+            const uint64_t start = rowinfo_start(ri);
+            const int L1 = read_len(p.reads, r1);
+            // candidates first (their rows are the long-latency loads of this kernel), then the query
+            for (int i = lane; i < nc; i += 32) {
+                const uint64_t c = p.rows[start + i];
+                s.hits[i] = c;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.reads.words + (uint64_t)hit_read(c) * (uint64_t)p.reads.stride));
+            }
+            stage_read(p.reads, r1, L1, s.A, s.R, WP, lane);
+            const bool count_pos = (ri & kInfoCrowded) != 0; // only reads with a crowded position pay for per-position counts
+            int hsz = 64;
+            while (hsz < 2 * nc) hsz <<= 1;         // <= p.hset
+            const uint32_t hm = (uint32_t)hsz - 1;
+            for (int k = lane; k < hsz; k += 32) hset[k] = 0xFFFFFFFFu;
+            if (count_pos) for (int k = lane; k < L1 - K; k += 32) cntj[k] = 0;
+            __syncwarp();
+            bool dup = false, over = false;
+            for (int i0 = 0; i0 < nc; i0 += 32) {
+                const int i = i0 + lane;
+                if (i < nc) {
+                    const uint64_t c = s.hits[i];
+                    const uint32_t r2 = hit_read(c);
+                    const bool ok = verify_dovetail<NW>(p, s, L1, hit_j(c), hit_type(c), r2);
+                    if (ok) {
+                        // first hit per neighbour: insert r2 into the warp's id set
+                        uint32_t hh = (r2 * 0x9E3779B1u) >> 7 & hm;
+                        for (;;) {
+                            const uint32_t old = atomicCAS(&hset[hh], 0xFFFFFFFFu, r2);
+                            if (old == 0xFFFFFFFFu) break;
+                            if (old == r2) { dup = true; break; }
+                            hh = (hh + 1) & hm;
+                        }
+                        if (count_pos) over |= atomicAdd(&cntj[hit_j(c)], 1) >= cap;
+                    } else {
+                        s.hits[i] = ~0ULL;
+                    }
+                }
+            }
+            n_verified += (lane == 0) ? (unsigned)nc : 0u;
+            over = __any_sync(FULL, over); // a position with more than cap partners: redo exactly
+            dup = __any_sync(FULL, dup);
+            __syncwarp();
+            if (over) {
+                if (lane == 0) p.rowinfo[r1] = kInfoExact;
+                continue;
+            }
+            if (dup) {
+                // rare (tandem repeats, circular overlaps): a neighbour reached through two positions keeps the
+                // first one in (position, record) order (OverlapGraph.cpp:656)
+                unsigned drop = 0;
+                for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++) {
+                    const int i = i0 + lane;
+                    const uint64_t hk = (i < nc) ? s.hits[i] : ~0ULL;
+                    if (hk == ~0ULL) continue;
+                    const uint32_t r2 = hit_read(hk);
+                    for (int k = 0; k < nc; k++) {
+                        const uint64_t o = s.hits[k];
+                        if (o != ~0ULL && hit_read(o) == r2 && o < hk) { drop |= 1u << rd; break; }
+                    }
+                }
+                __syncwarp();
+                for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++)
+                    if ((drop >> rd) & 1) s.hits[i0 + lane] = ~0ULL;
+                __syncwarp();
+            }
+            // survivors become adjacency entries, ballot-compacted at the front of the same row (unsorted: the
+            // reduction picks neighbours in offset order itself)
+            int off = 0;
+            for (int i0 = 0; i0 < nc; i0 += 32) {
+                const int i = i0 + lane;
+                const uint64_t hk = (i < nc) ? s.hits[i] : ~0ULL;
+                const bool valid = hk != ~0ULL;
+                const unsigned m = __ballot_sync(FULL, valid);
+                if (valid) {
+                    int orient, ovl;
+                    type_to_edge(hit_type(hk), L1, K, hit_j(hk), &orient, &ovl);
+                    p.rows[start + off + __popc(m & lt_mask)] = make_entry(L1 - ovl, hit_read(hk), orient);
+                }
+                off += __popc(m);
+            }
+            if (lane == 0) p.rowinfo[r1] = off ? make_rowinfo(start, (uint32_t)off) : 0ULL;
+            n_hits += (lane == 0) ? (unsigned)off : 0u;
+            n_entries += (lane == 0) ? (unsigned long long)off : 0ULL;
+            if ((unsigned)off > maxdeg) maxdeg = off;
+            __syncwarp();
+        }
+    }
+    warp_stat_add(p.stats, ST_VERIFIED, n_verified);
+    warp_stat_add(p.stats, ST_HITS, n_hits);
+    warp_stat_add(p.stats, ST_ENTRIES, n_entries);
+    for (int o = 16; o; o >>= 1) { unsigned t = __shfl_xor_sync(FULL, maxdeg, o); if (t > maxdeg) maxdeg = t; }
+    if (lane == 0 && maxdeg) atomicMax(p.stats + ST_MAXDEG, (unsigned long long)maxdeg);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(kThreads) k_edges_exact(SearchParams p)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int WP = ((p.reads.max_len + 31) >> 5) + 2;
+    WarpSmem s;
+    uint64_t *w0 = smem + wib * exact_words_per_warp(WP, p.rowcap);
+    s.A = reinterpret_cast<uint32_t *>(w0); s.R = s.A + 2 * WP; s.p_u32 = 2 * WP;
+    s.row = w0 + 2 * WP; s.best = s.row + p.rowcap; s.ctrl = reinterpret_cast<int *>(s.best + kBestMax);
+    s.hits = nullptr; s.ph = nullptr; s.pj = nullptr;
+    unsigned n_probes = 0, n_buckets = 0, n_verified = 0, n_capfired = 0, n_slow = 0, maxdeg = 0;
+    unsigned long long n_entries = 0;
+    uint64_t rb, re;
+    while (grab_chunk(p.work_counter + 2, p.q_lo, p.q_hi, lane, &rb, &re)) {
+        for (uint64_t r1 = rb; r1 < re; r1++) {
+            if (!(p.rowinfo[r1] & kInfoExact)) continue;
+            const int L1 = read_len(p.reads, r1);
+            stage_read(p.reads, r1, L1, s.A, s.R, WP, lane);
+            n_slow += (lane == 0);
+            search_edges_slow<NW>(p, s, r1, L1, lane, n_probes, n_buckets, n_verified, n_capfired);
+            int nrow = s.ctrl[2];
+            if (nrow > p.rowcap) nrow = p.rowcap; // cannot happen: rowcap >= cap * positions
+            unsigned long long base = 0;
+            if (lane == 0 && nrow) base = atomicAdd(p.rows_cursor, (unsigned long long)nrow);
+            base = __shfl_sync(FULL, base, 0);
+            if (nrow == 0) { if (lane == 0) p.rowinfo[r1] = 0ULL; continue; }
+            n_entries += (lane == 0) ? (unsigned long long)nrow : 0ULL;
+            if ((unsigned)nrow > maxdeg) maxdeg = nrow;
+            if (base + nrow <= p.rows_cap) {
+                for (int i = lane; i < nrow; i += 32) p.rows[base + i] = s.row[i];
+                if (lane == 0) p.rowinfo[r1] = make_rowinfo(base, (uint32_t)nrow);
+            } else if (lane == 0) {
+                p.rowinfo[r1] = 0ULL;
+                atomicExch(p.stats + ST_OVERFLOW, 1ULL);
+            }
+            __syncwarp();
+        }
+    }
+    warp_stat_add(p.stats, ST_PROBES, n_probes);
+    warp_stat_add(p.stats, ST_BUCKETS, n_buckets);
+    warp_stat_add(p.stats, ST_VERIFIED, n_verified);
+    warp_stat_add(p.stats, ST_ENTRIES, n_entries);
+    warp_stat_add(p.stats, ST_CAP_FIRED, n_capfired);
+    warp_stat_add(p.stats, ST_SLOW_READS, n_slow);
+    for (int o = 16; o; o >>= 1) { unsigned t = __shfl_xor_sync(FULL, maxdeg, o); if (t > maxdeg) maxdeg = t; }
+    if (lane == 0 && maxdeg) atomicMax(p.stats + ST_MAXDEG, (unsigned long long)maxdeg);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // containment bookkeeping
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void k_contained_finish(const unsigned long long *best, uint64_t n, uint32_t *bits, unsigned long long *count)
@@ -1164,7 +1476,48 @@ cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStre
     }
     return launch_search<MODE_CONTAIN>(p, num_sms, s);
 }
-cudaError_t launch_search_edges(const SearchParams &p, int num_sms, cudaStream_t s) { return launch_search<MODE_EDGES>(p, num_sms, s); }
+template <typename Kern>
+static cudaError_t launch_warps(Kern kern, const SearchParams &p, size_t per_warp_bytes, int num_sms, cudaStream_t s)
+{
+    const int warps = warps_that_fit(per_warp_bytes);
+    if (!warps) return cudaErrorInvalidConfiguration;
+    int grid = 0;
+    cudaError_t e = persistent_grid(kern, per_warp_bytes * warps, num_sms, &grid, warps * 32);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, warps * 32, per_warp_bytes * warps, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_search_edges(const SearchParams &p_in, int num_sms, cudaStream_t s)
+{
+    if (getenv("DISCO_FUSED")) return launch_search<MODE_EDGES>(p_in, num_sms, s); // the single-kernel variant, for A/B timing
+    SearchParams p = p_in;
+    size_search(p, MODE_EDGES);
+    const int WP = wp_of(p.reads.max_len);
+    cudaError_t e = launch_warps(k_edges_probe, p, probe_words_per_warp(WP, p.npos, p.hcap) * sizeof(uint64_t), num_sms, s);
+    if (e != cudaSuccess) return e;
+    const size_t vb = verify_words_per_warp(WP, p.npos, p.hcap, p.hset) * sizeof(uint64_t);
+    const size_t xb = exact_words_per_warp(WP, p.rowcap) * sizeof(uint64_t);
+#define DISCO_LAUNCH_E(NWV)                                                          \
+    {                                                                                \
+        e = launch_warps(k_edges_verify<NWV>, p, vb, num_sms, s);                    \
+        if (e != cudaSuccess) return e;                                              \
+        e = launch_warps(k_edges_exact<NWV>, p, xb, num_sms, s);                     \
+        break;                                                                       \
+    }
+    const int words = (p.reads.max_len + 31) / 32;
+    switch (words <= 16 ? (words + 1) / 2 : 0) {
+    case 1: DISCO_LAUNCH_E(2)
+    case 2: DISCO_LAUNCH_E(4)
+    case 3: DISCO_LAUNCH_E(6)
+    case 4: DISCO_LAUNCH_E(8)
+    case 5: case 6: DISCO_LAUNCH_E(12)
+    case 7: case 8: DISCO_LAUNCH_E(16)
+    default: DISCO_LAUNCH_E(0)
+    }
+#undef DISCO_LAUNCH_E
+    return e;
+}
 
 cudaError_t launch_contained_finish(const unsigned long long *best, uint64_t n, uint32_t *bits, unsigned long long *count, cudaStream_t s)
 {

@@ -47,7 +47,7 @@ struct SearchParams {
     int K;                 // hashStringLength = minOverlap - 1
     int cap;               // MAX_EDGE_PER_KMER
     uint64_t q_lo, q_hi;   // query reads [q_lo, q_hi)
-    unsigned long long *work_counter;
+    unsigned long long *work_counter; // [0] (and [1], [2] for the verify / exact kernels of the edge pass)
     unsigned long long *stats;
     // containment pass
     unsigned long long *best; // n keys, ~0 = not contained
