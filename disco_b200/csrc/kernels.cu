@@ -1187,10 +1187,16 @@ __global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
                     const uint64_t e = ent[k];
                     if (st[k] == 0 && e < best) { best = e; bk = k; }
                 }
-                for (int o = 16; o; o >>= 1) {
-                    const uint64_t ob = __shfl_xor_sync(FULL, best, o);
-                    const int ok = __shfl_xor_sync(FULL, bk, o);
-                    if (ob < best) { best = ob; bk = ok; }
+                {   // warp arg-min in two 32-bit hardware reductions (REDUX): offset first, then neighbour id -- one
+                    // entry per neighbour, so (offset, id) is unique
+                    const unsigned off = (best == ~0ULL) ? 0xFFFFFFFFu : (unsigned)entry_offset(best);
+                    const unsigned moff = __reduce_min_sync(FULL, off);
+                    if (moff == 0xFFFFFFFFu) break;
+                    const unsigned id = (off == moff) ? (unsigned)entry_nbr(best) : 0xFFFFFFFFu;
+                    const unsigned mid = __reduce_min_sync(FULL, id);
+                    const int src = __ffs(__ballot_sync(FULL, off == moff && id == mid)) - 1;
+                    best = __shfl_sync(FULL, best, src);
+                    bk = __shfl_sync(FULL, bk, src);
                 }
                 if (best == ~0ULL) break;
                 if (lane == 0) st[bk] = 1;
