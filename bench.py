@@ -312,21 +312,36 @@ def run_ours(args):
         dist.all_reduce(t)
         tot_raw, tot_edges = int(t[0]), int(t[1])
     peak, peak_src = measured_peak()
-    # algorithmic bytes of the dominant kernel (overlap search), SURVEY 8(d):  R + P*S + H*2S + 8*E_raw per read
-    # with R = 40 B packed read, S = 32 B sector, P probes, H candidates fetched (48-byte rows = 2 sectors), all taken
-    # from the kernel's own counters for THIS rank's launch
-    ms_k = float(np.mean([x["ms_edges_kernel"] for x in stats_acc]))
-    alg_bytes = st["queries_edges"] * 40 + st["probes_edges"] * 32 + st["verified_edges"] * 64 + st["raw_directed_edges"] * 8
-    achieved = alg_bytes / (ms_k / 1000.0) / 1e9 if ms_k > 0 else None
-    traffic = None
+    # Roofline of the dominant kernel.  The edge pass runs as k_edges_probe (hash, filter, bucket probe) and
+    # k_edges_verify (candidate fetch + overlap compare); both take about the same time, verify is the larger one and
+    # is reported as `roofline`, probe and the whole pass next to it.  Algorithmic bytes follow SURVEY 8(d)
+    # (R = 40 B packed read, S = 32 B sector, candidate rows of 48 B = 2 sectors, 8 B per parked candidate / entry),
+    # taken from the kernels' own counters of THIS rank's launch; time = CUDA events recorded on the launching stream
+    # inside the C ABI (disco_stats.ms_edges_*).
+    def mean_ms(k):
+        return float(np.mean([x[k] for x in stats_acc]))
+    ms_probe, ms_verify, ms_pass = mean_ms("ms_edges_probe"), mean_ms("ms_edges_verify"), mean_ms("ms_edges_kernel")
+    q, pr, bk, vf, en = st["queries_edges"], st["probes_edges"], st["buckets_edges"], st["verified_edges"], st["raw_directed_edges"]
+    alg_probe = q * 40 + pr * 4 + bk * 32 + vf * 8                 # read, 1 filter word per probe, buckets, parked candidates
+    alg_verify = q * 40 + vf * 8 + vf * 64 + en * 8                # read, parked candidates, candidate rows, adjacency entries
+    alg_pass = q * 40 + pr * 32 + vf * 64 + en * 8                 # R + P*S + H*2S + 8*E_raw
+    peak, peak_src = measured_peak()
+
+    def roof(name, alg, ms, traffic=None):
+        ach = alg / (ms / 1000.0) / 1e9 if ms > 0 else None
+        return {"bound": "hbm", "kernel": name, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": (ach / peak) if ach else None,
+                "traffic": traffic, "peak_source": peak_src, "ms_per_launch": ms, "algorithmic_bytes_per_launch": int(alg)}
+    traffic = {}
     tp = os.path.join(ROOT, "profiles", "traffic_search_edges.json")
     if os.path.exists(tp):
         try:
             tj = json.load(open(tp))
             if int(tj.get("reads", -1)) == n and world == 1:
-                traffic = tj["dram_bytes_per_launch"]  # dram__bytes_read.sum + dram__bytes_write.sum, one ncu --set full capture
+                traffic = tj["dram_bytes_per_launch"]  # dram__bytes_read.sum + dram__bytes_write.sum per kernel, ncu
         except Exception:
             pass
+    if ms_verify <= 0:   # fused single-kernel variant (DISCO_FUSED)
+        ms_verify, alg_verify = ms_pass, alg_pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
@@ -337,11 +352,14 @@ def run_ours(args):
                    "max_edge_per_kmer": 4, "l2": "inputs larger than L2 (packed reads + table > 126 MB), no flush needed"},
         "e2e": {"value": n / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e},
-        "gpu_launches": int(8 * args.steps),
+        "gpu_launches": int(10 * args.steps),
         "clocks": clk.summary(),
-        "roofline": {"bound": "hbm", "kernel": "k_search<EDGES>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": peak_src,
-                     "ms_per_launch": ms_k, "algorithmic_bytes_per_launch": int(alg_bytes)},
+        "roofline": roof("k_edges_verify", alg_verify, ms_verify, traffic.get("k_edges_verify") if isinstance(traffic, dict) else None),
+        "roofline_probe": roof("k_edges_probe", alg_probe, ms_probe, traffic.get("k_edges_probe") if isinstance(traffic, dict) else None),
+        "roofline_edge_pass": roof("k_edges_probe+k_edges_verify+k_edges_exact", alg_pass, ms_pass,
+                                   traffic.get("edge_pass") if isinstance(traffic, dict) else None),
+        "random_access_peak": {"accesses_per_s": 39.4e9, "source": "profiles/gather_bench.cu on B200: 39.4 G independent <=128 B line accesses/s",
+                               "edge_pass_accesses_per_s": (bk + vf) / (ms_pass / 1000.0) if ms_pass > 0 else None},
         "edges_per_s": {"raw_directed": tot_raw / (ms_step / 1000.0), "reduced": tot_edges / (ms_step / 1000.0)},
         "phase_ms": {k: float(np.mean([s[k] for s in stats_acc])) for k in st if k.startswith("ms_")},
         "counters": {k: int(v) for k, v in st.items() if not k.startswith("ms_")},

@@ -19,7 +19,7 @@ thread_local std::string g_create_error;
 
 enum Cursor { CUR_WORK = 0, CUR_WORK2, CUR_WORK3, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_COUNT };
 enum Ev { EV_T0 = 0, EV_TABLE_ALL, EV_CONTAINED, EV_FINISH, EV_TABLE_NC, EV_EDGES, EV_MARK, EV_EMIT, EV_EDGES_K0, EV_EDGES_K1,
-          EV_CONT_K0, EV_CONT_K1, EV_COUNT };
+          EV_CONT_K0, EV_CONT_K1, EV_PROBE_K1, EV_VERIFY_K1, EV_COUNT };
 } // namespace
 
 struct disco_ctx {
@@ -393,7 +393,10 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
         if (attempt) CK(cudaMemsetAsync(ctx->d_rowinfo + q_lo, 0, nq * sizeof(uint64_t), ctx->stream));
         p.rows = ctx->d_rows; p.rows_cap = ctx->rows_cap;
         { int rc = record(ctx, EV_EDGES_K0); if (rc) return rc; }
-        if (nq) CK(launch_search_edges(p, ctx->num_sms, ctx->stream));
+        if (nq) {
+            CK(launch_search_edges(p, ctx->num_sms, ctx->stream, ctx->ev[EV_PROBE_K1], ctx->ev[EV_VERIFY_K1]));
+            ctx->ev_done[EV_PROBE_K1] = ctx->ev_done[EV_VERIFY_K1] = !getenv("DISCO_FUSED");
+        }
         { int rc = record(ctx, EV_EDGES_K1); if (rc) return rc; }
         unsigned long long cur[2] = {0, 0}, st[ST_COUNT];
         CK(cudaMemcpyAsync(cur, ctx->d_cursors + CUR_WORK3, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream)); // [1] = CUR_ROWS
@@ -555,6 +558,8 @@ int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out)
     s.ms_edges = ms(EV_TABLE_NC, EV_EDGES); s.ms_mark = ms(EV_EDGES, EV_MARK); s.ms_emit = ms(EV_MARK, EV_EMIT);
     s.ms_total = ms(EV_T0, EV_EMIT);
     s.ms_edges_kernel = ms(EV_EDGES_K0, EV_EDGES_K1); s.ms_contained_kernel = ms(EV_CONT_K0, EV_CONT_K1);
+    s.ms_edges_probe = ms(EV_EDGES_K0, EV_PROBE_K1); s.ms_edges_verify = ms(EV_PROBE_K1, EV_VERIFY_K1);
+    s.ms_edges_exact = ms(EV_VERIFY_K1, EV_EDGES_K1);
     *out = s;
     return DISCO_OK;
 }

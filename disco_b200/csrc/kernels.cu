@@ -1494,7 +1494,7 @@ static cudaError_t launch_warps(Kern kern, const SearchParams &p, size_t per_war
     return cudaGetLastError();
 }
 
-cudaError_t launch_search_edges(const SearchParams &p_in, int num_sms, cudaStream_t s)
+cudaError_t launch_search_edges(const SearchParams &p_in, int num_sms, cudaStream_t s, cudaEvent_t ev_probe_done, cudaEvent_t ev_verify_done)
 {
     if (getenv("DISCO_FUSED")) return launch_search<MODE_EDGES>(p_in, num_sms, s); // the single-kernel variant, for A/B timing
     SearchParams p = p_in;
@@ -1502,12 +1502,14 @@ cudaError_t launch_search_edges(const SearchParams &p_in, int num_sms, cudaStrea
     const int WP = wp_of(p.reads.max_len);
     cudaError_t e = launch_warps(k_edges_probe, p, probe_words_per_warp(WP, p.npos, p.hcap) * sizeof(uint64_t), num_sms, s);
     if (e != cudaSuccess) return e;
+    if (ev_probe_done) cudaEventRecord(ev_probe_done, s);
     const size_t vb = verify_words_per_warp(WP, p.npos, p.hcap, p.hset) * sizeof(uint64_t);
     const size_t xb = exact_words_per_warp(WP, p.rowcap) * sizeof(uint64_t);
 #define DISCO_LAUNCH_E(NWV)                                                          \
     {                                                                                \
         e = launch_warps(k_edges_verify<NWV>, p, vb, num_sms, s);                    \
         if (e != cudaSuccess) return e;                                              \
+        if (ev_verify_done) cudaEventRecord(ev_verify_done, s);                      \
         e = launch_warps(k_edges_exact<NWV>, p, xb, num_sms, s);                     \
         break;                                                                       \
     }

@@ -82,7 +82,9 @@ struct ReduceParams {
 cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, const uint32_t *skip_bits,
                                 int num_sms, cudaStream_t s);
 cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStream_t s);
-cudaError_t launch_search_edges(const SearchParams &p, int num_sms, cudaStream_t s);
+// ev_probe_done / ev_verify_done (optional) are recorded after the probe and verify kernels of the edge pass
+cudaError_t launch_search_edges(const SearchParams &p, int num_sms, cudaStream_t s, cudaEvent_t ev_probe_done = nullptr,
+                                cudaEvent_t ev_verify_done = nullptr);
 cudaError_t launch_contained_finish(const unsigned long long *best, uint64_t n, uint32_t *bits,
                                     unsigned long long *count, cudaStream_t s);
 // rows for contained reads: keys -> (contained, container, orient, start), compacted in read order

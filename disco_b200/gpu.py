@@ -29,7 +29,7 @@ class Stats(C.Structure):
         "verified_contained", "verified_edges", "max_degree", "reduce_rows_fetched", "reduce_entries_fetched",
         "table_buckets", "edge_capacity", "queries_contained", "queries_edges")] + [(n, C.c_float) for n in (
             "ms_table_all", "ms_contained", "ms_finish_contained", "ms_table_nc", "ms_edges", "ms_mark", "ms_emit", "ms_total",
-            "ms_edges_kernel", "ms_contained_kernel")]
+            "ms_edges_kernel", "ms_contained_kernel", "ms_edges_probe", "ms_edges_verify", "ms_edges_exact")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}

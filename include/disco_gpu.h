@@ -70,7 +70,8 @@ typedef struct {
     uint64_t queries_contained, queries_edges;    /* reads searched by this context's launches */
     /* device time of the last disco_gpu_build_graph(), CUDA events on the context's stream, milliseconds */
     float ms_table_all, ms_contained, ms_finish_contained, ms_table_nc, ms_edges, ms_mark, ms_emit, ms_total;
-    float ms_edges_kernel, ms_contained_kernel; /* the two search kernels alone */
+    float ms_edges_kernel, ms_contained_kernel; /* the search kernels alone (edge pass = probe + verify + exact) */
+    float ms_edges_probe, ms_edges_verify, ms_edges_exact; /* the three kernels of the edge pass */
 } disco_stats;
 
 /* ---- life cycle ---------------------------------------------------------------------------------------------- */
