@@ -583,6 +583,39 @@ int disco_gpu_rebase_rows(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi, uint64_t
     return DISCO_OK;
 }
 
+int disco_gpu_reserve_rows(disco_ctx *ctx, uint64_t n_entries)
+{
+    if (!ctx || !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass not finished");
+    CK(cudaSetDevice(ctx->device));
+    if (n_entries <= ctx->rows_cap) return DISCO_OK;
+    uint64_t *nr = nullptr;
+    CK(cudaMalloc(&nr, n_entries * sizeof(uint64_t)));
+    if (ctx->rows_used) CK(cudaMemcpyAsync(nr, ctx->d_rows, ctx->rows_used * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    dfree(ctx->d_rows);
+    ctx->d_rows = nr;
+    ctx->rows_cap = n_entries;
+    ctx->stats.edge_capacity = n_entries;
+    return DISCO_OK;
+}
+
+int disco_gpu_move_rows(disco_ctx *ctx, uint64_t dst_offset)
+{
+    if (!ctx || !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass not finished");
+    if (dst_offset == 0 || ctx->rows_used == 0) return DISCO_OK;
+    if (dst_offset < ctx->rows_used || dst_offset + ctx->rows_used > ctx->rows_cap) return fail(ctx, DISCO_E_ARG, "move_rows: bad destination");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(ctx->d_rows + dst_offset, ctx->d_rows, ctx->rows_used * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    return DISCO_OK;
+}
+
+int disco_gpu_set_rows_used(disco_ctx *ctx, uint64_t n_entries)
+{
+    if (!ctx || n_entries > ctx->rows_cap) return fail(ctx, DISCO_E_ARG, "set_rows_used: beyond capacity");
+    ctx->rows_used = n_entries;
+    return DISCO_OK;
+}
+
 int disco_gpu_adopt_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entries)
 {
     if (!ctx || !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass not finished");

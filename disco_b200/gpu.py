@@ -18,7 +18,8 @@ EXPORTS = [
     "disco_gpu_get_edges", "disco_gpu_get_row", "disco_gpu_get_stats", "disco_gpu_begin", "disco_gpu_phase_table",
     "disco_gpu_phase_contained", "disco_gpu_phase_finish_contained", "disco_gpu_phase_edges", "disco_gpu_phase_reduce",
     "disco_gpu_dev_contained_keys", "disco_gpu_dev_rowinfo", "disco_gpu_dev_rows", "disco_gpu_rebase_rows",
-    "disco_gpu_adopt_rows", "disco_gpu_set_max_degree", "disco_gpu_sync",
+    "disco_gpu_adopt_rows", "disco_gpu_set_max_degree", "disco_gpu_sync", "disco_gpu_reserve_rows", "disco_gpu_move_rows",
+    "disco_gpu_set_rows_used",
 ]
 
 
@@ -77,6 +78,9 @@ def lib():
         L.disco_gpu_rebase_rows.argtypes = [vp, u64, u64, u64]
         L.disco_gpu_adopt_rows.argtypes = [vp, vp, u64]
         L.disco_gpu_set_max_degree.argtypes = [vp, u64]
+        L.disco_gpu_reserve_rows.argtypes = [vp, u64]
+        L.disco_gpu_move_rows.argtypes = [vp, u64]
+        L.disco_gpu_set_rows_used.argtypes = [vp, u64]
         L.disco_gpu_sync.argtypes = [vp]
         _lib = L
     return _lib
@@ -171,6 +175,15 @@ class GpuBuildGraph:
 
     def adopt_rows(self, d_rows_ptr: int, n_entries: int):
         self._ck(self._L.disco_gpu_adopt_rows(self._h, C.c_void_p(d_rows_ptr), n_entries), "adopt_rows")
+
+    def reserve_rows(self, n_entries: int):
+        self._ck(self._L.disco_gpu_reserve_rows(self._h, n_entries), "reserve_rows")
+
+    def move_rows(self, dst_offset: int):
+        self._ck(self._L.disco_gpu_move_rows(self._h, dst_offset), "move_rows")
+
+    def set_rows_used(self, n_entries: int):
+        self._ck(self._L.disco_gpu_set_rows_used(self._h, n_entries), "set_rows_used")
 
     def set_max_degree(self, d: int):
         self._ck(self._L.disco_gpu_set_max_degree(self._h, d), "set_max_degree")

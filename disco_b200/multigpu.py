@@ -5,7 +5,7 @@ Partitioning = the reference's BuildGraphMPI ("distributed computation": src/Bui
 Where the MPI code gossips `int[numReads+1]` maps every few seconds (OverlapGraph.cpp:566-575, :225-234), the offline
 formulation needs exactly two exchanges:
   1. containment keys  u64[n]  all-reduce(MIN)   -> every rank derives the same contained set and rows
-  2. adjacency         row info u64[n] all-reduce(SUM) + rows all-gather (variable length, by broadcast)
+  2. adjacency         row info u64[n] all-reduce(SUM) + rows all-gather (in place, one slot per rank)
 after which each rank reduces and emits the edges whose lower endpoint lies in its range (its shard of parGraph).
 """
 import torch
@@ -29,12 +29,23 @@ class GpuTensors:
     def rowinfo(self):
         return torch.as_tensor(_DevArray(self.g.dev_rowinfo(), self.g.n), device=self.device)
 
-    def rows(self):
-        ptr, used = self.g.dev_rows()
-        return torch.as_tensor(_DevArray(ptr, used), device=self.device) if used else torch.empty(0, dtype=torch.int64, device=self.device)
+    def rows_used(self):
+        return self.g.dev_rows()[1]
 
-    def adopt_rows(self, t):
-        self.g.adopt_rows(t.data_ptr(), t.numel())
+    def reserve_rows(self, n):
+        self.g.reserve_rows(n)
+
+    def move_rows(self, dst):
+        self.g.move_rows(dst)
+
+    def rebase_rows(self, lo, hi, base):
+        self.g.rebase_rows(lo, hi, base)
+
+    def rows_buffer(self, n):
+        return torch.as_tensor(_DevArray(self.g.dev_rows()[0], n), device=self.device)
+
+    def set_rows_used(self, n):
+        self.g.set_rows_used(n)
 
 
 def partition(n: int, rank: int, world: int):
@@ -52,28 +63,26 @@ def allreduce_unsigned_min(keys: torch.Tensor, group=None):
     return keys
 
 
-def exchange_adjacency(local_rows: torch.Tensor, max_degree: int, rebase, rowinfo: torch.Tensor, rank: int, world: int, group=None):
-    """All ranks end up with the concatenation (rank order) of everybody's rows and a row-info array that points into
-    it.  `rebase(base)` must add `base` to the start field of this rank's row-info entries before the SUM."""
-    dev = local_rows.device
-    meta = torch.tensor([local_rows.numel(), max_degree], device=dev, dtype=torch.int64)
+def exchange_adjacency(t, max_degree: int, lo: int, hi: int, rank: int, world: int, group=None):
+    """All ranks end up with every rank's rows in one common layout -- rank r's rows at [r * slot, r * slot + count_r),
+    slot = the largest count -- and a row-info array that points into it.  One in-place all-gather (each rank
+    contributes its own slot of the shared buffer) instead of per-rank broadcasts; no staging copy."""
+    used = t.rows_used()
+    dev = t.device
+    meta = torch.tensor([used, max_degree], device=dev, dtype=torch.int64)
     allm = [torch.empty_like(meta) for _ in range(world)]
     dist.all_gather(allm, meta, group=group)
     counts = [int(m[0]) for m in allm]
     maxdeg = max(int(m[1]) for m in allm)
-    bases = [0]
-    for c in counts[:-1]:
-        bases.append(bases[-1] + c)
-    total = bases[-1] + counts[-1]
-    rebase(bases[rank])
-    dist.all_reduce(rowinfo, op=dist.ReduceOp.SUM, group=group)  # entries of rows owned by other ranks are zero here
-    big = torch.empty(max(total, 1), dtype=torch.int64, device=dev)
-    if counts[rank]:
-        big[bases[rank]:bases[rank] + counts[rank]].copy_(local_rows)
-    for r in range(world):
-        if counts[r]:
-            dist.broadcast(big[bases[r]:bases[r] + counts[r]], src=r, group=group)
-    return big[:total], maxdeg, bases, counts
+    slot = max(max(counts), 1)
+    t.reserve_rows(world * slot)
+    t.move_rows(rank * slot)                   # this rank's rows from the front of the buffer into its slot
+    t.rebase_rows(lo, hi, rank * slot)
+    dist.all_reduce(t.rowinfo(), op=dist.ReduceOp.SUM, group=group)  # entries of rows owned by other ranks are zero here
+    buf = t.rows_buffer(world * slot)
+    dist.all_gather_into_tensor(buf, buf[rank * slot:(rank + 1) * slot], group=group)
+    t.set_rows_used(world * slot)
+    return maxdeg, slot, counts
 
 
 class ShardedBuildGraph:
@@ -91,9 +100,7 @@ class ShardedBuildGraph:
         g.phase_finish_contained()
         g.phase_table(True)
         g.phase_edges(lo, hi)
-        big, maxdeg, _, _ = exchange_adjacency(self.t.rows(), int(g.stats()["max_degree"]), lambda base: g.rebase_rows(lo, hi, base),
-                                               self.t.rowinfo(), self.rank, self.world, self.group)
-        self.t.adopt_rows(big)
+        maxdeg, _, _ = exchange_adjacency(self.t, int(g.stats()["max_degree"]), lo, hi, self.rank, self.world, self.group)
         g.set_max_degree(maxdeg)
         g.phase_reduce(lo, hi)
         g.sync()

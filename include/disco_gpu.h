@@ -118,9 +118,16 @@ int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi);
 void *disco_gpu_dev_contained_keys(disco_ctx *ctx);
 void *disco_gpu_dev_rowinfo(disco_ctx *ctx);
 void *disco_gpu_dev_rows(disco_ctx *ctx, uint64_t *n_entries);
-/* Replace the adjacency by a gathered one: rows u64[n_entries] on this device (copied), row info already reduced
- * in place.  rebase adds `base` to the start of every local row in [u_lo,u_hi) before the exchange. */
+/* Adjacency exchange helpers.  Common layout on every rank: rank r's rows live at [r * slot, r * slot + count_r).
+ *   reserve_rows : make the adjacency buffer hold at least n_entries (contents kept)
+ *   move_rows    : move this rank's rows from the front of the buffer to dst_offset (regions may not overlap)
+ *   rebase_rows  : add `base` to the start of every local row in [u_lo,u_hi) (before the row-info all-reduce)
+ *   set_rows_used: entries in use after the gather
+ *   adopt_rows   : alternative: replace the adjacency by a copy of d_rows[n_entries] */
+int disco_gpu_reserve_rows(disco_ctx *ctx, uint64_t n_entries);
+int disco_gpu_move_rows(disco_ctx *ctx, uint64_t dst_offset);
 int disco_gpu_rebase_rows(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi, uint64_t base);
+int disco_gpu_set_rows_used(disco_ctx *ctx, uint64_t n_entries);
 int disco_gpu_adopt_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entries);
 /* largest row length over all ranks (sizes the reduction kernel's shared memory) */
 int disco_gpu_set_max_degree(disco_ctx *ctx, uint64_t max_degree);
