@@ -67,21 +67,41 @@ def exchange_adjacency(t, max_degree: int, lo: int, hi: int, rank: int, world: i
     """All ranks end up with every rank's rows in one common layout -- rank r's rows at [r * slot, r * slot + count_r),
     slot = the largest count -- and a row-info array that points into it.  One in-place all-gather (each rank
     contributes its own slot of the shared buffer) instead of per-rank broadcasts; no staging copy."""
+    import os
+    trace = os.environ.get("DISCO_TRACE_EXCHANGE") and rank == 0
+    marks = []
+
+    def mark(name):
+        if trace:
+            e = torch.cuda.Event(enable_timing=True); e.record(); marks.append((name, e))
     used = t.rows_used()
     dev = t.device
+    mark("start")
     meta = torch.tensor([used, max_degree], device=dev, dtype=torch.int64)
     allm = [torch.empty_like(meta) for _ in range(world)]
     dist.all_gather(allm, meta, group=group)
     counts = [int(m[0]) for m in allm]
     maxdeg = max(int(m[1]) for m in allm)
+    # slot = largest count plus 2% head room: the counts jitter from step to step (warp-private slices), and a slot
+    # that grows by a few entries must not trigger a reallocation of the whole buffer
     slot = max(max(counts), 1)
+    slot += slot // 50 + 1024
+    mark("counts")
     t.reserve_rows(world * slot)
+    mark("reserve")
     t.move_rows(rank * slot)                   # this rank's rows from the front of the buffer into its slot
     t.rebase_rows(lo, hi, rank * slot)
+    mark("move+rebase")
     dist.all_reduce(t.rowinfo(), op=dist.ReduceOp.SUM, group=group)  # entries of rows owned by other ranks are zero here
+    mark("rowinfo all-reduce")
     buf = t.rows_buffer(world * slot)
     dist.all_gather_into_tensor(buf, buf[rank * slot:(rank + 1) * slot], group=group)
+    mark("rows all-gather")
     t.set_rows_used(world * slot)
+    if trace:
+        torch.cuda.synchronize()
+        print("exchange:", ", ".join(f"{b[0]} {a[1].elapsed_time(b[1]):.2f} ms" for a, b in zip(marks, marks[1:])),
+              f"| slot {slot} entries, {world * slot * 8 / 1e9:.2f} GB gathered", flush=True)
     return maxdeg, slot, counts
 
 

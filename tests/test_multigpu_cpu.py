@@ -112,6 +112,7 @@ def test_sharded_exchange_gloo(world):
     keys = np.stack([_keys_for(r, *parts[r]) for r in range(world)]).view(np.uint64).min(axis=0).view(np.int64)
     rows, infos, mds = zip(*[_rows_for(r, *parts[r]) for r in range(world)])
     slot = max(max(len(x) for x in rows), 1)
+    slot += slot // 50 + 1024   # head room, see multigpu.exchange_adjacency
     for rank, k, info, adopted, md, log in res:
         assert np.array_equal(k, keys)
         assert len(adopted) == world * slot
