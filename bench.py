@@ -239,9 +239,22 @@ def run_ours(args):
     h_edges = None
     h_crows = None
 
+    d_in_packed = torch.empty_like(d_packed) if world > 1 else None
+    d_in_lens = torch.empty_like(d_lens) if world > 1 else None
+
     def e2e_step():
         nonlocal h_edges, h_crows
-        g.load_reads_ptr(h_packed.data_ptr(), h_lens.data_ptr(), n, wpr)
+        if world > 1:
+            # every rank uploads only its own shard of the packed reads over PCIe and the shards are all-gathered over
+            # NVLink (the read set is replicated on every GPU in this partitioning)
+            d_in_packed[lo:hi].copy_(h_packed[lo:hi], non_blocking=True)
+            d_in_lens[lo:hi].copy_(h_lens[lo:hi], non_blocking=True)
+            dist.all_gather_into_tensor(d_in_packed.view(-1), d_in_packed[lo:hi].view(-1))
+            lb = d_in_lens.view(torch.uint8)   # NCCL has no int16
+            dist.all_gather_into_tensor(lb, lb[2 * lo:2 * hi])
+            g.load_reads_device(d_in_packed.data_ptr(), d_in_lens.data_ptr(), n, wpr, READ_LEN, READ_LEN)
+        else:
+            g.load_reads_ptr(h_packed.data_ptr(), h_lens.data_ptr(), n, wpr)
         if runner:
             runner.build_graph(MIN_OVERLAP, 4)
         else:
@@ -302,7 +315,7 @@ def run_ours(args):
         e2e_step()
     ms_e2e, (ne_out, nc_out) = timed(e2e_step, args.steps)
     ms_e2e /= args.steps
-    h2d = h_packed.numel() * 8 + h_lens.numel() * 2
+    h2d = (h_packed.numel() * 8 + h_lens.numel() * 2) // world   # per rank: its shard (N > 1) or everything (N = 1)
     d2h = (ne_out + nc_out) * 16
 
     st = stats_acc[-1]
