@@ -117,6 +117,37 @@ struct RegMatcher<0> {
     __device__ __forceinline__ bool operator()(const uint32_t *P, int a, int b, int n, int) const { return m(P, a, b, n); }
 };
 
+// Verify-kernel compare: the candidate's words are parked in shared memory, transposed (word w of lane l at
+// cw[w * 32 + l], conflict-free), so that the compare is a plain loop over exactly the words the overlap touches --
+// no per-word range selects, no unrolling over the longest read.
+struct SmemMatcher {
+    const uint64_t *cw; // + lane already applied
+    __device__ __forceinline__ uint64_t word(int w) const { return cw[w * 32]; }
+    __device__ __forceinline__ bool operator()(const uint32_t *P, int a, int b, int n) const
+    {
+        const int q0 = a - b + 32;           // query base (in padded coordinates) facing candidate base 0
+        const int sh = (q0 & 15) * 2;
+        const int wlo = b >> 5, whi = (b + n - 1) >> 5;
+        const uint32_t *q = P + ((q0 >> 4) + 2 * wlo);
+        uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+        uint64_t x = (((uint64_t)fsl32(w1, w0, sh) << 32) | fsl32(w2, w1, sh)) ^ word(wlo);
+        x &= ~0ULL >> (2 * (b & 31));                       // first word: bases before b do not count
+        const int tb = (b + n) & 31;
+        const uint64_t tail = tb ? ~(~0ULL >> (2 * tb)) : ~0ULL;
+        if (wlo == whi) return (x & tail) == 0;
+        uint64_t diff = x;
+        for (int w = wlo + 1; w < whi; w++) {
+            q += 2;
+            w0 = w2; w1 = q[1]; w2 = q[2];
+            diff |= (((uint64_t)fsl32(w1, w0, sh) << 32) | fsl32(w2, w1, sh)) ^ word(w);
+        }
+        q += 2;
+        w0 = w2; w1 = q[1]; w2 = q[2];
+        x = (((uint64_t)fsl32(w1, w0, sh) << 32) | fsl32(w2, w1, sh)) ^ word(whi);
+        return (diff | (x & tail)) == 0;
+    }
+};
+
 // stage read r into the warp's padded arrays A (forward) and R (reverse complement); WP = words(max_len) + 2 padded
 // words per array (stored as base-ordered 32-bit halves, see dna.cuh)
 __device__ __forceinline__ void stage_read(const ReadsView &rv, uint64_t r, int L, uint32_t *A, uint32_t *R, int WP, int lane)
@@ -791,7 +822,11 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
 //                    candidates)
 // ---------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t probe_words_per_warp(int WP, int npos, int hcap) { return 2 * (size_t)WP + (size_t)npos + ((size_t)npos + 1) / 2 + (size_t)hcap + 2; }
-__host__ __device__ inline size_t verify_words_per_warp(int WP, int npos, int hcap, int hset) { return 2 * (size_t)WP + (size_t)hcap + ((size_t)hset + (size_t)npos + 1) / 2 + 2; }
+__host__ __device__ inline size_t verify_words_per_warp(int WP, int npos, int hcap, int hset)
+{   // A, R, candidate queue, id set + per-position counters, transposed candidate words (32 x up to 16), control
+    const int nw = WP - 2 <= 16 ? ((WP - 2 + 1) / 2) * 2 : 0;
+    return 2 * (size_t)WP + (size_t)hcap + ((size_t)hset + (size_t)npos + 1) / 2 + (size_t)32 * nw + 2;
+}
 __host__ __device__ inline size_t exact_words_per_warp(int WP, int rowcap) { return 2 * (size_t)WP + (size_t)rowcap + kBestMax + 2; }
 
 __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
@@ -938,6 +973,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
     uint32_t *hset = reinterpret_cast<uint32_t *>(s.hits + p.hcap);
     int *cntj = reinterpret_cast<int *>(hset + p.hset);
     s.ctrl = reinterpret_cast<int *>(w0 + verify_words_per_warp(WP, p.npos, p.hcap, p.hset) - 2);
+    uint64_t *cw = w0 + 2 * WP + p.hcap + (p.hset + p.npos + 1) / 2 + lane; // transposed candidate words, this lane's column
     s.row = nullptr; s.best = nullptr; s.ph = nullptr; s.pj = nullptr;
     const unsigned lt_mask = (1u << lane) - 1;
     const int cap = p.cap;
@@ -971,7 +1007,20 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
                 if (i < nc) {
                     const uint64_t c = s.hits[i];
                     const uint32_t r2 = hit_read(c);
-                    const bool ok = verify_dovetail<NW>(p, s, L1, hit_j(c), hit_type(c), r2);
+                    bool ok;
+                    if (NW == 0) {
+                        ok = verify_dovetail<NW>(p, s, L1, hit_j(c), hit_type(c), r2);
+                    } else {
+                        RegMatcher<(NW > 0 ? NW : 2)> m;
+                        m.stride = p.reads.stride;
+                        m.load(p.reads.words, r2);
+                        const int L2 = read_len(p.reads, r2);
+#pragma unroll
+                        for (int w = 0; w < (NW > 0 ? NW : 2); w++) cw[w * 32] = m.v[w];
+                        int use_rc, a, b, n;
+                        ok = dovetail_window(hit_type(c), L1, hit_j(c), K, L2, &use_rc, &a, &b, &n) &&
+                             SmemMatcher{cw}(use_rc ? s.R : s.A, a, b, n);
+                    }
                     if (ok) {
                         // first hit per neighbour: insert r2 into the warp's id set
                         uint32_t hh = (r2 * 0x9E3779B1u) >> 7 & hm;
