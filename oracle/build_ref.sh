@@ -35,3 +35,18 @@ GZ=""
 if echo '#include <zlib.h>' | g++ -x c++ -fsyntax-only - 2>/dev/null; then GZ="-DINCLUDE_READGZ"; GZL="-lz"; else GZL=""; fi
 g++ $GZ -Wno-sign-compare -fopenmp -std=c++11 -O3 -w -o "$OUT/buildG" "$TMP"/*.cpp $GZL
 echo "build_ref: built $OUT/buildG"
+
+# The first consumer of the hot path's files: parsimplify (src/SimplifyGraph), used only to check that our
+# files are accepted and lead to the same contracted graph.  Same treatment: scratch copy, compile fixes only
+# (SSTR in Config.h:47 and OverlapGraphSimple.h:17, missing <cstdint> in Utils.cpp).
+SG="${DISCO_REFERENCE:-/root/reference}/src/SimplifyGraph/src"
+TMP2="$(mktemp -d /tmp/disco_ref_build2.XXXXXX)"
+trap 'rm -rf "$TMP" "$TMP2"' EXIT
+cp -r "$SG"/. "$TMP2"/
+chmod -R u+w "$TMP2"
+for f in Config.h OverlapGraphSimple.h; do
+  sed -i 's|^#define SSTR( x ).*|#define SSTR( x ) (static_cast< std::ostringstream \&\& >( std::ostringstream() << std::dec << x ).str())|' "$TMP2/$f"
+done
+sed -i '1i #include <cstdint>' "$TMP2/Utils.cpp"
+( cd "$TMP2" && g++ $GZ -Wno-sign-compare -fopenmp -std=c++11 -O3 -w -o "$OUT/parsimplify" Config.cpp DataSet.cpp EdgeSimple.cpp OverlapGraphSimple.cpp Read.cpp Utils.cpp dna.cpp mainParSimplify.cpp $GZL ) \
+  && echo "build_ref: built $OUT/parsimplify" || echo "build_ref: parsimplify did not build (acceptance test will be skipped)"

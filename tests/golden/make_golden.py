@@ -33,10 +33,20 @@ def make(name, records, min_overlap, paired=False):
             f.write(f">{i + 1}\n{s}\n")
     ref = oracle.run_ref([fa], os.path.join(d, "o"), min_overlap, threads=1, paired=paired)
     assert "Graph construction complete" in ref["log"], ref["log"][-2000:]
+    # downstream acceptance: what the reference's own parsimplify makes of the reference's own file
+    simple = []
+    ps = os.path.join(ROOT, "oracle", "_ref", "parsimplify")
+    if os.access(ps, os.X_OK):
+        import subprocess
+        out = os.path.join(d, "simple.txt")
+        r = subprocess.run([ps, os.path.join(d, "o_0_parGraph.txt"), out, str(min_overlap), "1"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        simple = sorted(open(out).read().splitlines())
     np.savez_compressed(os.path.join(HERE, name + ".npz"),
                         records=np.array(records, dtype=object), min_overlap=min_overlap,
                         ref_edges=np.array(ref["edges"], dtype=object),
-                        ref_crows=np.array(ref["contained_rows"], dtype=object))
+                        ref_crows=np.array(ref["contained_rows"], dtype=object),
+                        ref_parsimplify=np.array(simple, dtype=object))
     print(f"{name}: {len(records)} records, m={min_overlap}: {len(ref['edges'])} edges, {len(ref['contained_rows'])} contained rows")
 
 

@@ -10,7 +10,8 @@ GOLDEN = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
 def load_golden(path):
     z = np.load(path, allow_pickle=True)
     return dict(name=os.path.basename(path)[:-4], records=[str(x) for x in z["records"]], min_overlap=int(z["min_overlap"]),
-                ref_edges=[str(x) for x in z["ref_edges"]], ref_crows=[str(x) for x in z["ref_crows"]])
+                ref_edges=[str(x) for x in z["ref_edges"]], ref_crows=[str(x) for x in z["ref_crows"]],
+                ref_parsimplify=[str(x) for x in z["ref_parsimplify"]] if "ref_parsimplify" in z.files else None)
 
 
 def oracle_filter(records, min_overlap):
