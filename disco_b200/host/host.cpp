@@ -8,6 +8,7 @@
 #include <string>
 #include <vector>
 #include <zlib.h>
+#include <chrono>
 
 namespace {
 thread_local std::string g_err;
@@ -28,7 +29,7 @@ const char *kFilterStrings[] = {
     "ATACATACATACATACATACATACATACA", "GTTTGTTTGTTTGTTTGTTTGTTTGTTTG", "TGTTTGTTTGTTTGTTTGTTTGTTTGTTT",
     "TTTGTTTGTTTGTTTGTTTGTTTGTTTGT", "AGGGAGGGAGGGAGGGAGGGAGGGAGGGA", "GAGGGAGGGAGGGAGGGAGGGAGGGAGGG",
     "GGAGGGAGGGAGGGAGGGAGGGAGGGAGG", "GGGAGGGAGGGAGGGAGGGAGGGAGGGAG"};
-const char *kMerStrings[] = {"AC", "AG", "AT", "CG", "CT", "GT", "AAT", "ATA", "TAA", "AAC", "ACA", "CAA", "AAG", "AGA", "GAA", "GGGGCC"};
+// merCheckStrings (Dataset.cpp:87): AC AG AT CG CT GT AAT ATA TAA AAC ACA CAA AAG AGA GAA GGGGCC -- see short_repeat_hit()
 constexpr uint64_t kMinReadSize = 30; // Dataset.h:15
 
 uint64_t count_substring(const char *s, uint64_t n, const char *sub, uint64_t m)
@@ -43,43 +44,95 @@ uint64_t count_substring(const char *s, uint64_t n, const char *sub, uint64_t m)
     return cnt;
 }
 
-bool test_read(const char *s, uint64_t n)
+// base class table: A C G T -> 0 1 2 3 (the packing code, HashTable.h:16-22), everything else 255
+const struct BaseTab {
+    uint8_t t[256];
+    BaseTab() { for (int i = 0; i < 256; i++) t[i] = 255; t['A'] = 0; t['C'] = 1; t['G'] = 2; t['T'] = 3; }
+} kBase;
+
+// The di-/tri-mer repeat test of Dataset.cpp:431-438 for all fifteen short patterns in ONE pass over the base codes.
+// countSubstring() counts greedily from the left without overlap; of the listed patterns only ATA, ACA and AGA can
+// overlap themselves, so they carry a "next allowed start", the others are plain occurrence counts.
+bool short_repeat_hit(const uint8_t *c, uint64_t n, uint64_t thr)
+{
+    uint32_t di[16] = {0}, tri[64] = {0};
+    uint32_t next_xyx[16] = {0}; // indexed by (x, y) of an xyx pattern
+    int c0 = c[0], c1 = n > 1 ? c[1] : 0;
+    if (n > 1) di[c0 * 4 + c1]++;
+    for (uint64_t i = 2; i < n; i++) {
+        const int c2 = c[i];
+        di[c1 * 4 + c2]++;
+        const int t = (c0 * 4 + c1) * 4 + c2;
+        if (c0 == c2) { // xyx patterns: greedy, non-overlapping
+            const uint32_t start = (uint32_t)(i - 2);
+            uint32_t &nx = next_xyx[c0 * 4 + c1];
+            if (start >= nx) { tri[t]++; nx = start + 3; }
+        } else tri[t]++;
+        c0 = c1; c1 = c2;
+    }
+    // A0 C1 G2 T3 -- "AC","AG","AT","CG","CT","GT"
+    const int dimers[6] = {0 * 4 + 1, 0 * 4 + 2, 0 * 4 + 3, 1 * 4 + 2, 1 * 4 + 3, 2 * 4 + 3};
+    for (int d : dimers) if ((uint64_t)di[d] * 2 >= thr) return true;
+    // "AAT","ATA","TAA","AAC","ACA","CAA","AAG","AGA","GAA"
+    const int trimers[9] = {(0 * 4 + 0) * 4 + 3, (0 * 4 + 3) * 4 + 0, (3 * 4 + 0) * 4 + 0, (0 * 4 + 0) * 4 + 1, (0 * 4 + 1) * 4 + 0,
+                            (1 * 4 + 0) * 4 + 0, (0 * 4 + 0) * 4 + 2, (0 * 4 + 2) * 4 + 0, (2 * 4 + 0) * 4 + 0};
+    for (int t : trimers) if ((uint64_t)tri[t] * 3 >= thr) return true;
+    return false;
+}
+
+// s = upper-cased read, codes = scratch of n bytes that receives the base codes (valid when the function returns true)
+bool test_read_codes(const char *s, uint64_t n, uint8_t *codes)
 {
     if (n < kMinReadSize) return false;
     uint64_t cnt[4] = {0, 0, 0, 0};
+    uint8_t bad = 0;
     for (uint64_t i = 0; i < n; i++) {
-        const char c = s[i];
-        if (c != 'A' && c != 'C' && c != 'G' && c != 'T') return false;
-        cnt[(c >> 1) & 3]++;
+        const uint8_t c = kBase.t[(unsigned char)s[i]];
+        codes[i] = c;
+        bad |= c;
+        cnt[c & 3]++;
     }
+    if (bad & 0x80) return false; // something other than A C G T (Dataset.cpp:411)
+    // (the reference counts with (ch >> 1) & 3 = A0 C1 T2 G3: the same four counters in another order)
     uint64_t thr = (uint64_t)((double)n * .7); // Dataset.cpp:415
     if (cnt[0] >= thr || cnt[1] >= thr || cnt[2] >= thr || cnt[3] >= thr) return false;
     for (const char *f : kFilterStrings) {
-        const uint64_t len = strlen(f);
+        const uint64_t len = 29;
         if (n < len) return false;
-        if (memcmp(f, s, len) == 0 || memcmp(f, s + n - len, len) == 0) return false;
+        if (f[0] == s[0] && memcmp(f, s, len) == 0) return false;
+        if (f[0] == s[n - len] && memcmp(f, s + n - len, len) == 0) return false;
     }
     thr = (uint64_t)((double)n * .5); // Dataset.cpp:431
-    for (const char *m : kMerStrings) {
-        const uint64_t ml = strlen(m);
-        if (count_substring(s, n, m, ml) * ml >= thr) return false;
-    }
+    if (short_repeat_hit(codes, n, thr)) return false;
+    if (count_substring(s, n, "GGGGCC", 6) * 6 >= thr) return false;
     return true;
 }
 
-inline uint64_t code_of(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : 3; } // HashTable.h:16-22
-
-void pack_ascii(const char *s, uint64_t n, uint64_t *out)
+bool test_read(const char *s, uint64_t n)
 {
-    for (uint64_t i = 0; i < n; i++) out[i >> 5] |= code_of(s[i]) << (62 - 2 * (i & 31)); // HashTable.cpp:458-470
+    std::vector<uint8_t> codes(n ? n : 1);
+    return test_read_codes(s, n, codes.data());
 }
+
+void pack_codes_into(const uint8_t *c, uint64_t n, uint64_t *out)
+{
+    for (uint64_t w = 0; w * 32 < n; w++) {
+        const uint64_t e = std::min<uint64_t>(n, w * 32 + 32);
+        uint64_t v = 0;
+        for (uint64_t i = w * 32; i < e; i++) v = (v << 2) | c[i];
+        out[w] = v << (2 * (w * 32 + 32 - e)); // HashTable.cpp:458-470: base i at bits 62 - 2 (i mod 32)
+    }
+}
+
 } // namespace
 
 struct disco_reads {
     uint32_t min_overlap = 0;
     int threads = 1;
     uint64_t records = 0;             // file index of the last record seen
-    std::vector<std::string> seqs;    // accepted, upper-cased
+    std::vector<uint64_t> vwords;     // accepted reads, 2-bit packed back to back (variable length)
+    std::vector<uint64_t> woff{0};    // count + 1 word offsets into vwords
+    std::vector<uint16_t> vlen;       // accepted
     std::vector<uint64_t> file_index; // accepted
     bool finalized = false;
     uint32_t wpr = 0, min_len = 0, max_len = 0;
@@ -88,27 +141,67 @@ struct disco_reads {
 };
 
 namespace {
-// filter a batch of raw records (pointer, length) in parallel, then append the accepted ones in order
+// filter a batch of raw records (pointer, length) in parallel, then pack the accepted ones, in order, straight from
+// the input buffer into the variable-length 2-bit store (no per-read heap objects)
 struct RawRec { const char *p; uint64_t n; bool strip_nl; };
+
+inline uint64_t clean_into(const RawRec &rec, std::string &buf)
+{
+    static const struct Upper { char t[256]; Upper() { for (int i = 0; i < 256; i++) t[i] = (char)toupper(i); } } up;
+    buf.resize(rec.n);
+    uint64_t o = 0;
+    const char *p = rec.p;
+    if (rec.strip_nl) {
+        for (uint64_t k = 0; k < rec.n; k++) { const char c = p[k]; if (c != '\n') buf[o++] = up.t[(unsigned char)c]; } // Dataset.cpp:276 removes only '\n'
+    } else {
+        for (uint64_t k = 0; k < rec.n; k++) buf[o++] = up.t[(unsigned char)p[k]];                                   // Dataset.cpp:303-304
+    }
+    return o;
+}
+
 void absorb(disco_reads *r, const std::vector<RawRec> &batch)
 {
     const size_t m = batch.size();
-    std::vector<std::string> clean(m);
-    std::vector<char> good(m, 0);
-#pragma omp parallel for schedule(dynamic, 256) num_threads(r->threads)
-    for (size_t i = 0; i < m; i++) {
-        std::string &s = clean[i];
-        s.reserve(batch[i].n);
-        for (uint64_t k = 0; k < batch[i].n; k++) {
-            char c = batch[i].p[k];
-            if (batch[i].strip_nl && c == '\n') continue;            // Dataset.cpp:276 removes only '\n'
-            s.push_back((char)toupper((unsigned char)c));           // Dataset.cpp:303-304
+    std::vector<uint16_t> clen(m, 0); // 0 = rejected
+#pragma omp parallel num_threads(r->threads)
+    {
+        std::string buf;
+        std::vector<uint8_t> codes;
+#pragma omp for schedule(dynamic, 2048)
+        for (size_t i = 0; i < m; i++) {
+            const uint64_t o = clean_into(batch[i], buf);
+            if (codes.size() < o) codes.resize(o);
+            if (o > r->min_overlap && o <= 32767 && test_read_codes(buf.data(), o, codes.data())) clen[i] = (uint16_t)o; // Dataset.cpp:305
         }
-        good[i] = s.size() > r->min_overlap && s.size() <= 32767 && test_read(s.data(), s.size()); // Dataset.cpp:305
     }
+    // accepted records get consecutive read ids in file order (Dataset.cpp:133-134 after the file-order sort)
+    const size_t n0 = r->vlen.size();
+    std::vector<uint64_t> slot(m);
+    uint64_t k = n0, w = r->woff.back();
     for (size_t i = 0; i < m; i++) {
         r->records++;
-        if (good[i]) { r->seqs.push_back(std::move(clean[i])); r->file_index.push_back(r->records); }
+        slot[i] = k;
+        if (clen[i]) {
+            r->file_index.push_back(r->records);
+            r->vlen.push_back(clen[i]);
+            w += (clen[i] + 31) / 32;
+            r->woff.push_back(w);
+            k++;
+        }
+    }
+    r->vwords.resize(w, 0);
+#pragma omp parallel num_threads(r->threads)
+    {
+        std::string buf;
+        std::vector<uint8_t> codes;
+#pragma omp for schedule(dynamic, 2048)
+        for (size_t i = 0; i < m; i++) {
+            if (!clen[i]) continue;
+            const uint64_t o = clean_into(batch[i], buf);
+            if (codes.size() < o) codes.resize(o);
+            for (uint64_t q = 0; q < o; q++) codes[q] = kBase.t[(unsigned char)buf[q]];
+            pack_codes_into(codes.data(), o, r->vwords.data() + r->woff[slot[i]]);
+        }
     }
 }
 } // namespace
@@ -138,20 +231,40 @@ int disco_reads_add_records(disco_reads *r, const char *seqs, const uint64_t *of
     return 0;
 }
 
+static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int disco_reads_add_file(disco_reads *r, const char *path)
 {
+    const bool trace = getenv("DISCO_HOST_TRACE") != nullptr;
+    double t0 = now_s();
     if (!r || r->finalized) return fail("reads object already finalized");
-    gzFile fp = gzopen(path, "rb"); // transparently reads plain files too
-    if (!fp) return fail(std::string("Unable to open file: ") + path);
-    gzbuffer(fp, 1 << 20);
     std::string data;
     {
-        std::vector<char> buf(1 << 24);
-        int got;
-        while ((got = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)got);
-        if (got < 0) { gzclose(fp); return fail(std::string("read error in ") + path); }
+        FILE *f = fopen(path, "rb");
+        if (!f) return fail(std::string("Unable to open file: ") + path);
+        unsigned char magic[2] = {0, 0};
+        const size_t got = fread(magic, 1, 2, f);
+        const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        if (!gz) { // plain text: one read of the whole file
+            fseek(f, 0, SEEK_END);
+            const long sz = ftell(f);
+            fseek(f, 0, SEEK_SET);
+            data.resize(sz > 0 ? (size_t)sz : 0);
+            if (sz > 0 && fread(&data[0], 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(std::string("read error in ") + path); }
+            fclose(f);
+        } else {
+            fclose(f);
+            gzFile fp = gzopen(path, "rb");
+            if (!fp) return fail(std::string("Unable to open file: ") + path);
+            gzbuffer(fp, 1 << 20);
+            std::vector<char> buf(1 << 24);
+            int n;
+            while ((n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)n);
+            if (n < 0) { gzclose(fp); return fail(std::string("read error in ") + path); }
+            gzclose(fp);
+        }
     }
-    gzclose(fp);
+    if (trace) { fprintf(stderr, "[host] read %.3fs\n", now_s() - t0); t0 = now_s(); }
     const uint64_t before = r->records;
     if (!data.empty()) {
         const char *b = data.data(), *e = b + data.size();
@@ -190,7 +303,9 @@ int disco_reads_add_file(disco_reads *r, const char *path)
         } else {
             return fail("Unknown input file format."); // Dataset.cpp:267
         }
+        if (trace) { fprintf(stderr, "[host] index %.3fs (%zu records)\n", now_s() - t0, batch.size()); t0 = now_s(); }
         absorb(r, batch);
+        if (trace) { fprintf(stderr, "[host] absorb %.3fs\n", now_s() - t0); t0 = now_s(); }
     }
     if (r->records <= before) return fail(std::string("File empty. No reads loaded from ") + path); // Dataset.cpp:113-114
     return 0;
@@ -200,25 +315,25 @@ int disco_reads_finalize(disco_reads *r)
 {
     if (!r) return fail("NULL");
     if (r->finalized) return 0;
-    const uint64_t n = r->seqs.size();
+    const uint64_t n = r->vlen.size();
     uint32_t mn = 0xFFFFFFFFu, mx = 0;
-    for (const auto &s : r->seqs) { mn = std::min<uint32_t>(mn, (uint32_t)s.size()); mx = std::max<uint32_t>(mx, (uint32_t)s.size()); }
+    for (uint16_t l : r->vlen) { mn = std::min<uint32_t>(mn, l); mx = std::max<uint32_t>(mx, l); }
     if (n == 0) { mn = mx = 0; }
     r->min_len = mn; r->max_len = mx;
     r->wpr = std::max<uint32_t>(2, (((mx + 31) / 32) + 1) & ~1u);
     r->packed.assign(n * (uint64_t)r->wpr, 0);
-    r->len.resize(n);
+    r->len = r->vlen;
 #pragma omp parallel for schedule(static) num_threads(r->threads)
     for (uint64_t i = 0; i < n; i++) {
-        pack_ascii(r->seqs[i].data(), r->seqs[i].size(), r->packed.data() + i * r->wpr);
-        r->len[i] = (uint16_t)r->seqs[i].size();
+        const uint64_t nw = r->woff[i + 1] - r->woff[i];
+        memcpy(r->packed.data() + i * r->wpr, r->vwords.data() + r->woff[i], nw * sizeof(uint64_t));
     }
-    std::vector<std::string>().swap(r->seqs);
+    std::vector<uint64_t>().swap(r->vwords);
     r->finalized = true;
     return 0;
 }
 
-uint64_t disco_reads_count(const disco_reads *r) { return r->finalized ? r->len.size() : r->seqs.size(); }
+uint64_t disco_reads_count(const disco_reads *r) { return r->vlen.size(); }
 uint64_t disco_reads_records(const disco_reads *r) { return r->records; }
 uint32_t disco_reads_words_per_read(const disco_reads *r) { return r->wpr; }
 const uint64_t *disco_reads_packed(const disco_reads *r) { return r->packed.data(); }
