@@ -1,0 +1,127 @@
+"""GPU edge cases against the CPU oracle: tiny inputs, reads barely longer than the minimum overlap, long reads (generic
+matcher, one warp per block), very high coverage (exact path), reverse-palindromic k-mers, cap values."""
+import numpy as np
+import pytest
+from helpers import oracle_forms
+from disco_b200 import gpu, host, synth
+from disco_b200.buildgraph import BuildGraph
+
+pytestmark = pytest.mark.gpu
+
+
+def _both(records, m, cap=4):
+    o = oracle_forms(records, m)
+    bg = BuildGraph(min_overlap=m, max_edge_per_kmer=cap)
+    bg.add_records(records)
+    res = bg.run()
+    out = (bg.crow_lines(), sorted(bg.edge_lines()), res.stats, o)
+    bg.close()
+    return out
+
+
+def test_single_read_and_pairs():
+    a = synth.single_genome(1, 120, 1.0, seed=3).strings()[0]
+    crows, edges, st, o = _both([a], 40)
+    assert crows == [] and edges == [] and st["n_reads"] == 1
+    b = a[60:] + synth.single_genome(1, 60, 1.0, seed=4).strings()[0]      # 60-base dovetail
+    brc = b[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    for recs in ([a, b], [b, a], [a, brc], [brc, a]):
+        crows, edges, st, o = _both(recs, 40)
+        assert edges == o["edges"] and len(edges) == 1
+        assert crows == o["crows"] == []
+
+
+def test_reads_barely_longer_than_min_overlap():
+    rs = synth.single_genome(4000, 52, 40.0, seed=5)     # length 52, minOverlap 50: one search position per read
+    crows, edges, st, o = _both(rs.strings(), 50)
+    assert crows == o["crows"] and edges == o["edges"]
+    assert st["cap_fired"] == 0
+
+
+def test_long_reads_generic_matcher():
+    rng = np.random.default_rng(6)
+    g = synth.random_genome(rng, 60000)
+    recs = []
+    for _ in range(400):
+        L = int(rng.integers(900, 2500))
+        s = int(rng.integers(0, len(g) - L))
+        r = g[s:s + L]
+        if rng.random() < 0.5:
+            r = synth.revcomp_codes(r)
+        recs.append("".join("ACGT"[c] for c in r))
+    crows, edges, st, o = _both(recs, 63)
+    assert crows == o["crows"] and edges == o["edges"]
+
+
+def test_very_high_coverage_takes_exact_path():
+    rs = synth.single_genome(6000, 150, 400.0, seed=7)   # ~400x: hundreds of candidates per read, cap fires
+    recs = rs.strings()
+    o = oracle_forms(recs, 50)
+    bg = BuildGraph(min_overlap=50)
+    bg.add_records(recs)
+    res = bg.run()
+    try:
+        assert bg.crow_lines() == o["crows"]
+        assert res.stats["slow_path_reads"] > 0
+        assert res.stats["cap_fired"] == o["res"].stats["cap_fired"]
+        assert res.stats["raw_directed_edges"] == o["res"].stats["raw_directed"]
+        rows = sorted((int(e["src"]) + 1, int(e["offset"]), int(e["dst"]) + 1, int(e["orient"])) for r in range(res.n) for e in bg._g.row(r))
+        assert rows == sorted((int(e["src"]), int(e["offset"]), int(e["dst"]), int(e["orient"])) for e in o["res"].raw)
+    finally:
+        bg.close()
+
+
+def test_reverse_palindromic_kmers_even_k():
+    """K = 34 (minOverlap 35): planted reverse-palindromic 34-mers at read ends.  The contained set and
+    the per-read search rows must still equal the oracle's (which types them like the reference: forward only)."""
+    rng = np.random.default_rng(21)
+    g = synth.random_genome(rng, 12000)
+    for pos in range(100, len(g) - 200, 250):
+        half = g[pos:pos + 17].copy()
+        g[pos + 17:pos + 34] = synth.revcomp_codes(half)
+    recs = []
+    for _ in range(3000):
+        L = int(rng.integers(100, 151))
+        if rng.random() < 0.3:
+            p = int(rng.integers(0, (len(g) - 400) // 250)) * 250 + 100
+            s = p if rng.random() < 0.5 else p + 34 - L
+            s = max(0, min(s, len(g) - L))
+        else:
+            s = int(rng.integers(0, len(g) - L))
+        r = g[s:s + L]
+        if rng.random() < 0.5:
+            r = synth.revcomp_codes(r)
+        recs.append("".join("ACGT"[c] for c in r))
+    o = oracle_forms(recs, 35)
+    bg = BuildGraph(min_overlap=35)
+    bg.add_records(recs)
+    res = bg.run()
+    try:
+        assert bg.crow_lines() == o["crows"]
+        rows = sorted((int(e["src"]) + 1, int(e["offset"]), int(e["dst"]) + 1, int(e["orient"])) for r in range(res.n) for e in bg._g.row(r))
+        assert rows == sorted((int(e["src"]), int(e["offset"]), int(e["dst"]), int(e["orient"])) for e in o["res"].raw)
+        assert res.stats["cap_fired"] == o["res"].stats["cap_fired"]
+    finally:
+        bg.close()
+
+
+@pytest.mark.parametrize("cap", [1, 2, 8])
+def test_other_cap_values(cap):
+    """MAX_EDGE_PER_KMER is a compile-time constant in the reference (Common.h:62); the library takes it as an argument."""
+    import ctypes as C
+    from oracle import oracle
+    rs = synth.repeats(2500, 150, seed=13)
+    recs = rs.strings()
+    bg = BuildGraph(min_overlap=50, max_edge_per_kmer=cap)
+    bg.add_records(recs)
+    res = bg.run()
+    try:
+        # per-read rows obey the cap: at most `cap` entries per k-mer position of the source read
+        for r in range(0, res.n, 7):
+            row = bg._g.row(r)
+            L = int(res.lens[r])
+            pos = np.where((row["orient"] == 3) | (row["orient"] == 2), row["offset"], L - 49 - row["offset"])
+            if len(pos):
+                assert np.bincount(pos.astype(np.int64)).max() <= cap
+    finally:
+        bg.close()
