@@ -24,6 +24,7 @@ constexpr int kChunk = 16;     // reads per work-counter grab
 constexpr int kScanLimit = 6;  // buckets a lane may walk on the fast path before the read is deferred to the slow path
 constexpr int kRowBlock = 1024; // adjacency entries a warp reserves per global atomic
 constexpr int kHitCap = 128;    // fast-path candidate queue entries per warp (edge pass)
+constexpr int kParkMax = 512;    // candidates one read may park for the verify kernel (queue flushed in pieces); more -> exact path
 constexpr int kContainQueue = 64; // candidate queue entries per warp (containment pass, drained every 32 positions)
 constexpr int kBestMax = 16;   // slow path: smallest-record candidates kept per position (>= 2 * cap)
 
@@ -887,7 +888,22 @@ __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
                 np += __popc(m);
             }
             __syncwarp();
-            // ---- probe: one lane per surviving position
+            // ---- probe: one lane per surviving position.  Tag matches go to the shared-memory queue; a read with many
+            // of them (high coverage) flushes the queue into a kParkMax-entry row reserved on first need.
+            unsigned long long park_base = 0;
+            int park_cap = 0, parked = 0;
+            bool overflow = false;
+            auto reserve = [&](int n) -> unsigned long long { // n entries from this warp's slice of the adjacency buffer
+                if (blk_cur + n > blk_end) {
+                    const unsigned long long want = n > kRowBlock ? (unsigned long long)n : (unsigned long long)kRowBlock;
+                    if (lane == 0) blk_cur = atomicAdd(p.rows_cursor, want);
+                    blk_cur = __shfl_sync(FULL, blk_cur, 0);
+                    blk_end = blk_cur + want;
+                }
+                const unsigned long long b = blk_cur;
+                blk_cur += n;
+                return b;
+            };
             for (int i0 = 0; i0 < np; i0 += 32) {
                 const int i = i0 + lane;
                 if (i < np) {
@@ -929,23 +945,31 @@ __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
                     }
                     if (pushed > cap) ctrl[3] = 1;
                 }
+                __syncwarp();
+                const int q = ctrl[0];
+                if (q > hcap) { overflow = true; break; }            // one round overran the queue: exact path
+                if (q >= hcap / 2 && i0 + 32 < np) {                 // make room for the next round
+                    if (!park_cap) { park_base = reserve(kParkMax); park_cap = kParkMax; }
+                    if (parked + q > park_cap) { overflow = true; break; }
+                    if (park_base + park_cap <= p.rows_cap)
+                        for (int k = lane; k < q; k += 32) p.rows[park_base + parked + k] = hits[k];
+                    parked += q;
+                    __syncwarp();
+                    if (lane == 0) ctrl[0] = 0;
+                    __syncwarp();
+                }
             }
             __syncwarp();
-            // ---- park the candidates in the read's row (the verify kernel compacts the survivors in place)
-            const int nc = ctrl[0];
-            if (ctrl[1] != 0 || nc > hcap) {
+            // ---- park the (remaining) candidates in the read's row (the verify kernel compacts the survivors in place)
+            const int q = ctrl[0];
+            const int nc = parked + q;
+            if (overflow || ctrl[1] != 0 || q > hcap || (park_cap && nc > park_cap)) {
                 if (lane == 0) p.rowinfo[r1] = kInfoExact;
             } else if (nc > 0) {
-                if (blk_cur + nc > blk_end) {
-                    const unsigned long long want = nc > kRowBlock ? (unsigned long long)nc : (unsigned long long)kRowBlock;
-                    if (lane == 0) blk_cur = atomicAdd(p.rows_cursor, want);
-                    blk_cur = __shfl_sync(FULL, blk_cur, 0);
-                    blk_end = blk_cur + want;
-                }
-                const unsigned long long base = blk_cur;
-                blk_cur += nc;
-                if (base + nc <= p.rows_cap) {
-                    for (int i = lane; i < nc; i += 32) p.rows[base + i] = hits[i];
+                const unsigned long long base = park_cap ? park_base : reserve(nc);
+                const unsigned long long room = park_cap ? (unsigned long long)park_cap : (unsigned long long)nc;
+                if (base + room <= p.rows_cap) {
+                    for (int k = lane; k < q; k += 32) p.rows[base + parked + k] = hits[k];
                     if (lane == 0) p.rowinfo[r1] = make_rowinfo(base, (uint32_t)nc) | (ctrl[3] ? kInfoCrowded : 0ULL);
                 } else if (lane == 0) {
                     atomicExch(p.stats + ST_OVERFLOW, 1ULL);
@@ -987,6 +1011,96 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
             if ((ri & kInfoExact) || nc == 0) continue;
             const uint64_t start = rowinfo_start(ri);
             const int L1 = read_len(p.reads, r1);
+            if (nc > p.hcap) {
+                // ---- big row (high coverage, up to kParkMax candidates): same steps, but the candidates stay in the
+                // parked row in global memory and are taken 32 at a time
+                stage_read(p.reads, r1, L1, s.A, s.R, WP, lane);
+                const bool count_pos = (ri & kInfoCrowded) != 0;
+                if (count_pos) for (int k = lane; k < L1 - K; k += 32) cntj[k] = 0;
+                __syncwarp();
+                bool over = false;
+                for (int i0 = 0; i0 < nc; i0 += 32) {
+                    const int i = i0 + lane;
+                    if (i < nc) {
+                        const uint64_t c = p.rows[start + i];
+                        const bool ok = verify_dovetail<NW>(p, s, L1, hit_j(c), hit_type(c), hit_read(c));
+                        if (!ok) p.rows[start + i] = ~0ULL;
+                        else if (count_pos) over |= atomicAdd(&cntj[hit_j(c)], 1) >= cap;
+                    }
+                }
+                n_verified += (lane == 0) ? (unsigned)nc : 0u;
+                if (__any_sync(FULL, over)) { // a position with more than cap partners: redo exactly
+                    if (lane == 0) p.rowinfo[r1] = kInfoExact;
+                    __syncwarp();
+                    continue;
+                }
+                __syncwarp();
+                // first hit per neighbour (OverlapGraph.cpp:656): neighbour ids go through a shared-memory set in two
+                // passes (one hash bit each) so that 512 slots are enough; an id seen twice marks the read for the
+                // quadratic clean-up below
+                uint32_t *bigset = reinterpret_cast<uint32_t *>(s.hits); // queue + id-set space, unused on this path
+                const int slots = 2 * p.hcap + p.hset;                    // u32 slots (hits is u64[hcap])
+                bool dup = false, full = false;
+                for (int pass = 0; pass < 2; pass++) {
+                    for (int k = lane; k < slots; k += 32) bigset[k] = 0xFFFFFFFFu;
+                    __syncwarp();
+                    for (int i0 = 0; i0 < nc; i0 += 32) {
+                        const int i = i0 + lane;
+                        const uint64_t hk = (i < nc) ? __ldcg(p.rows + start + i) : ~0ULL;
+                        if (hk == ~0ULL) continue;
+                        const uint32_t r2 = hit_read(hk);
+                        const uint32_t hv = r2 * 0x9E3779B1u;
+                        if ((int)(hv >> 31) != pass) continue;
+                        uint32_t hh = (hv >> 7) % (uint32_t)slots;
+                        for (int tries = 0;; tries++) {
+                            if (tries == slots) { full = true; break; }
+                            const uint32_t old = atomicCAS(&bigset[hh], 0xFFFFFFFFu, r2);
+                            if (old == 0xFFFFFFFFu) break;
+                            if (old == r2) { dup = true; break; }
+                            hh = (hh + 1 == (uint32_t)slots) ? 0 : hh + 1;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (__any_sync(FULL, dup || full)) {
+                    unsigned drop = 0;
+                    for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++) {
+                        const int i = i0 + lane;
+                        const uint64_t hk = (i < nc) ? __ldcg(p.rows + start + i) : ~0ULL;
+                        if (hk == ~0ULL) continue;
+                        const uint32_t r2 = hit_read(hk);
+                        for (int k = 0; k < nc; k++) {
+                            const uint64_t o = __ldcg(p.rows + start + k);
+                            if (o != ~0ULL && hit_read(o) == r2 && o < hk) { drop |= 1u << rd; break; }
+                        }
+                    }
+                    __syncwarp();
+                    for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++)
+                        if ((drop >> rd) & 1) p.rows[start + i0 + lane] = ~0ULL;
+                    __syncwarp();
+                }
+                // compact the survivors at the front of the row, as adjacency entries
+                int off = 0;
+                for (int i0 = 0; i0 < nc; i0 += 32) {
+                    const int i = i0 + lane;
+                    const uint64_t hk = (i < nc) ? __ldcg(p.rows + start + i) : ~0ULL;
+                    const bool valid = hk != ~0ULL;
+                    const unsigned m = __ballot_sync(FULL, valid); // everybody has read before anybody writes
+                    if (valid) {
+                        int orient, ovl;
+                        type_to_edge(hit_type(hk), L1, K, hit_j(hk), &orient, &ovl);
+                        p.rows[start + off + __popc(m & lt_mask)] = make_entry(L1 - ovl, hit_read(hk), orient);
+                    }
+                    off += __popc(m);
+                    __syncwarp();
+                }
+                if (lane == 0) p.rowinfo[r1] = off ? make_rowinfo(start, (uint32_t)off) : 0ULL;
+                n_hits += (lane == 0) ? (unsigned)off : 0u;
+                n_entries += (lane == 0) ? (unsigned long long)off : 0ULL;
+                if ((unsigned)off > maxdeg) maxdeg = off;
+                __syncwarp();
+                continue;
+            }
             // candidates first (their rows are the long-latency loads of this kernel), then the query
             for (int i = lane; i < nc; i += 32) {
                 const uint64_t c = p.rows[start + i];

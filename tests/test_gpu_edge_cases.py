@@ -53,8 +53,8 @@ def test_long_reads_generic_matcher():
     assert crows == o["crows"] and edges == o["edges"]
 
 
-def test_very_high_coverage_takes_exact_path():
-    rs = synth.single_genome(6000, 150, 400.0, seed=7)   # ~400x: hundreds of candidates per read, cap fires
+def test_very_high_coverage():
+    rs = synth.single_genome(6000, 150, 400.0, seed=7)   # ~400x: one read per start and strand survives, ~500 candidates each
     recs = rs.strings()
     o = oracle_forms(recs, 50)
     bg = BuildGraph(min_overlap=50)
@@ -62,11 +62,35 @@ def test_very_high_coverage_takes_exact_path():
     res = bg.run()
     try:
         assert bg.crow_lines() == o["crows"]
-        assert res.stats["slow_path_reads"] > 0
+        assert res.stats["max_degree"] > 128   # beyond the shared-memory queue: parked in pieces, chunked verify
         assert res.stats["cap_fired"] == o["res"].stats["cap_fired"]
         assert res.stats["raw_directed_edges"] == o["res"].stats["raw_directed"]
         rows = sorted((int(e["src"]) + 1, int(e["offset"]), int(e["dst"]) + 1, int(e["orient"])) for r in range(res.n) for e in bg._g.row(r))
         assert rows == sorted((int(e["src"]), int(e["offset"]), int(e["dst"]), int(e["orient"])) for e in o["res"].raw)
+    finally:
+        bg.close()
+
+
+@pytest.mark.parametrize("cov", [170.0, 300.0])
+def test_high_coverage_big_rows(cov):
+    """130-250 candidates per read: more than the shared-memory queue holds, so the probe kernel parks them in pieces
+    and the verify kernel takes its chunked path; positions rarely exceed the cap."""
+    rs = synth.single_genome(8000, 150, cov, seed=17)
+    recs = rs.strings()
+    o = oracle_forms(recs, 50)
+    bg = BuildGraph(min_overlap=50)
+    bg.add_records(recs)
+    res = bg.run()
+    try:
+        assert bg.crow_lines() == o["crows"]
+        assert res.stats["max_degree"] > 128
+        assert res.stats["slow_path_reads"] < res.n - len(res.crows)      # not everything fell to the exact path
+        assert res.stats["cap_fired"] == o["res"].stats["cap_fired"]
+        assert res.stats["raw_directed_edges"] == o["res"].stats["raw_directed"]
+        rows = sorted((int(e["src"]) + 1, int(e["offset"]), int(e["dst"]) + 1, int(e["orient"])) for r in range(res.n) for e in bg._g.row(r))
+        assert rows == sorted((int(e["src"]), int(e["offset"]), int(e["dst"]), int(e["orient"])) for e in o["res"].raw)
+        if res.stats["cap_fired"] == 0 and res.stats["one_sided_edges"] == 0:
+            assert sorted(bg.edge_lines()) == o["edges"]
     finally:
         bg.close()
 
