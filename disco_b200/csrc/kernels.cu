@@ -822,7 +822,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
 //   k_edges_exact  : the few reads flagged for the exact sequential search (cap may fire, long chains, > hcap
 //                    candidates)
 // ---------------------------------------------------------------------------------------------------------------
-__host__ __device__ inline size_t probe_words_per_warp(int WP, int npos, int hcap) { return 2 * (size_t)WP + (size_t)npos + ((size_t)npos + 1) / 2 + (size_t)hcap + 2; }
+__host__ __device__ inline size_t probe_words_per_warp(int WP, int npos, int hcap) { return 2 * (size_t)WP + (size_t)npos + ((size_t)npos + 1) / 2 + (size_t)hcap + 4; }
 __host__ __device__ inline size_t verify_words_per_warp(int WP, int npos, int hcap, int hset)
 {   // A, R, candidate queue, id set + per-position counters, transposed candidate words (32 x up to 16), control
     const int nw = WP - 2 <= 16 ? ((WP - 2 + 1) / 2) * 2 : 0;
@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
                 stage_read(p.reads, r1, L1, A, R, WP, lane);
             }
             n_queries += (lane == 0);
-            if (lane < 4) ctrl[lane] = 0; // [0] queued, [1] needs exact path, [3] some position has > cap candidates
+            if (lane < 8) ctrl[lane] = 0; // [0] queued, [1] needs exact path, [3] some position has > cap candidates, [4..7] parking
             __syncwarp();
             const int jhi = L1 - K; // positions [1, L1-K) (OverlapGraph.cpp:638)
             // ---- hash + presence filter: passing positions ballot-compacted, their bucket prefetched into L2
@@ -890,8 +890,8 @@ __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
             __syncwarp();
             // ---- probe: one lane per surviving position.  Tag matches go to the shared-memory queue; a read with many
             // of them (high coverage) flushes the queue into a kParkMax-entry row reserved on first need.
-            unsigned long long park_base = 0;
-            int park_cap = 0, parked = 0;
+            // (the parking state lives in shared memory -- ctrl[4] parked, ctrl[5] capacity, ctrl[6..7] row start -- so that
+            // the common case, no flush at all, keeps the registers for the probe loop)
             bool overflow = false;
             auto reserve = [&](int n) -> unsigned long long { // n entries from this warp's slice of the adjacency buffer
                 if (blk_cur + n > blk_end) {
@@ -949,24 +949,31 @@ __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
                 const int q = ctrl[0];
                 if (q > hcap) { overflow = true; break; }            // one round overran the queue: exact path
                 if (q >= hcap / 2 && i0 + 32 < np) {                 // make room for the next round
-                    if (!park_cap) { park_base = reserve(kParkMax); park_cap = kParkMax; }
-                    if (parked + q > park_cap) { overflow = true; break; }
-                    if (park_base + park_cap <= p.rows_cap)
-                        for (int k = lane; k < q; k += 32) p.rows[park_base + parked + k] = hits[k];
-                    parked += q;
+                    unsigned long long *pb = reinterpret_cast<unsigned long long *>(ctrl + 6);
+                    if (!ctrl[5]) {
+                        const unsigned long long b = reserve(kParkMax);
+                        __syncwarp();
+                        if (lane == 0) { *pb = b; ctrl[5] = kParkMax; }
+                        __syncwarp();
+                    }
+                    const int parked = ctrl[4];
+                    if (parked + q > ctrl[5]) { overflow = true; break; }
+                    if (*pb + ctrl[5] <= p.rows_cap)
+                        for (int k = lane; k < q; k += 32) p.rows[*pb + parked + k] = hits[k];
                     __syncwarp();
-                    if (lane == 0) ctrl[0] = 0;
+                    if (lane == 0) { ctrl[0] = 0; ctrl[4] = parked + q; }
                     __syncwarp();
                 }
             }
             __syncwarp();
             // ---- park the (remaining) candidates in the read's row (the verify kernel compacts the survivors in place)
             const int q = ctrl[0];
+            const int parked = ctrl[4], park_cap = ctrl[5];
             const int nc = parked + q;
             if (overflow || ctrl[1] != 0 || q > hcap || (park_cap && nc > park_cap)) {
                 if (lane == 0) p.rowinfo[r1] = kInfoExact;
             } else if (nc > 0) {
-                const unsigned long long base = park_cap ? park_base : reserve(nc);
+                const unsigned long long base = park_cap ? *reinterpret_cast<unsigned long long *>(ctrl + 6) : reserve(nc);
                 const unsigned long long room = park_cap ? (unsigned long long)park_cap : (unsigned long long)nc;
                 if (base + room <= p.rows_cap) {
                     for (int k = lane; k < q; k += 32) p.rows[base + parked + k] = hits[k];
