@@ -32,6 +32,8 @@ struct disco_ctx {
     // reads
     uint64_t *d_words = nullptr;
     uint16_t *d_len = nullptr;
+    uint64_t *d_stage = nullptr; // host rows arrive here when their pitch differs from the device row
+    uint64_t stage_words = 0;
     ReadsView reads{};
     // run parameters
     int K = 0, cap = 0;
@@ -112,7 +114,8 @@ void free_run_buffers(disco_ctx *c)
 
 void free_reads(disco_ctx *c)
 {
-    dfree(c->d_words); dfree(c->d_len);
+    dfree(c->d_words); dfree(c->d_len); dfree(c->d_stage);
+    c->stage_words = 0;
     c->reads = ReadsView{};
 }
 
@@ -153,13 +156,23 @@ int copy_reads(disco_ctx *ctx, const uint64_t *packed, const uint16_t *len, uint
     const int stride = ctx->reads.stride;
     const int W = (ctx->reads.max_len + 31) / 32;
     if ((int)wpr < W) return fail(ctx, DISCO_E_ARG, "words_per_read %u too small for max length %d", wpr, ctx->reads.max_len);
-    const size_t width = (size_t)std::min<int>((int)wpr, stride) * sizeof(uint64_t);
-    if (width < (size_t)stride * sizeof(uint64_t))
-        CK(cudaMemsetAsync(ctx->d_words, 0, n * (uint64_t)stride * sizeof(uint64_t), ctx->stream));
-    if ((int)wpr == stride) // same pitch on both sides: one flat copy (a pitched copy of 10M 48-byte rows is far slower)
+    if ((int)wpr == stride) { // same pitch on both sides: one flat copy
         CK(cudaMemcpyAsync(ctx->d_words, packed, n * (uint64_t)stride * sizeof(uint64_t), kind, ctx->stream));
-    else
-        CK(cudaMemcpy2DAsync(ctx->d_words, (size_t)stride * sizeof(uint64_t), packed, (size_t)wpr * sizeof(uint64_t), width, n, kind, ctx->stream));
+    } else if (kind == cudaMemcpyDeviceToDevice) {
+        CK(launch_restride(packed, (int)wpr, std::min<int>((int)wpr, stride), ctx->d_words, stride, n, ctx->stream));
+    } else {
+        // host rows with another pitch: one flat copy into a staging buffer (a pitched copy of millions of 40-byte rows
+        // is far slower than PCIe), then a re-stride kernel
+        const uint64_t need = n * (uint64_t)wpr;
+        if (ctx->stage_words < need) {
+            dfree(ctx->d_stage);
+            ctx->stage_words = 0;
+            CK(cudaMalloc(&ctx->d_stage, need * sizeof(uint64_t)));
+            ctx->stage_words = need;
+        }
+        CK(cudaMemcpyAsync(ctx->d_stage, packed, need * sizeof(uint64_t), kind, ctx->stream));
+        CK(launch_restride(ctx->d_stage, (int)wpr, std::min<int>((int)wpr, stride), ctx->d_words, stride, n, ctx->stream));
+    }
     CK(cudaMemcpyAsync(ctx->d_len, len, n * sizeof(uint16_t), kind, ctx->stream));
     return DISCO_OK;
 }

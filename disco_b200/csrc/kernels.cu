@@ -1298,6 +1298,15 @@ __global__ void k_contained_rows(const unsigned long long *best, ReadsView rv, i
     }
 }
 
+// packed reads arrive with the caller's row pitch; the kernels want power-of-two rows (one DRAM line per candidate)
+__global__ void k_restride(const uint64_t *src, int src_stride, int src_words, uint64_t *dst, int dst_stride, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; // one destination word per thread
+    const uint64_t r = i / dst_stride;
+    const int w = (int)(i - r * dst_stride);
+    if (r < n) dst[i] = (w < src_words) ? src[r * src_stride + w] : 0ULL;
+}
+
 __global__ void k_rebase_rowinfo(uint64_t *rowinfo, uint64_t lo, uint64_t hi, uint64_t base)
 {
     const uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1711,6 +1720,14 @@ cudaError_t launch_contained_rows(const unsigned long long *best, const ReadsVie
     if (r.n == 0) return cudaSuccess;
     const uint64_t blocks = (r.n + 255) / 256;
     k_contained_rows<<<(unsigned)blocks, 256, 0, s>>>(best, r, K, reinterpret_cast<disco_crow *>(rows_out), cursor);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_restride(const uint64_t *src, int src_stride, int src_words, uint64_t *dst, int dst_stride, uint64_t n, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    const uint64_t total = n * (uint64_t)dst_stride;
+    k_restride<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, src_stride, src_words, dst, dst_stride, n);
     return cudaGetLastError();
 }
 

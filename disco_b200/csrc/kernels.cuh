@@ -93,6 +93,8 @@ cudaError_t launch_contained_rows(const unsigned long long *best, const ReadsVie
 cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t s);
 cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t s);
 cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s);
+// copy n rows of src_words u64 (pitch src_stride) into rows of dst_stride u64, zero-filling the tail (dst_stride >= src_words)
+cudaError_t launch_restride(const uint64_t *src, int src_stride, int src_words, uint64_t *dst, int dst_stride, uint64_t n, cudaStream_t s);
 // smem bytes a search / reduce block needs for the given shape (0 = does not fit)
 bool search_edges_fits(int max_len, int K, int cap);
 

@@ -131,7 +131,7 @@ def pack_codes(codes: np.ndarray, off: np.ndarray, words_per_read: int = None, o
     n = len(off) - 1
     if words_per_read is None:
         mx = int(np.diff(off.astype(np.int64)).max()) if n else 1
-        words_per_read = max(2, (((mx + 31) // 32) + 1) & ~1)
+        words_per_read = max(1, (mx + 31) // 32)
     if out is None:
         out = np.empty((n, words_per_read), dtype=np.uint64)
     if lens_out is None:

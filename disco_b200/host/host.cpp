@@ -320,7 +320,7 @@ int disco_reads_finalize(disco_reads *r)
     for (uint16_t l : r->vlen) { mn = std::min<uint32_t>(mn, l); mx = std::max<uint32_t>(mx, l); }
     if (n == 0) { mn = mx = 0; }
     r->min_len = mn; r->max_len = mx;
-    r->wpr = std::max<uint32_t>(2, (((mx + 31) / 32) + 1) & ~1u);
+    r->wpr = std::max<uint32_t>(1, (mx + 31) / 32); // exact: the GPU library re-strides on the device
     r->packed.assign(n * (uint64_t)r->wpr, 0);
     r->len = r->vlen;
 #pragma omp parallel for schedule(static) num_threads(r->threads)

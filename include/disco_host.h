@@ -32,7 +32,7 @@ void disco_reads_free(disco_reads *r);
 int disco_reads_add_file(disco_reads *r, const char *path);
 /* Same for in-memory records (tests, synthetic data): seqs = concatenated raw sequences, off = n+1 offsets. */
 int disco_reads_add_records(disco_reads *r, const char *seqs, const uint64_t *off, uint64_t n);
-/* Build the packed arrays (stride = words for the longest accepted read, rounded up to even). */
+/* Build the packed arrays (stride = words for the longest accepted read). */
 int disco_reads_finalize(disco_reads *r);
 uint64_t disco_reads_count(const disco_reads *r);          /* accepted reads */
 uint64_t disco_reads_records(const disco_reads *r);        /* all records seen = last file index */
