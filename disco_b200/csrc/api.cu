@@ -52,7 +52,8 @@ struct disco_ctx {
     uint64_t run_n = 0; // reads the run buffers are sized for
     // adjacency
     uint64_t *d_rowinfo = nullptr;
-    uint64_t *d_rows = nullptr;
+    uint64_t *d_rows = nullptr;        // owned
+    uint64_t *d_rows_active = nullptr; // what the reduction reads: d_rows, or a caller-owned gathered buffer (use_rows)
     uint64_t rows_cap = 0, rows_used = 0; // rows_used = cursor (includes warp-slice slack)
     // output
     disco_edge *d_edges = nullptr;
@@ -61,6 +62,7 @@ struct disco_ctx {
     unsigned long long *d_cursors = nullptr;  // CUR_COUNT
     unsigned long long *d_stats_c = nullptr;  // containment pass
     unsigned long long *d_stats_e = nullptr;  // edge pass + reduction
+    float acc_probe = 0.f, acc_verify = 0.f, acc_exact = 0.f, acc_edges = 0.f; // edge-pass kernel times summed over parts
     cudaEvent_t ev[EV_COUNT] = {};
     bool ev_done[EV_COUNT] = {};
     disco_stats stats{};
@@ -108,6 +110,7 @@ void free_run_buffers(disco_ctx *c)
 {
     dfree(c->d_slots); dfree(c->d_filter); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
     dfree(c->d_rowinfo); dfree(c->d_rows); dfree(c->d_edges);
+    c->d_rows_active = nullptr;
     c->rows_cap = c->edges_cap = c->crows_cap = c->run_n = 0;
     c->begun = c->have_contained = c->have_edges = c->have_reduced = false;
 }
@@ -378,15 +381,20 @@ int disco_gpu_phase_finish_contained(disco_ctx *ctx)
     return record(ctx, EV_FINISH);
 }
 
-int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
+// Edge pass over the query reads [part_lo, part_hi) of this context's share [q_lo, q_hi).  part_lo == q_lo starts the
+// pass (adjacency cursor and counters reset, buffer sized for the whole share); later parts append.  A caller that
+// overlaps communication with compute (multigpu.py) runs the share in a few parts; everybody else runs one.
+int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uint64_t part_lo, uint64_t part_hi)
 {
     if (!ctx || !ctx->begun || !ctx->have_contained) return fail(ctx, DISCO_E_ARG, "containment pass not finished");
-    if (q_lo > q_hi || q_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad query range");
+    if (q_lo > q_hi || q_hi > ctx->reads.n || part_lo < q_lo || part_hi > q_hi || part_lo > part_hi) return fail(ctx, DISCO_E_ARG, "bad query range");
     CK(cudaSetDevice(ctx->device));
-    const uint64_t nq = q_hi - q_lo;
+    const bool first = part_lo == q_lo;
+    if (!first && !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass parts must start at q_lo");
+    const uint64_t nq = q_hi - q_lo, np = part_hi - part_lo;
     SearchParams p{};
     p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets, ctx->d_filter, (uint32_t)(ctx->filter_bits ? ctx->filter_bits - 1 : 0)};
-    p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
+    p.K = ctx->K; p.cap = ctx->cap; p.q_lo = part_lo; p.q_hi = part_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.contained_bits = ctx->d_bits; p.rows_cursor = ctx->d_cursors + CUR_ROWS; p.rowinfo = ctx->d_rowinfo;
     // adjacency capacity: start from 48 entries per query read (30x, 150 bp, minOverlap 50 needs ~33), bounded by free
@@ -400,13 +408,23 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
         CK(cudaMalloc(&ctx->d_rows, want * sizeof(uint64_t)));
         ctx->rows_cap = want;
     }
+    ctx->d_rows_active = ctx->d_rows;
+    const uint64_t cursor_before = first ? 0 : ctx->rows_used;
+    unsigned long long st_before[ST_COUNT] = {};
+    if (!first) {
+        CK(cudaMemcpyAsync(st_before, ctx->d_stats_e, sizeof st_before, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     for (int attempt = 0;; attempt++) {
-        CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, 4 * sizeof(unsigned long long), ctx->stream)); // 3 work counters + CUR_ROWS
-        CK(cudaMemsetAsync(ctx->d_stats_e, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
-        if (attempt) CK(cudaMemsetAsync(ctx->d_rowinfo + q_lo, 0, nq * sizeof(uint64_t), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, 3 * sizeof(unsigned long long), ctx->stream)); // 3 work counters
+        const unsigned long long cb = cursor_before;
+        CK(cudaMemcpyAsync(ctx->d_cursors + CUR_ROWS, &cb, sizeof cb, cudaMemcpyHostToDevice, ctx->stream));
+        if (first) CK(cudaMemsetAsync(ctx->d_stats_e, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
+        else if (attempt) CK(cudaMemcpyAsync(ctx->d_stats_e, st_before, sizeof st_before, cudaMemcpyHostToDevice, ctx->stream));
+        if (attempt) CK(cudaMemsetAsync(ctx->d_rowinfo + part_lo, 0, np * sizeof(uint64_t), ctx->stream));
         p.rows = ctx->d_rows; p.rows_cap = ctx->rows_cap;
         { int rc = record(ctx, EV_EDGES_K0); if (rc) return rc; }
-        if (nq) {
+        if (np) {
             CK(launch_search_edges(p, ctx->num_sms, ctx->stream, ctx->ev[EV_PROBE_K1], ctx->ev[EV_VERIFY_K1]));
             ctx->ev_done[EV_PROBE_K1] = ctx->ev_done[EV_VERIFY_K1] = !getenv("DISCO_FUSED");
         }
@@ -415,22 +433,40 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
         CK(cudaMemcpyAsync(cur, ctx->d_cursors + CUR_WORK3, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream)); // [1] = CUR_ROWS
         CK(cudaMemcpyAsync(st, ctx->d_stats_e, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        ctx->rows_used = cur[1];
         ctx->stats.raw_directed_edges = st[ST_ENTRIES];
         ctx->stats.max_degree = st[ST_MAXDEG];
-        if (!st[ST_OVERFLOW]) break;
+        if (!st[ST_OVERFLOW]) {
+            ctx->rows_used = cur[1];
+            if (first) ctx->acc_probe = ctx->acc_verify = ctx->acc_exact = ctx->acc_edges = 0.f;
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, ctx->ev[EV_EDGES_K0], ctx->ev[EV_EDGES_K1]) == cudaSuccess) ctx->acc_edges += t;
+            if (ctx->ev_done[EV_PROBE_K1] && np) {
+                if (cudaEventElapsedTime(&t, ctx->ev[EV_EDGES_K0], ctx->ev[EV_PROBE_K1]) == cudaSuccess) ctx->acc_probe += t;
+                if (cudaEventElapsedTime(&t, ctx->ev[EV_PROBE_K1], ctx->ev[EV_VERIFY_K1]) == cudaSuccess) ctx->acc_verify += t;
+                if (cudaEventElapsedTime(&t, ctx->ev[EV_VERIFY_K1], ctx->ev[EV_EDGES_K1]) == cudaSuccess) ctx->acc_exact += t;
+            }
+            break;
+        }
         if (attempt >= 2) return fail(ctx, DISCO_E_NOMEM, "adjacency buffer overflow after retry (%llu entries needed)", cur[1]);
-        // slices are handed out per warp, so the slack differs between runs: add one slice per resident warp
-        const uint64_t need = cur[1] + (uint64_t)ctx->num_sms * 64 * 1024;
+        // grow (keeping earlier parts) and redo this part.  Slices are handed out per warp, so the slack differs between
+        // runs: add one slice per resident warp; scale for the parts still to come
+        uint64_t need = cur[1] + (uint64_t)ctx->num_sms * 64 * 1024;
+        if (np && np < nq) need += (cur[1] - cursor_before) * ((q_hi - part_hi) / np + 1);
+        uint64_t *nr = nullptr;
+        CK(cudaMalloc(&nr, need * sizeof(uint64_t)));
+        if (cursor_before) CK(cudaMemcpyAsync(nr, ctx->d_rows, cursor_before * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
         dfree(ctx->d_rows);
-        ctx->rows_cap = 0;
-        CK(cudaMalloc(&ctx->d_rows, need * sizeof(uint64_t)));
+        ctx->d_rows = ctx->d_rows_active = nr;
         ctx->rows_cap = need;
+        if (!first) st_before[ST_OVERFLOW] = 0;
     }
     ctx->stats.edge_capacity = ctx->rows_cap;
     ctx->have_edges = true;
     return record(ctx, EV_EDGES);
 }
+
+int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi) { return disco_gpu_phase_edges_part(ctx, q_lo, q_hi, q_lo, q_hi); }
 
 int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
 {
@@ -438,7 +474,7 @@ int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
     if (u_lo > u_hi || u_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad node range");
     CK(cudaSetDevice(ctx->device));
     ReduceParams p{};
-    p.reads = ctx->reads; p.rows = ctx->d_rows; p.rowinfo = ctx->d_rowinfo; p.u_lo = u_lo; p.u_hi = u_hi;
+    p.reads = ctx->reads; p.rows = ctx->d_rows_active; p.rowinfo = ctx->d_rowinfo; p.u_lo = u_lo; p.u_hi = u_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.maxdeg = (int)std::max<uint64_t>(ctx->stats.max_degree, 1);
     if ((size_t)p.maxdeg * 25 + 512 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
@@ -533,7 +569,7 @@ int disco_gpu_get_row(disco_ctx *ctx, uint64_t read, disco_edge *out, uint64_t c
     if (deg > capacity) return fail(ctx, DISCO_E_ARG, "capacity too small");
     std::vector<uint64_t> e(deg);
     if (deg) {
-        CK(cudaMemcpyAsync(e.data(), ctx->d_rows + rowinfo_start(ri), deg * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(e.data(), ctx->d_rows_active + rowinfo_start(ri), deg * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     for (auto &x : e) x &= ~kElimBit;
@@ -570,9 +606,8 @@ int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out)
     s.ms_finish_contained = ms(EV_CONTAINED, EV_FINISH); s.ms_table_nc = ms(EV_FINISH, EV_TABLE_NC);
     s.ms_edges = ms(EV_TABLE_NC, EV_EDGES); s.ms_mark = ms(EV_EDGES, EV_MARK); s.ms_emit = ms(EV_MARK, EV_EMIT);
     s.ms_total = ms(EV_T0, EV_EMIT);
-    s.ms_edges_kernel = ms(EV_EDGES_K0, EV_EDGES_K1); s.ms_contained_kernel = ms(EV_CONT_K0, EV_CONT_K1);
-    s.ms_edges_probe = ms(EV_EDGES_K0, EV_PROBE_K1); s.ms_edges_verify = ms(EV_PROBE_K1, EV_VERIFY_K1);
-    s.ms_edges_exact = ms(EV_VERIFY_K1, EV_EDGES_K1);
+    s.ms_edges_kernel = ctx->acc_edges; s.ms_contained_kernel = ms(EV_CONT_K0, EV_CONT_K1);
+    s.ms_edges_probe = ctx->acc_probe; s.ms_edges_verify = ctx->acc_verify; s.ms_edges_exact = ctx->acc_exact;
     *out = s;
     return DISCO_OK;
 }
@@ -606,7 +641,7 @@ int disco_gpu_reserve_rows(disco_ctx *ctx, uint64_t n_entries)
     if (ctx->rows_used) CK(cudaMemcpyAsync(nr, ctx->d_rows, ctx->rows_used * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     dfree(ctx->d_rows);
-    ctx->d_rows = nr;
+    ctx->d_rows = ctx->d_rows_active = nr;
     ctx->rows_cap = n_entries;
     ctx->stats.edge_capacity = n_entries;
     return DISCO_OK;
@@ -619,6 +654,14 @@ int disco_gpu_move_rows(disco_ctx *ctx, uint64_t dst_offset)
     if (dst_offset < ctx->rows_used || dst_offset + ctx->rows_used > ctx->rows_cap) return fail(ctx, DISCO_E_ARG, "move_rows: bad destination");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemcpyAsync(ctx->d_rows + dst_offset, ctx->d_rows, ctx->rows_used * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    return DISCO_OK;
+}
+
+int disco_gpu_use_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entries)
+{
+    if (!ctx || !ctx->have_edges || !d_rows) return fail(ctx, DISCO_E_ARG, "edge pass not finished");
+    (void)n_entries;
+    ctx->d_rows_active = const_cast<uint64_t *>(d_rows); // caller-owned; must outlive phase_reduce / get_row
     return DISCO_OK;
 }
 
@@ -637,6 +680,7 @@ int disco_gpu_adopt_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entr
     dfree(ctx->d_rows);
     ctx->rows_cap = 0;
     CK(cudaMalloc(&ctx->d_rows, std::max<uint64_t>(n_entries, 1) * sizeof(uint64_t)));
+    ctx->d_rows_active = ctx->d_rows;
     ctx->rows_cap = ctx->rows_used = n_entries;
     if (n_entries) CK(cudaMemcpyAsync(ctx->d_rows, d_rows, n_entries * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
     return DISCO_OK;

@@ -19,7 +19,7 @@ EXPORTS = [
     "disco_gpu_phase_contained", "disco_gpu_phase_finish_contained", "disco_gpu_phase_edges", "disco_gpu_phase_reduce",
     "disco_gpu_dev_contained_keys", "disco_gpu_dev_rowinfo", "disco_gpu_dev_rows", "disco_gpu_rebase_rows",
     "disco_gpu_adopt_rows", "disco_gpu_set_max_degree", "disco_gpu_sync", "disco_gpu_reserve_rows", "disco_gpu_move_rows",
-    "disco_gpu_set_rows_used",
+    "disco_gpu_set_rows_used", "disco_gpu_use_rows", "disco_gpu_phase_edges_part",
 ]
 
 
@@ -81,6 +81,8 @@ def lib():
         L.disco_gpu_reserve_rows.argtypes = [vp, u64]
         L.disco_gpu_move_rows.argtypes = [vp, u64]
         L.disco_gpu_set_rows_used.argtypes = [vp, u64]
+        L.disco_gpu_use_rows.argtypes = [vp, vp, u64]
+        L.disco_gpu_phase_edges_part.argtypes = [vp, u64, u64, u64, u64]
         L.disco_gpu_sync.argtypes = [vp]
         _lib = L
     return _lib
@@ -155,6 +157,12 @@ class GpuBuildGraph:
 
     def phase_edges(self, lo, hi):
         self._ck(self._L.disco_gpu_phase_edges(self._h, lo, hi), "phase_edges")
+
+    def phase_edges_part(self, lo, hi, part_lo, part_hi):
+        self._ck(self._L.disco_gpu_phase_edges_part(self._h, lo, hi, part_lo, part_hi), "phase_edges_part")
+
+    def use_rows(self, d_rows_ptr: int, n_entries: int):
+        self._ck(self._L.disco_gpu_use_rows(self._h, C.c_void_p(d_rows_ptr), n_entries), "use_rows")
 
     def phase_reduce(self, lo, hi):
         self._ck(self._L.disco_gpu_phase_reduce(self._h, lo, hi), "phase_reduce")

@@ -44,6 +44,9 @@ class GpuTensors:
     def rows_buffer(self, n):
         return torch.as_tensor(_DevArray(self.g.dev_rows()[0], n), device=self.device)
 
+    def rows_slice(self, start, n):
+        return torch.as_tensor(_DevArray(self.g.dev_rows()[0] + 8 * start, n), device=self.device)
+
     def set_rows_used(self, n):
         self.g.set_rows_used(n)
 
@@ -106,9 +109,15 @@ def exchange_adjacency(t, max_degree: int, lo: int, hi: int, rank: int, world: i
 
 
 class ShardedBuildGraph:
-    def __init__(self, g, rank: int, world: int, group=None, tensors=None):
+    """Mode A driver.  `parts` > 1 pipelines the adjacency exchange with the edge pass: the local query range is searched
+    in `parts` pieces and the all-gather of piece c runs on the NCCL stream while piece c+1 is being searched."""
+
+    def __init__(self, g, rank: int, world: int, group=None, tensors=None, parts: int = 4):
         self.g, self.rank, self.world, self.group = g, rank, world, group
         self.t = tensors or GpuTensors(g, torch.device("cuda", torch.cuda.current_device()))
+        self.parts = max(1, parts)
+        self.big = None           # gathered adjacency, kept across calls
+        self.comm = None
 
     def build_graph(self, min_overlap: int, max_edge_per_kmer: int = 4):
         g, n = self.g, self.g.n
@@ -119,8 +128,58 @@ class ShardedBuildGraph:
         allreduce_unsigned_min(self.t.keys(), self.group)
         g.phase_finish_contained()
         g.phase_table(True)
-        g.phase_edges(lo, hi)
-        maxdeg, _, _ = exchange_adjacency(self.t, int(g.stats()["max_degree"]), lo, hi, self.rank, self.world, self.group)
+        if self.parts == 1 or not hasattr(self.t, "rows_slice"):
+            g.phase_edges(lo, hi)
+            maxdeg, _, _ = exchange_adjacency(self.t, int(g.stats()["max_degree"]), lo, hi, self.rank, self.world, self.group)
+        else:
+            maxdeg = self._edges_pipelined(lo, hi)
         g.set_max_degree(maxdeg)
         g.phase_reduce(lo, hi)
         g.sync()
+
+    def _edges_pipelined(self, lo, hi):
+        g, t, rank, world = self.g, self.t, self.rank, self.world
+        dev = t.device
+        if self.comm is None:
+            self.comm = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        bounds = [lo + (hi - lo) * c // self.parts for c in range(self.parts + 1)]
+        region = 0                      # entries of the gathered buffer handed out so far
+        used_prev = 0                   # where this part's rows start in the local buffer
+        works = []
+        for c in range(self.parts):
+            g.phase_edges_part(lo, hi, bounds[c], bounds[c + 1])      # returns with the part finished (reads the cursor)
+            cnt = t.rows_used() - used_prev
+            meta = torch.tensor([cnt], device=dev, dtype=torch.int64)
+            allm = [torch.empty_like(meta) for _ in range(world)]
+            dist.all_gather(allm, meta, group=self.group)
+            slot = max(max(int(m[0]) for m in allm), 1)
+            # the local rows of this part become the slot [region + rank*slot, +slot) of the gathered buffer; pad the
+            # local buffer to a full slot so that the (equal-sized) all-gather never reads what the next part writes
+            t.reserve_rows(used_prev + slot)
+            t.set_rows_used(used_prev + slot)
+            t.rebase_rows(bounds[c], bounds[c + 1], region + rank * slot - used_prev)
+            need = region + world * slot
+            if self.big is None or self.big.numel() < need:
+                est = need if c == self.parts - 1 else int(need * self.parts / (c + 1) * 1.05)
+                nb = torch.empty(est, dtype=torch.int64, device=dev)
+                if self.big is not None and region:
+                    for w in works:
+                        w.wait()
+                    nb[:region].copy_(self.big[:region])
+                self.big = nb
+            src = t.rows_slice(used_prev, slot)
+            self.comm.wait_stream(main)
+            with torch.cuda.stream(self.comm):
+                works.append(dist.all_gather_into_tensor(self.big[region:region + world * slot], src, group=self.group, async_op=True))
+            region += world * slot
+            used_prev += slot
+        st = g.stats()
+        meta = torch.tensor([int(st["max_degree"])], device=dev, dtype=torch.int64)
+        dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=self.group)
+        dist.all_reduce(t.rowinfo(), op=dist.ReduceOp.SUM, group=self.group)  # entries of rows owned by other ranks are zero here
+        for w in works:
+            w.wait()
+        main.wait_stream(self.comm)
+        g.use_rows(self.big.data_ptr(), region)
+        return int(meta[0])

@@ -112,6 +112,8 @@ int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained);
 int disco_gpu_phase_contained(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi);
 int disco_gpu_phase_finish_contained(disco_ctx *ctx);
 int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi);
+/* the same pass in pieces: parts of [q_lo,q_hi) in ascending order, the first one starting at q_lo; rows append */
+int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uint64_t part_lo, uint64_t part_hi);
 int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi);
 /* device pointers for collectives: containment keys u64[n] (all-reduce MIN), row info u64[n] (all-reduce SUM after
  * rebase), adjacency entries u64[*n_entries] (all-gather) */
@@ -122,12 +124,14 @@ void *disco_gpu_dev_rows(disco_ctx *ctx, uint64_t *n_entries);
  *   reserve_rows : make the adjacency buffer hold at least n_entries (contents kept)
  *   move_rows    : move this rank's rows from the front of the buffer to dst_offset (regions may not overlap)
  *   rebase_rows  : add `base` to the start of every local row in [u_lo,u_hi) (before the row-info all-reduce)
- *   set_rows_used: entries in use after the gather
+ *   set_rows_used: entries in use after the gather / where the next part of the edge pass starts appending
+ *   use_rows     : let the reduction read a caller-owned device buffer (the gathered adjacency) instead, no copy
  *   adopt_rows   : alternative: replace the adjacency by a copy of d_rows[n_entries] */
 int disco_gpu_reserve_rows(disco_ctx *ctx, uint64_t n_entries);
 int disco_gpu_move_rows(disco_ctx *ctx, uint64_t dst_offset);
 int disco_gpu_rebase_rows(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi, uint64_t base);
 int disco_gpu_set_rows_used(disco_ctx *ctx, uint64_t n_entries);
+int disco_gpu_use_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entries);
 int disco_gpu_adopt_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entries);
 /* largest row length over all ranks (sizes the reduction kernel's shared memory) */
 int disco_gpu_set_max_degree(disco_ctx *ctx, uint64_t max_degree);
