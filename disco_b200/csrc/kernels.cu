@@ -175,6 +175,8 @@ __device__ __forceinline__ void stage_read_pre(uint64_t myword, int L, uint32_t 
     __syncwarp();
 }
 
+__device__ __forceinline__ bool is_contained(const uint32_t *bits, uint32_t r) { return (__ldg(bits + (r >> 5)) >> (r & 31)) & 1; }
+
 __device__ __forceinline__ int read_len(const ReadsView &rv, uint64_t r)
 {
     return rv.uniform_len ? rv.uniform_len : (int)__ldg(rv.len + r);
@@ -473,7 +475,7 @@ __device__ void search_edges_slow(const SearchParams &p, const WarpSmem &s, uint
             uint64_t key = 0;
             if (lane <= limit && v != kEmptySlot && (uint32_t)(v >> 33) == tag) {
                 const uint32_t rec = (uint32_t)v, r2 = rec >> 1;
-                bool seen = (r2 == (uint32_t)r1);
+                bool seen = (r2 == (uint32_t)r1) || (p.skip_contained && is_contained(p.contained_bits, r2));
                 for (int k = 0; k < nrow && !seen; k++) seen = (uint32_t)entry_nbr(s.row[k]) == r2;
                 if (!seen) {
                     const int type = cand_type(rec & 1, (int)((v >> 32) & 1) == fq);
@@ -652,6 +654,11 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
                             // not this read itself: OverlapGraph.cpp:421 / :655
                             const bool match = !empty && (uint32_t)(v[q] >> 33) == tag && ((uint32_t)v[q] >> 1) != (uint32_t)r1;
                             mbits |= (unsigned)match << q;
+                        }
+                        if (MODE == MODE_EDGES && mbits && p.skip_contained) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+                                if (((mbits >> q) & 1) && is_contained(p.contained_bits, (uint32_t)v[q] >> 1)) mbits &= ~(1u << q);
                         }
                         if (mbits) {
                             const int cnt = __popc(mbits);
@@ -926,6 +933,11 @@ __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
                             hole |= empty;
                             const bool match = !empty && (uint32_t)(v[q] >> 33) == tag && ((uint32_t)v[q] >> 1) != (uint32_t)r1; // :655
                             mbits |= (unsigned)match << q;
+                        }
+                        if (mbits && p.skip_contained) { // "ignore contained reads" (HashTable.cpp:533); the bitmap sits in L2
+#pragma unroll
+                            for (int q = 0; q < 4; q++)
+                                if (((mbits >> q) & 1) && is_contained(p.contained_bits, (uint32_t)v[q] >> 1)) mbits &= ~(1u << q);
                         }
                         if (mbits) {
                             const int cnt = __popc(mbits);

@@ -53,6 +53,7 @@ struct SearchParams {
     unsigned long long *best; // n keys, ~0 = not contained
     // edge pass
     const uint32_t *contained_bits;
+    int skip_contained; // the table still holds contained reads (built once): drop them as candidates (HashTable.cpp:533)
     uint64_t *rows;
     uint64_t rows_cap;
     unsigned long long *rows_cursor;

@@ -106,6 +106,8 @@ int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out);
 /* ---- phase-level entry points (multi-GPU: query reads sharded by id, table and reads replicated; mirrors
  * BuildGraphMPI/src/OverlapGraph.cpp:524-529 and :293-295).  disco_gpu_build_graph() == the sequence
  *   table(0) -> contained(0,n) -> finish_contained -> table(1) -> edges(0,n) -> reduce(0,n).
+ * table(1), the rebuild without the contained reads, is optional: when it is skipped the edge pass drops contained
+ * candidates through the bitmap (same results, slower probes; worth it only when the table is replicated on many GPUs).
  * Between phases the host exchanges the buffers exposed below with NCCL. ---------------------------------------- */
 int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_kmer);
 int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained);

@@ -117,7 +117,7 @@ def test_sharded_exchange_gloo(world):
         assert np.array_equal(k, keys)
         assert len(adopted) == world * slot
         assert md == max(mds)
-        assert log == ["begin", "table0", "contained", "finish", "table1", "edges", "reduce"]
+        assert log == ["begin", "table0", "contained", "finish"] + (["table1"] if world <= 2 else []) + ["edges", "reduce"]
         # every row info entry must point at that read's own row inside the gathered array
         for r in range(world):
             base = r * slot
