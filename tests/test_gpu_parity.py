@@ -57,8 +57,13 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("single_table", [False, True], ids=["rebuild", "single_table"])
 @pytest.mark.parametrize("name,make,m", CASES, ids=[c[0] for c in CASES])
-def test_against_oracle(name, make, m):
+def test_against_oracle(name, make, m, single_table, monkeypatch):
+    """single_table: skip the rebuild without contained reads, the edge pass filters them through the bitmap instead
+    (what the sharded driver does beyond two ranks) -- results must not change."""
+    if single_table:
+        monkeypatch.setenv("DISCO_SINGLE_TABLE", "1")
     rs = make()
     records = rs.strings()
     o = oracle_forms(records, m)
@@ -76,7 +81,10 @@ def test_against_oracle(name, make, m):
         bg.close()
 
 
-def test_cap_fires_rows_match_oracle():
+@pytest.mark.parametrize("single_table", [False, True], ids=["rebuild", "single_table"])
+def test_cap_fires_rows_match_oracle(single_table, monkeypatch):
+    if single_table:
+        monkeypatch.setenv("DISCO_SINGLE_TABLE", "1")
     rs = synth.repeats(4000, 150, seed=31)
     records = rs.strings()
     o = oracle_forms(records, 50)
