@@ -64,6 +64,16 @@ struct disco_ctx {
     unsigned long long *d_stats_c = nullptr;  // containment pass
     unsigned long long *d_stats_e = nullptr;  // edge pass + reduction
     float acc_probe = 0.f, acc_verify = 0.f, acc_exact = 0.f, acc_edges = 0.f; // edge-pass kernel times summed over parts
+    // key-sharded mode (Mode B): this context holds shard `shard_rank` of `shard_world` of the table and the adjacency
+    // rows of its own query range; the other shards are reached through peer-mapped pointers (CUDA IPC)
+    uint32_t shard_world = 1, shard_rank = 0;
+    struct PeerSet {
+        const uint64_t **d_ptrs = nullptr;         // device array [DISCO_MAX_SHARDS]
+        void *opened[DISCO_MAX_SHARDS] = {};       // mappings this context opened (to close them again)
+        cudaIpcMemHandle_t handle[DISCO_MAX_SHARDS] = {};
+        bool ready = false;
+    } peer_table, peer_rows;
+    uint64_t *d_bounds = nullptr; // read-id bounds of the ranks' query ranges [shard_world + 1]
     cudaEvent_t ev[EV_COUNT] = {};
     bool ev_done[EV_COUNT] = {};
     disco_stats stats{};
@@ -121,6 +131,24 @@ void free_reads(disco_ctx *c)
     dfree(c->d_words); dfree(c->d_len); dfree(c->d_stage);
     c->stage_words = 0;
     c->reads = ReadsView{};
+}
+
+void close_peers(disco_ctx::PeerSet &ps)
+{
+    for (int r = 0; r < DISCO_MAX_SHARDS; r++) {
+        if (ps.opened[r]) cudaIpcCloseMemHandle(ps.opened[r]);
+        ps.opened[r] = nullptr;
+    }
+    ps.ready = false;
+}
+
+TableView table_view(const disco_ctx *c)
+{
+    TableView tv{};
+    tv.slots = c->d_slots; tv.nbuckets = c->nbuckets; tv.filter = c->d_filter;
+    tv.filter_mask = (uint32_t)(c->filter_bits ? c->filter_bits - 1 : 0);
+    tv.peers = c->peer_table.d_ptrs; tv.world = c->shard_world; tv.rank = c->shard_rank;
+    return tv;
 }
 
 int record(disco_ctx *ctx, int which)
@@ -226,6 +254,8 @@ void disco_gpu_destroy(disco_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    close_peers(ctx->peer_table); close_peers(ctx->peer_rows);
+    dfree(ctx->peer_table.d_ptrs); dfree(ctx->peer_rows.d_ptrs); dfree(ctx->d_bounds);
     free_run_buffers(ctx);
     free_reads(ctx);
     dfree(ctx->d_cursors); dfree(ctx->d_stats_c); dfree(ctx->d_stats_e);
@@ -295,7 +325,8 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
             uint64_t nb = 3 * n;
-            if (nb * 32 > free_b / 10) nb = n + n / 2;
+            if (nb * 32 > free_b / 10 * ctx->shard_world) nb = n + n / 2;
+            nb = (nb + ctx->shard_world - 1) / ctx->shard_world; // key-sharded: buckets of this GPU's shard
             ctx->nbuckets = std::max<uint64_t>(1024, nb);
         }
         CK(cudaMalloc(&ctx->d_slots, ctx->nbuckets * 4 * sizeof(uint64_t)));
@@ -322,7 +353,7 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
     CK(cudaMemsetAsync(ctx->d_stats_e, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
     ctx->stats = disco_stats{};
     ctx->stats.n_reads = n;
-    ctx->stats.table_buckets = ctx->nbuckets;
+    ctx->stats.table_buckets = ctx->nbuckets * ctx->shard_world;
     for (auto &d : ctx->ev_done) d = false;
     ctx->n_contained = ctx->n_edges = 0;
     ctx->begun = true;
@@ -337,7 +368,7 @@ int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained)
     CK(cudaMemsetAsync(ctx->d_slots, 0xFF, ctx->nbuckets * 4 * sizeof(uint64_t), ctx->stream));
     if (ctx->d_filter) CK(cudaMemsetAsync(ctx->d_filter, 0, ctx->filter_bits / 8, ctx->stream));
     ctx->table_has_contained = !exclude_contained;
-    TableView tv{ctx->d_slots, ctx->nbuckets, ctx->d_filter, (uint32_t)(ctx->filter_bits ? ctx->filter_bits - 1 : 0)};
+    const TableView tv = table_view(ctx);
     CK(launch_table_insert(ctx->reads, tv, ctx->K, exclude_contained ? ctx->d_bits : nullptr, ctx->num_sms, ctx->stream));
     return record(ctx, exclude_contained ? EV_TABLE_NC : EV_TABLE_ALL);
 }
@@ -346,10 +377,11 @@ int disco_gpu_phase_contained(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
 {
     if (!ctx || !ctx->begun) return fail(ctx, DISCO_E_ARG, "call disco_gpu_begin first");
     if (q_lo > q_hi || q_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad query range");
+    if (ctx->shard_world > 1 && !ctx->peer_table.ready) return fail(ctx, DISCO_E_ARG, "sharded table: import the peers' shards first (disco_gpu_import_peers)");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
     SearchParams p{};
-    p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets, ctx->d_filter, (uint32_t)(ctx->filter_bits ? ctx->filter_bits - 1 : 0)};
+    p.reads = ctx->reads; p.table = table_view(ctx);
     p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_c; p.best = ctx->d_best;
     int rc = record(ctx, EV_CONT_K0);
@@ -390,12 +422,13 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
 {
     if (!ctx || !ctx->begun || !ctx->have_contained) return fail(ctx, DISCO_E_ARG, "containment pass not finished");
     if (q_lo > q_hi || q_hi > ctx->reads.n || part_lo < q_lo || part_hi > q_hi || part_lo > part_hi) return fail(ctx, DISCO_E_ARG, "bad query range");
+    if (ctx->shard_world > 1 && !ctx->peer_table.ready) return fail(ctx, DISCO_E_ARG, "sharded table: import the peers' shards first (disco_gpu_import_peers)");
     CK(cudaSetDevice(ctx->device));
     const bool first = part_lo == q_lo;
     if (!first && !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass parts must start at q_lo");
     const uint64_t nq = q_hi - q_lo, np = part_hi - part_lo;
     SearchParams p{};
-    p.reads = ctx->reads; p.table = TableView{ctx->d_slots, ctx->nbuckets, ctx->d_filter, (uint32_t)(ctx->filter_bits ? ctx->filter_bits - 1 : 0)};
+    p.reads = ctx->reads; p.table = table_view(ctx);
     p.K = ctx->K; p.cap = ctx->cap; p.q_lo = part_lo; p.q_hi = part_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.contained_bits = ctx->d_bits; p.rows_cursor = ctx->d_cursors + CUR_ROWS; p.rowinfo = ctx->d_rowinfo;
@@ -471,20 +504,42 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
 
 int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi) { return disco_gpu_phase_edges_part(ctx, q_lo, q_hi, q_lo, q_hi); }
 
-int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
+namespace {
+int reduce_params(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi, ReduceParams &p)
 {
     if (!ctx || !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass not finished");
     if (u_lo > u_hi || u_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad node range");
-    CK(cudaSetDevice(ctx->device));
-    ReduceParams p{};
+    if (ctx->shard_world > 1 && !ctx->peer_rows.ready) return fail(ctx, DISCO_E_ARG, "sharded adjacency: import the peers' rows first (disco_gpu_import_peers)");
+    p = ReduceParams{};
     p.reads = ctx->reads; p.rows = ctx->d_rows_active; p.rowinfo = ctx->d_rowinfo; p.u_lo = u_lo; p.u_hi = u_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
+    p.peer_rows = ctx->peer_rows.d_ptrs; p.bounds = ctx->d_bounds; p.world = ctx->shard_world;
     p.maxdeg = (int)std::max<uint64_t>(ctx->stats.max_degree, 1);
     if ((size_t)p.maxdeg * 25 + 512 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
+    return DISCO_OK;
+}
+} // namespace
+
+// markTransitiveEdges for the nodes [u_lo, u_hi): sets the eliminated bit of their own entries
+int disco_gpu_phase_reduce_mark(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
+{
+    ReduceParams p;
+    int rc = reduce_params(ctx, u_lo, u_hi, p);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
     if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_mark(p, ctx->num_sms, ctx->stream));
-    int rc = record(ctx, EV_MARK);
+    return record(ctx, EV_MARK);
+}
+
+// removeTransitiveEdges + canonical selection for the nodes [u_lo, u_hi); every node's marks must be in place (in the
+// sharded mode: on every GPU -- the caller puts a barrier between the two calls)
+int disco_gpu_phase_reduce_emit(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
+{
+    ReduceParams p;
+    int rc = reduce_params(ctx, u_lo, u_hi, p);
     if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
     if (!ctx->d_edges) {
         const uint64_t want = std::max<uint64_t>(ctx->stats.raw_directed_edges / 4, 1 << 16);
         CK(cudaMalloc(&ctx->d_edges, want * sizeof(disco_edge)));
@@ -509,6 +564,112 @@ int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
     ctx->have_reduced = true;
     return record(ctx, EV_EMIT);
 }
+
+int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
+{
+    const int rc = disco_gpu_phase_reduce_mark(ctx, u_lo, u_hi);
+    return rc ? rc : disco_gpu_phase_reduce_emit(ctx, u_lo, u_hi);
+}
+
+// ---- key-sharded mode (Mode B) --------------------------------------------------------------------------------------
+int disco_gpu_set_shard(disco_ctx *ctx, uint32_t world, uint32_t rank)
+{
+    if (!ctx) return DISCO_E_ARG;
+    if (world < 1 || world > DISCO_MAX_SHARDS || rank >= world) return fail(ctx, DISCO_E_ARG, "bad shard %u of %u (at most %d)", rank, world, DISCO_MAX_SHARDS);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (world != ctx->shard_world || rank != ctx->shard_rank) {
+        close_peers(ctx->peer_table); close_peers(ctx->peer_rows);
+        free_run_buffers(ctx); // the table is sized per shard
+    }
+    ctx->shard_world = world; ctx->shard_rank = rank;
+    if (world > 1) {
+        if (!ctx->peer_table.d_ptrs) CK(cudaMalloc(&ctx->peer_table.d_ptrs, DISCO_MAX_SHARDS * sizeof(uint64_t *)));
+        if (!ctx->peer_rows.d_ptrs) CK(cudaMalloc(&ctx->peer_rows.d_ptrs, DISCO_MAX_SHARDS * sizeof(uint64_t *)));
+        if (!ctx->d_bounds) CK(cudaMalloc(&ctx->d_bounds, (DISCO_MAX_SHARDS + 1) * sizeof(uint64_t)));
+    }
+    return DISCO_OK;
+}
+
+int disco_gpu_export_mem(disco_ctx *ctx, int which, void *handle_out)
+{
+    if (!ctx || !handle_out) return DISCO_E_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == DISCO_IPC_HANDLE_BYTES, "IPC handle size");
+    void *ptr = which == DISCO_MEM_TABLE ? (void *)ctx->d_slots : which == DISCO_MEM_ROWS ? (void *)ctx->d_rows : nullptr;
+    if (!ptr) return fail(ctx, DISCO_E_ARG, "nothing to export (which = %d): buffer not allocated yet", which);
+    CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, ptr));
+    memcpy(handle_out, &h, sizeof h);
+    return DISCO_OK;
+}
+
+namespace {
+int check_import(disco_ctx *ctx, int which, const void *src, const uint64_t *bounds)
+{
+    if (!ctx || !src) return DISCO_E_ARG;
+    if (ctx->shard_world < 2) return fail(ctx, DISCO_E_ARG, "not in sharded mode (disco_gpu_set_shard)");
+    if (which != DISCO_MEM_TABLE && which != DISCO_MEM_ROWS) return fail(ctx, DISCO_E_ARG, "bad buffer selector %d", which);
+    if (which == DISCO_MEM_ROWS && !bounds) return fail(ctx, DISCO_E_ARG, "the adjacency needs the ranks' read-id bounds");
+    if (!(which == DISCO_MEM_TABLE ? (void *)ctx->d_slots : (void *)ctx->d_rows)) return fail(ctx, DISCO_E_ARG, "own buffer not allocated yet");
+    if (which == DISCO_MEM_ROWS)
+        for (uint32_t r = 0; r < ctx->shard_world; r++)
+            if (bounds[r] > bounds[r + 1] || bounds[r + 1] > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad read-id bounds");
+    return DISCO_OK;
+}
+
+int publish_peers(disco_ctx *ctx, int which, const uint64_t *const *ptrs, const uint64_t *bounds)
+{
+    disco_ctx::PeerSet &ps = which == DISCO_MEM_TABLE ? ctx->peer_table : ctx->peer_rows;
+    CK(cudaMemcpy(ps.d_ptrs, ptrs, DISCO_MAX_SHARDS * sizeof(uint64_t *), cudaMemcpyHostToDevice));
+    if (which == DISCO_MEM_ROWS) CK(cudaMemcpy(ctx->d_bounds, bounds, (ctx->shard_world + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    ps.ready = true;
+    return DISCO_OK;
+}
+} // namespace
+
+int disco_gpu_import_peers(disco_ctx *ctx, int which, const void *handles, const uint64_t *bounds)
+{
+    int rc = check_import(ctx, which, handles, bounds);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    disco_ctx::PeerSet &ps = which == DISCO_MEM_TABLE ? ctx->peer_table : ctx->peer_rows;
+    const cudaIpcMemHandle_t *hs = static_cast<const cudaIpcMemHandle_t *>(handles);
+    const uint64_t *ptrs[DISCO_MAX_SHARDS] = {};
+    for (uint32_t r = 0; r < ctx->shard_world; r++) {
+        if (r == ctx->shard_rank) { ptrs[r] = which == DISCO_MEM_TABLE ? ctx->d_slots : ctx->d_rows; continue; }
+        if (ps.opened[r] && memcmp(&ps.handle[r], &hs[r], sizeof(cudaIpcMemHandle_t)) != 0) { // the peer reallocated
+            cudaIpcCloseMemHandle(ps.opened[r]);
+            ps.opened[r] = nullptr;
+        }
+        if (!ps.opened[r]) {
+            CK(cudaIpcOpenMemHandle(&ps.opened[r], hs[r], cudaIpcMemLazyEnablePeerAccess));
+            ps.handle[r] = hs[r];
+        }
+        ptrs[r] = static_cast<const uint64_t *>(ps.opened[r]);
+    }
+    return publish_peers(ctx, which, ptrs, bounds);
+}
+
+// the same for shards that live in this process (one host process driving several contexts): plain device pointers; the
+// caller has enabled peer access between the devices involved
+int disco_gpu_import_peer_ptrs(disco_ctx *ctx, int which, const void *const *device_ptrs, const uint64_t *bounds)
+{
+    int rc = check_import(ctx, which, device_ptrs, bounds);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    close_peers(which == DISCO_MEM_TABLE ? ctx->peer_table : ctx->peer_rows);
+    const uint64_t *ptrs[DISCO_MAX_SHARDS] = {};
+    for (uint32_t r = 0; r < ctx->shard_world; r++) {
+        ptrs[r] = r == ctx->shard_rank ? (which == DISCO_MEM_TABLE ? ctx->d_slots : ctx->d_rows) : static_cast<const uint64_t *>(device_ptrs[r]);
+        if (!ptrs[r]) return fail(ctx, DISCO_E_ARG, "NULL pointer for shard %u", r);
+    }
+    return publish_peers(ctx, which, ptrs, bounds);
+}
+
+void *disco_gpu_dev_table(disco_ctx *ctx) { return ctx ? ctx->d_slots : nullptr; }
 
 int disco_gpu_build_graph(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_kmer)
 {

@@ -55,6 +55,25 @@ __device__ __forceinline__ void load_bucket(const uint64_t *slots, uint64_t b, u
                  : "l"(slots + 4 * b), "l"(pol));
 }
 
+// where the chain of fingerprint h starts: the shard (a peer pointer when the table is key-sharded) and the bucket in it
+struct Home {
+    const uint64_t *slots;
+    uint64_t b;
+};
+__device__ __forceinline__ uint32_t shard_of(const TableView &t, uint64_t h) { return (uint32_t)__umul64hi(h, (uint64_t)t.world); }
+__device__ __forceinline__ uint64_t shard_bucket(const TableView &t, uint64_t h)
+{
+    // the fraction of h * world left after taking the shard picks the bucket: uniform inside the shard
+    return __umul64hi(t.world > 1 ? h * (uint64_t)t.world : h, t.nbuckets);
+}
+__device__ __forceinline__ Home home_of(const TableView &t, uint64_t h)
+{
+    Home o;
+    o.slots = (t.world > 1) ? t.peers[shard_of(t, h)] : t.slots;
+    o.b = shard_bucket(t, h);
+    return o;
+}
+
 __device__ __forceinline__ bool filter_test(const TableView &t, uint64_t h, uint64_t pol)
 {
     if (!t.filter) return true;
@@ -229,8 +248,9 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
                 const uint32_t bit = (uint32_t)(h >> 13) & tv.filter_mask;
                 atomicOr(tv.filter + (bit >> 5), 1u << (bit & 31));
             }
-            uint64_t b = bucket_of(h, tv.nbuckets);
-            for (;;) {
+            const bool mine = !(tv.world > 1 && shard_of(tv, h) != tv.rank); // else another GPU's key (uniform within the quad)
+            uint64_t b = shard_bucket(tv, h);
+            while (mine) {
                 unsigned long long *slot = reinterpret_cast<unsigned long long *>(tv.slots) + 4 * b + sub;
                 const uint64_t cur = __ldcg(slot); // L2 (coherent) read: slots change under our feet
                 const unsigned empties = (__ballot_sync(qmask, cur == kEmptySlot) >> (quad * 4)) & 0xFu;
@@ -311,7 +331,8 @@ __global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, T
             const uint64_t hh = (rec & 1) ? hb : ha, val = (rec & 1) ? vb : va;
             const int ok_rec = __shfl_sync(FULL, (int)valid, owner);
             if (!ok_rec) continue; // uniform within the quad
-            uint64_t b = bucket_of(hh, tv.nbuckets);
+            if (tv.world > 1 && shard_of(tv, hh) != tv.rank) continue; // another GPU's key
+            uint64_t b = shard_bucket(tv, hh);
             for (;;) {
                 unsigned long long *slot = reinterpret_cast<unsigned long long *>(tv.slots) + 4 * b + sub;
                 const uint64_t cur = __ldcg(slot); // L2 (coherent) read: slots change under our feet
@@ -359,10 +380,11 @@ __global__ void __launch_bounds__(kThreads) k_contain_uniform(SearchParams p)
         const uint64_t h = canon_kmer_hash(A, R, L, 0, K, &fq);
         if (!filter_test(p.table, h, pol_keep)) continue; // cannot happen for a read in the table; kept for symmetry
         const uint32_t tag = slot_tag(h);
-        uint64_t b = bucket_of(h, p.table.nbuckets);
+        const Home home = home_of(p.table, h);
+        uint64_t b = home.b;
         for (;;) {
             uint64_t v[4];
-            load_bucket(p.table.slots, b, v, pol_stream);
+            load_bucket(home.slots, b, v, pol_stream);
             n_buckets++;
             bool hole = false;
 #pragma unroll
@@ -461,13 +483,14 @@ __device__ void search_edges_slow(const SearchParams &p, const WarpSmem &s, uint
         int fq;
         const uint64_t h = canon_kmer_hash(s.A, s.R, L1, j, K, &fq);
         const uint32_t tag = slot_tag(h);
-        uint64_t b = bucket_of(h, p.table.nbuckets);
+        const Home home = home_of(p.table, h);
+        uint64_t b = home.b;
         int nbest = 0, nvalid = 0;
         n_probes += (lane == 0);
         for (;;) {
             uint64_t bb = b + (lane >> 2);
             if (bb >= p.table.nbuckets) bb -= p.table.nbuckets;
-            const uint64_t v = __ldg(p.table.slots + 4 * bb + (lane & 3));
+            const uint64_t v = __ldg(home.slots + 4 * bb + (lane & 3));
             const unsigned empties = __ballot_sync(FULL, v == kEmptySlot);
             const int limit = empties ? ((__ffs(empties) - 1) | 3) : 31; // the chain ends in the first bucket with a hole
             n_buckets += (lane == 0) ? (unsigned)((limit >> 2) + 1) : 0u;
@@ -618,7 +641,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
                     n_probes++;
                     // most positions match no record at all: the L2-resident presence bit answers that without DRAM
                     pass = filter_test(p.table, h, pol_keep);
-                    if (pass) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table.slots + 4 * bucket_of(h, nbuckets)));
+                    if (pass && p.table.world <= 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table.slots + 4 * bucket_of(h, nbuckets)));
                 }
                 const unsigned m = __ballot_sync(FULL, pass);
                 if (pass) {
@@ -638,12 +661,13 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
                     const uint32_t jf = s.pj[i];
                     const int j = (int)(jf >> 1), fq = (int)(jf & 1);
                     const uint32_t tag = slot_tag(h);
-                    uint64_t b = bucket_of(h, nbuckets);
+                    const Home home = home_of(p.table, h);
+                    uint64_t b = home.b;
                     int pushed = 0;
                     for (int walked = 0;; walked++) {
                         if (MODE == MODE_EDGES && walked == kScanLimit) { s.ctrl[1] = 1; break; } // long chain: exact path
                         uint64_t v[4];
-                        load_bucket(p.table.slots, b, v, pol_stream);
+                        load_bucket(home.slots, b, v, pol_stream);
                         n_buckets++;
                         bool hole = false;
                         unsigned mbits = 0;
@@ -837,6 +861,9 @@ __host__ __device__ inline size_t verify_words_per_warp(int WP, int npos, int hc
 }
 __host__ __device__ inline size_t exact_words_per_warp(int WP, int rowcap) { return 2 * (size_t)WP + (size_t)rowcap + kBestMax + 2; }
 
+// SHARDED: the table is key-sharded over GPUs, buckets are read through NVLink peer pointers (a separate instantiation
+// so that the single-GPU kernel keeps its registers)
+template <bool SHARDED>
 __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
 {
     extern __shared__ uint64_t smem[];
@@ -884,7 +911,7 @@ __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
                     h = canon_kmer_hash(A, R, L1, j, K, &fq);
                     n_probes++;
                     pass = filter_test(p.table, h, pol_keep);
-                    if (pass) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table.slots + 4 * bucket_of(h, nbuckets)));
+                    if (!SHARDED && pass) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.table.slots + 4 * bucket_of(h, nbuckets)));
                 }
                 const unsigned m = __ballot_sync(FULL, pass);
                 if (pass) {
@@ -918,12 +945,15 @@ __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
                     const uint32_t jf = pj[i];
                     const int j = (int)(jf >> 1), fq = (int)(jf & 1);
                     const uint32_t tag = slot_tag(h);
-                    uint64_t b = bucket_of(h, nbuckets);
+                    const uint64_t *slots = p.table.slots;
+                    uint64_t b;
+                    if (SHARDED) { const Home home = home_of(p.table, h); slots = home.slots; b = home.b; }
+                    else b = bucket_of(h, nbuckets);
                     int pushed = 0;
                     for (int walked = 0;; walked++) {
                         if (walked == kScanLimit) { ctrl[1] = 1; break; } // long chain: exact path
                         uint64_t v[4];
-                        load_bucket(p.table.slots, b, v, pol_stream);
+                        load_bucket(slots, b, v, pol_stream);
                         n_buckets++;
                         bool hole = false;
                         unsigned mbits = 0;
@@ -1328,13 +1358,31 @@ __global__ void k_rebase_rowinfo(uint64_t *rowinfo, uint64_t lo, uint64_t hi, ui
     }
 }
 
+// pull the adjacency row described by `ri` into L2 (one 128-byte line per lane; rows longer than 512 entries: the head)
+__device__ __forceinline__ void prefetch_row(const uint64_t *rows, uint64_t ri, int lane)
+{
+    const int deg = (int)rowinfo_deg(ri);
+    if (lane * 16 < deg) asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + rowinfo_start(ri) + lane * 16));
+}
+
+// the buffer that holds the row of read v: local, or (range-partitioned adjacency) the owning GPU's through NVLink
+template <bool SHARDED>
+__device__ __forceinline__ const uint64_t *rows_of(const ReduceParams &p, uint64_t v)
+{
+    if (!SHARDED) return p.rows;
+    uint32_t r = 0;
+    for (uint32_t i = 1; i < p.world; i++) r += (v >= p.bounds[i]) ? 1u : 0u;
+    return p.peer_rows[r];
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // transitive reduction, pass 1: Myers marking of every node on the full graph (OverlapGraph.cpp:687-723).
 // Warp per node u; u's row lives in shared memory (neighbour id + orientation + state); for every neighbour v still
 // INPLAY, in ascending offset order, the warp streams v's row (coalesced) and eliminates common neighbours whose
 // orientations chain through v.  The result is the eliminated bit of u's own entries.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
+template <bool SHARDED>
+__global__ void __launch_bounds__(kThreads, 8) k_reduce_mark(ReduceParams p) // 32 registers: full occupancy, the kernel waits on dependent row fetches
 {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -1394,11 +1442,11 @@ __global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
                 const int t1 = entry_orient(best);
                 const uint64_t vri = p.rowinfo[entry_nbr(best)];
                 const int vd = (int)rowinfo_deg(vri);
-                const uint64_t vs = rowinfo_start(vri);
+                const uint64_t *vrow = rows_of<SHARDED>(p, entry_nbr(best)) + rowinfo_start(vri);
                 n_rows += (lane == 0); n_ent += (lane == 0) ? (unsigned long long)vd : 0ULL;
                 __syncwarp();
                 for (int q = lane; q < vd; q += 32) {
-                    const uint64_t e = __ldcg(p.rows + vs + q); // other warps may be setting eliminated bits: ignored
+                    const uint64_t e = __ldcg(vrow + q); // other warps may be setting eliminated bits: ignored
                     if (!chain_ok(t1, entry_orient(e))) continue;
                     // is w also a neighbour of u?  (markedNodes->find(read3), OverlapGraph.cpp:701)
                     const uint32_t w = (uint32_t)entry_nbr(e);
@@ -1426,7 +1474,8 @@ __global__ void __launch_bounds__(kThreads) k_reduce_mark(ReduceParams p)
 // together in the reference, OverlapGraph.cpp:717-718).  For each surviving entry u->w the warp finds the twin in
 // w's row; the lower id emits the canonical record (OverlapGraph.cpp:808).
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_reduce_emit(ReduceParams p)
+template <bool SHARDED>
+__global__ void __launch_bounds__(kThreads, 8) k_reduce_emit(ReduceParams p) // 32 registers: all 64 warps of an SM resident (latency bound)
 {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     disco_edge *out = reinterpret_cast<disco_edge *>(p.edges_out);
@@ -1441,19 +1490,26 @@ __global__ void __launch_bounds__(kThreads) k_reduce_emit(ReduceParams p)
             const int deg = (int)rowinfo_deg(ri);
             if (deg == 0) continue;
             const uint64_t start = rowinfo_start(ri);
+            if (u + 1 < ue) prefetch_row(p.rows, p.rowinfo[u + 1], lane);
             const int Lu = read_len(p.reads, u);
             for (int k0 = 0; k0 < deg; k0 += 32) {
                 const int k = k0 + lane;
                 const uint64_t e = (k < deg) ? p.rows[start + k] : kElimBit;
                 unsigned alive = __ballot_sync(FULL, !(e & kElimBit));
+                // the surviving entries' row infos are fetched together (one lane each) and their rows pulled into L2
+                // before the twins are looked up one after the other
+                uint64_t my_ri = 0;
+                if (!(e & kElimBit)) my_ri = p.rowinfo[entry_nbr(e)];
+                if (!SHARDED)
+                    for (unsigned m = alive; m; m &= m - 1) prefetch_row(p.rows, __shfl_sync(FULL, my_ri, __ffs(m) - 1), lane);
                 while (alive) {
                     const int src = __ffs(alive) - 1; alive &= alive - 1;
                     const uint64_t ee = __shfl_sync(FULL, e, src);
                     const uint64_t w = entry_nbr(ee);
                     const int orient = entry_orient(ee), offset = entry_offset(ee);
-                    const uint64_t wri = p.rowinfo[w];
+                    const uint64_t wri = __shfl_sync(FULL, my_ri, src);
                     const int wd = (int)rowinfo_deg(wri);
-                    const uint64_t ws = rowinfo_start(wri);
+                    const uint64_t *wrow = rows_of<SHARDED>(p, w) + rowinfo_start(wri);
                     const int Lw = read_len(p.reads, w);
                     n_rows += (lane == 0); n_ent += (lane == 0) ? (unsigned long long)wd : 0ULL;
                     // twin of u->w as seen from w (OverlapGraph.cpp:617-619)
@@ -1463,7 +1519,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_emit(ReduceParams p)
                         const int q = q0 + lane;
                         uint64_t te = 0;
                         bool hit = false;
-                        if (q < wd) { te = p.rows[ws + q]; hit = entry_nbr(te) == u; }
+                        if (q < wd) { te = __ldcg(wrow + q); hit = entry_nbr(te) == u; }
                         const unsigned hm = __ballot_sync(FULL, hit);
                         if (hm) {
                             const uint64_t t = __shfl_sync(FULL, te, __ffs(hm) - 1);
@@ -1691,7 +1747,8 @@ cudaError_t launch_search_edges(const SearchParams &p_in, int num_sms, cudaStrea
     SearchParams p = p_in;
     size_search(p, MODE_EDGES);
     const int WP = wp_of(p.reads.max_len);
-    cudaError_t e = launch_warps(k_edges_probe, p, probe_words_per_warp(WP, p.npos, p.hcap) * sizeof(uint64_t), num_sms, s);
+    const size_t pb = probe_words_per_warp(WP, p.npos, p.hcap) * sizeof(uint64_t);
+    cudaError_t e = p.table.world > 1 ? launch_warps(k_edges_probe<true>, p, pb, num_sms, s) : launch_warps(k_edges_probe<false>, p, pb, num_sms, s);
     if (e != cudaSuccess) return e;
     if (ev_probe_done) cudaEventRecord(ev_probe_done, s);
     const size_t vb = verify_words_per_warp(WP, p.npos, p.hcap, p.hset) * sizeof(uint64_t);
@@ -1758,18 +1815,20 @@ cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t 
     if (!warps) return cudaErrorInvalidConfiguration;
     const size_t smem = per_warp * warps;
     int grid = 0;
-    cudaError_t e = persistent_grid(k_reduce_mark, smem, num_sms, &grid, warps * 32);
+    auto kern = p.world > 1 ? k_reduce_mark<true> : k_reduce_mark<false>;
+    cudaError_t e = persistent_grid(kern, smem, num_sms, &grid, warps * 32);
     if (e != cudaSuccess) return e;
-    k_reduce_mark<<<grid, warps * 32, smem, s>>>(p);
+    kern<<<grid, warps * 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t s)
 {
     int grid = 0;
-    cudaError_t e = persistent_grid(k_reduce_emit, 0, num_sms, &grid);
+    auto kern = p.world > 1 ? k_reduce_emit<true> : k_reduce_emit<false>;
+    cudaError_t e = persistent_grid(kern, 0, num_sms, &grid);
     if (e != cudaSuccess) return e;
-    k_reduce_emit<<<grid, kThreads, 0, s>>>(p);
+    kern<<<grid, kThreads, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -35,10 +35,14 @@ struct ReadsView {
 };
 
 struct TableView {
-    uint64_t *slots;   // nbuckets * 4
-    uint64_t nbuckets;
+    uint64_t *slots;   // nbuckets * 4 (this GPU's shard when world > 1)
+    uint64_t nbuckets; // buckets per shard
     uint32_t *filter;  // presence bitmap over a second slice of the k-mer hash, small enough to stay in L2 (or null)
     uint32_t filter_mask; // bits - 1 (power of two)
+    // key-sharded table (Mode B, BuildGraphMPIRMA's partitioning): shard = mulhi(hash, world); every GPU inserts the
+    // keys of its own shard and probes the other shards through NVLink peer pointers.  world <= 1: single table.
+    const uint64_t *const *peers; // device array [world] of shard base pointers (peer-mapped; [rank] == slots)
+    uint32_t world, rank;
 };
 
 struct SearchParams {
@@ -70,6 +74,11 @@ struct ReduceParams {
     ReadsView reads;
     uint64_t *rows;
     const uint64_t *rowinfo;
+    // range-partitioned adjacency (Mode B): the row of read v lives on the GPU whose [bounds[r], bounds[r+1]) holds v,
+    // at peer_rows[r] + start(v).  world <= 1: every row is in `rows`.
+    const uint64_t *const *peer_rows; // device array [world]
+    const uint64_t *bounds;           // device array [world + 1]
+    uint32_t world;
     uint64_t u_lo, u_hi;
     unsigned long long *work_counter;
     unsigned long long *stats;

@@ -19,8 +19,11 @@ EXPORTS = [
     "disco_gpu_phase_contained", "disco_gpu_phase_finish_contained", "disco_gpu_phase_edges", "disco_gpu_phase_reduce",
     "disco_gpu_dev_contained_keys", "disco_gpu_dev_rowinfo", "disco_gpu_dev_rows", "disco_gpu_rebase_rows",
     "disco_gpu_adopt_rows", "disco_gpu_set_max_degree", "disco_gpu_sync", "disco_gpu_reserve_rows", "disco_gpu_move_rows",
-    "disco_gpu_set_rows_used", "disco_gpu_use_rows", "disco_gpu_phase_edges_part",
+    "disco_gpu_set_rows_used", "disco_gpu_use_rows", "disco_gpu_phase_edges_part", "disco_gpu_phase_reduce_mark",
+    "disco_gpu_phase_reduce_emit", "disco_gpu_set_shard", "disco_gpu_export_mem", "disco_gpu_import_peers",
+    "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table",
 ]
+MAX_SHARDS, IPC_HANDLE_BYTES, MEM_TABLE, MEM_ROWS = 8, 64, 0, 1
 
 
 class Stats(C.Structure):
@@ -70,6 +73,14 @@ def lib():
         L.disco_gpu_phase_finish_contained.argtypes = [vp]
         L.disco_gpu_phase_edges.argtypes = [vp, u64, u64]
         L.disco_gpu_phase_reduce.argtypes = [vp, u64, u64]
+        L.disco_gpu_phase_reduce_mark.argtypes = [vp, u64, u64]
+        L.disco_gpu_phase_reduce_emit.argtypes = [vp, u64, u64]
+        L.disco_gpu_set_shard.argtypes = [vp, u32, u32]
+        L.disco_gpu_export_mem.argtypes = [vp, i32, vp]
+        L.disco_gpu_import_peers.argtypes = [vp, i32, vp, vp]
+        L.disco_gpu_import_peer_ptrs.argtypes = [vp, i32, vp, vp]
+        L.disco_gpu_dev_table.argtypes = [vp]
+        L.disco_gpu_dev_table.restype = vp
         for f in ("disco_gpu_dev_contained_keys", "disco_gpu_dev_rowinfo"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = vp
@@ -166,6 +177,36 @@ class GpuBuildGraph:
 
     def phase_reduce(self, lo, hi):
         self._ck(self._L.disco_gpu_phase_reduce(self._h, lo, hi), "phase_reduce")
+
+    def phase_reduce_mark(self, lo, hi):
+        self._ck(self._L.disco_gpu_phase_reduce_mark(self._h, lo, hi), "phase_reduce_mark")
+
+    def phase_reduce_emit(self, lo, hi):
+        self._ck(self._L.disco_gpu_phase_reduce_emit(self._h, lo, hi), "phase_reduce_emit")
+
+    # key-sharded mode (Mode B)
+    def set_shard(self, world: int, rank: int):
+        self._ck(self._L.disco_gpu_set_shard(self._h, world, rank), "set_shard")
+
+    def export_mem(self, which: int) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        self._ck(self._L.disco_gpu_export_mem(self._h, which, buf), "export_mem")
+        return buf.raw
+
+    def import_peers(self, which: int, handles, bounds=None):
+        """handles: one IPC_HANDLE_BYTES blob per rank, in rank order; bounds: world + 1 read ids (adjacency only)"""
+        blob = b"".join(bytes(h) for h in handles)
+        b = (C.c_uint64 * len(bounds))(*bounds) if bounds is not None else None
+        self._ck(self._L.disco_gpu_import_peers(self._h, which, blob, b), "import_peers")
+
+    def import_peer_ptrs(self, which: int, ptrs, bounds=None):
+        """the same for shards owned by contexts of this process: device pointers in rank order"""
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        b = (C.c_uint64 * len(bounds))(*bounds) if bounds is not None else None
+        self._ck(self._L.disco_gpu_import_peer_ptrs(self._h, which, arr, b), "import_peer_ptrs")
+
+    def dev_table(self) -> int:
+        return self._L.disco_gpu_dev_table(self._h)
 
     def dev_contained_keys(self) -> int:
         return self._L.disco_gpu_dev_contained_keys(self._h)

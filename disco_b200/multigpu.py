@@ -1,5 +1,9 @@
 """Multi-GPU BuildGraph, one process per GPU (torch.distributed / NCCL is the plumbing).
 
+Two partitionings, as in the reference: Mode A = ShardedBuildGraph (BuildGraphMPI: everything replicated, queries split),
+described next, and Mode B = KeyShardedBuildGraph (BuildGraphMPIRMA: the hash table split by key, reached one-sidedly),
+described at that class.
+
 Partitioning = the reference's BuildGraphMPI ("distributed computation": src/BuildGraphMPI/src/OverlapGraph.cpp:524-529,
 :293-295): packed reads and hash table replicated on every rank, query reads split into contiguous read-id ranges.
 Where the MPI code gossips `int[numReads+1]` maps every few seconds (OverlapGraph.cpp:566-575, :225-234), the offline
@@ -187,3 +191,64 @@ class ShardedBuildGraph:
         main.wait_stream(self.comm)
         g.use_rows(self.big.data_ptr(), region)
         return int(meta[0])
+
+
+class KeyShardedBuildGraph:
+    """Mode B driver (BASELINE config 5; the partitioning of BuildGraphMPIRMA: src/BuildGraphMPIRMA/src/HashTable.cpp
+    keeps a slice of the table per rank and fetches remote buckets with one-sided MPI_Get).
+
+    Reads are replicated; the hash table is split by key (shard = mulhi(fingerprint, world)) and the adjacency by
+    query range -- neither is ever gathered, so the per-GPU footprint of both shrinks with the number of GPUs:
+      table build  : every rank scans all reads, inserts only its own keys (no communication), sets all filter bits
+      probes       : the kernels read remote buckets through NVLink peer pointers (CUDA IPC mappings of the shards)
+      containment  : keys u64[n] all-reduce(MIN), as in Mode A
+      reduction    : row info u64[n] all-reduce(SUM); neighbours' rows are read from their owner through NVLink
+    What the host exchanges: the IPC handles (64 bytes per rank, once per allocation), the two all-reduces, and the
+    barriers that order the phases across ranks."""
+
+    def __init__(self, g, rank: int, world: int, group=None, tensors=None):
+        from . import gpu as _gpu
+        self.g, self.rank, self.world, self.group = g, rank, world, group
+        self.t = tensors or GpuTensors(g, torch.device("cuda", torch.cuda.current_device()))
+        self.MEM_TABLE, self.MEM_ROWS, self.HANDLE = _gpu.MEM_TABLE, _gpu.MEM_ROWS, _gpu.IPC_HANDLE_BYTES
+        g.set_shard(world, rank)
+
+    def _barrier(self):
+        """Every rank's queued device work is finished when this returns (host-level: the phases are milliseconds)."""
+        self.g.sync()
+        flag = torch.zeros(1, dtype=torch.int64, device=self.t.device)
+        dist.all_reduce(flag, group=self.group)
+        flag.item()
+
+    def _attach(self, which, bounds=None):
+        """All-gather the IPC handles of `which` and map the peers' buffers."""
+        mine = torch.frombuffer(bytearray(self.g.export_mem(which)), dtype=torch.uint8).to(self.t.device)
+        every = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(every, mine, group=self.group)
+        self.g.import_peers(which, [bytes(h.cpu().numpy().tobytes()) for h in every], bounds)
+
+    def build_graph(self, min_overlap: int, max_edge_per_kmer: int = 4):
+        g, n = self.g, self.g.n
+        lo, hi = partition(n, self.rank, self.world)
+        bounds = [partition(n, r, self.world)[0] for r in range(self.world)] + [n]
+        g.begin(min_overlap, max_edge_per_kmer)
+        g.phase_table(False)
+        self._attach(self.MEM_TABLE)
+        self._barrier()                         # every shard complete before anybody probes it
+        g.phase_contained(lo, hi)
+        allreduce_unsigned_min(self.t.keys(), self.group)
+        g.phase_finish_contained()
+        self._barrier()                         # everybody done probing before the shards are rebuilt
+        g.phase_table(True)                     # own shard only: 1/world of the single-GPU cost
+        self._barrier()
+        g.phase_edges(lo, hi)                   # rows of the own query range stay here
+        meta = torch.tensor([int(g.stats()["max_degree"])], device=self.t.device, dtype=torch.int64)
+        dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=self.group)
+        dist.all_reduce(self.t.rowinfo(), op=dist.ReduceOp.SUM, group=self.group)  # starts are offsets in the owner's buffer
+        g.set_max_degree(int(meta[0]))
+        self._attach(self.MEM_ROWS, bounds)     # after the pass: an overflow retry may have reallocated the rows
+        self._barrier()                         # every rank's rows complete before neighbours read them
+        g.phase_reduce_mark(lo, hi)
+        self._barrier()                         # emission reads the marks of remote neighbours
+        g.phase_reduce_emit(lo, hi)
+        self._barrier()                         # nobody may start overwriting rows while a peer still reads them

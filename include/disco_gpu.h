@@ -117,6 +117,11 @@ int disco_gpu_phase_edges(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi);
 /* the same pass in pieces: parts of [q_lo,q_hi) in ascending order, the first one starting at q_lo; rows append */
 int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uint64_t part_lo, uint64_t part_hi);
 int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi);
+/* the two halves of phase_reduce: markTransitiveEdges (OverlapGraph.cpp:687-723) and removeTransitiveEdges + emission
+ * (:731-761, :808).  Separate so that a multi-GPU caller can put a barrier between them (emit reads the marks of
+ * neighbouring nodes, which another GPU may own). */
+int disco_gpu_phase_reduce_mark(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi);
+int disco_gpu_phase_reduce_emit(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi);
 /* device pointers for collectives: containment keys u64[n] (all-reduce MIN), row info u64[n] (all-reduce SUM after
  * rebase), adjacency entries u64[*n_entries] (all-gather) */
 void *disco_gpu_dev_contained_keys(disco_ctx *ctx);
@@ -135,6 +140,31 @@ int disco_gpu_rebase_rows(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi, uint64_t
 int disco_gpu_set_rows_used(disco_ctx *ctx, uint64_t n_entries);
 int disco_gpu_use_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entries);
 int disco_gpu_adopt_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entries);
+/* ---- key-sharded table and range-partitioned adjacency (Mode B; the partitioning of BuildGraphMPIRMA,
+ * src/BuildGraphMPIRMA/src/HashTable.cpp: each rank owns a slice of the hash table, the others reach it by one-sided
+ * MPI_Get).  Reads stay replicated.  Shard = mulhi(fingerprint, world): every GPU scans all reads, inserts the keys of
+ * its own shard (no communication) and sets every key's bit in its own copy of the presence filter.  Probes of another
+ * shard are plain loads through NVLink peer pointers (CUDA IPC mappings) issued by the same kernels -- the one-sided
+ * get of the reference, without a host in the loop.  The adjacency is not gathered either: a rank keeps the rows of its
+ * own query range and the reduction reads neighbours' rows from their owner the same way.
+ *   set_shard    : before disco_gpu_begin; world = 1 returns to the single-table mode
+ *   export_mem   : CUDA IPC handle (DISCO_IPC_HANDLE_BYTES) of this rank's table shard / adjacency buffer
+ *   import_peers : handles of all ranks, [world] x DISCO_IPC_HANDLE_BYTES in rank order (own entry ignored); for the
+ *                  adjacency also the read-id bounds u64[world + 1] of the ranks' query ranges.  Call again whenever a
+ *                  rank's buffer may have been reallocated (mappings of unchanged handles are kept).
+ * The caller synchronises the ranks (barrier) between the phases: table complete before anybody probes, probing
+ * finished before the table is rebuilt, edge pass finished before the reduction, marks finished before the emission. */
+#define DISCO_MAX_SHARDS 8
+#define DISCO_IPC_HANDLE_BYTES 64
+#define DISCO_MEM_TABLE 0
+#define DISCO_MEM_ROWS 1
+int disco_gpu_set_shard(disco_ctx *ctx, uint32_t world, uint32_t rank);
+int disco_gpu_export_mem(disco_ctx *ctx, int which, void *handle_out);
+int disco_gpu_import_peers(disco_ctx *ctx, int which, const void *handles, const uint64_t *bounds);
+/* shards held by contexts of the same process: device pointers [world] instead of IPC handles (the table shard from
+ * disco_gpu_dev_table, the adjacency from disco_gpu_dev_rows); peer access between the devices is the caller's job */
+int disco_gpu_import_peer_ptrs(disco_ctx *ctx, int which, const void *const *device_ptrs, const uint64_t *bounds);
+void *disco_gpu_dev_table(disco_ctx *ctx);
 /* largest row length over all ranks (sizes the reduction kernel's shared memory) */
 int disco_gpu_set_max_degree(disco_ctx *ctx, uint64_t max_degree);
 /* wait for everything queued on the context's stream */

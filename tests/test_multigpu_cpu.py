@@ -130,3 +130,63 @@ def test_sharded_exchange_gloo(world):
                     s0, s1 = int(loc[i - lo] >> 20), int(info[i] >> 20)
                     assert s1 == s0 + base
                     assert np.array_equal(adopted[s1:s1 + d], rows[r][s0:s0 + d])
+
+
+# ---- Mode B (key-sharded table, range-partitioned adjacency): handle exchange, bounds, all-reduces, phase order ------
+class FakeShardCtx(FakeCtx):
+    def set_shard(self, world, rank): self.log.append(f"shard{rank}/{world}")
+    def export_mem(self, which): return bytes([which, self.rank]) + bytes(62)   # stands in for a CUDA IPC handle
+    def import_peers(self, which, handles, bounds=None):
+        self.log.append(f"import{which}")
+        self.imported = getattr(self, "imported", {})
+        self.imported[which] = ([bytes(h) for h in handles], bounds)
+    def phase_reduce_mark(self, lo, hi): self.log.append("mark")
+    def phase_reduce_emit(self, lo, hi): self.log.append("emit")
+    def sync(self): self.log.append("sync")
+
+
+def _worker_b(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from disco_b200 import multigpu
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = FakeShardCtx(rank, world)
+    multigpu.KeyShardedBuildGraph(g, rank, world, tensors=FakeTensors(g)).build_graph(50, 4)
+    q.put((rank, g.keys.numpy().copy(), g.rowinfo.numpy().copy(), g.final_maxdeg, g.log, g.imported))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_key_sharded_driver_gloo(world):
+    sys.path.insert(0, ROOT)
+    from disco_b200 import multigpu
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_worker_b, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    parts = [multigpu.partition(N, r, world) for r in range(world)]
+    keys = np.stack([_keys_for(r, *parts[r]) for r in range(world)]).view(np.uint64).min(axis=0).view(np.int64)
+    _, infos, mds = zip(*[_rows_for(r, *parts[r]) for r in range(world)])
+    info_sum = np.sum(np.stack(infos), axis=0)     # disjoint ranges: the sum is the union; starts stay owner-local
+    for rank, k, info, md, log, imported in res:
+        assert np.array_equal(k, keys)
+        assert np.array_equal(info, info_sum)
+        assert md == max(mds)
+        # a barrier (sync + all-reduce) separates: table | probing | rebuild | edge pass ... | mark | emit
+        assert [x for x in log if x != "sync"] == [f"shard{rank}/{world}", "begin", "table0", "import0", "contained", "finish",
+                                                   "table1", "edges", "import1", "mark", "emit"]
+        order = "".join("s" if x == "sync" else "." for x in log)
+        assert order.count("s") == 6
+        i_mark, i_emit = log.index("mark"), log.index("emit")
+        assert "sync" in log[i_mark:i_emit] and log[i_mark - 1] == "sync" and log[-1] == "sync"
+        assert log[log.index("contained") - 1] == "sync" and log[log.index("table1") - 1] == "sync" and log[log.index("edges") - 1] == "sync"
+        for which in (0, 1):
+            handles, bounds = imported[which]
+            assert handles == [bytes([which, r]) + bytes(62) for r in range(world)]   # rank order, every rank's handle
+        assert list(imported[1][1]) == [p[0] for p in parts] + [N] and imported[0][1] is None

@@ -21,7 +21,7 @@ packed, lens = host.pack_codes(rs.codes, rs.off)
 g = gpu.GpuBuildGraph(local)
 g.set_stream(torch.cuda.current_stream().cuda_stream)
 g.load_reads(packed, lens)
-multigpu.ShardedBuildGraph(g, rank, world).build_graph(50, 4)
+getattr(multigpu, %r)(g, rank, world).build_graph(50, 4)
 e = g.edges(); c = g.contained()
 lo, hi = multigpu.partition(rs.n, rank, world)
 assert ((e["src"] >= lo) & (e["src"] < hi)).all()          # each rank emits the edges whose lower endpoint it owns
@@ -38,12 +38,13 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_gpus_match_one(tmp_path):
+@pytest.mark.parametrize("driver", ["ShardedBuildGraph", "KeyShardedBuildGraph"], ids=["modeA_replicated", "modeB_key_sharded"])
+def test_two_gpus_match_one(tmp_path, driver):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     script = tmp_path / "run.py"
-    script.write_text(SCRIPT % ROOT)
+    script.write_text(SCRIPT % (ROOT, driver))
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", "29611", str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
