@@ -228,7 +228,12 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     g = gpu.GpuBuildGraph(local)
     g.set_stream(stream.cuda_stream)
-    runner = multigpu.ShardedBuildGraph(g, rank, world) if world > 1 else None
+    # N > 1: Mode A (reads + table replicated, adjacency all-gathered; BASELINE config 3) or Mode B (table sharded by key,
+    # adjacency by query range, remote shards read through NVLink; config 5's partitioning)
+    key_sharded = args.partition == "key-sharded"
+    runner = None
+    if world > 1:
+        runner = multigpu.KeyShardedBuildGraph(g, rank, world) if key_sharded else multigpu.ShardedBuildGraph(g, rank, world)
     lo, hi = (rank * n) // world, ((rank + 1) * n) // world
 
     def device_step():
@@ -362,7 +367,8 @@ def run_ours(args):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": f"synthetic {n} x {READ_LEN}bp {'single-genome' if args.workload == 'single' else '200-genome log-normal metagenome'} reads ({COVERAGE:.0f}x mean, both strands, error-free), "
-                               f"minOverlap={MIN_OVERLAP}" + (f", {world} GPUs: queries sharded by read id, table+reads replicated" if world > 1 else " (BASELINE config 2 when --reads 10000000)"),
+                               f"minOverlap={MIN_OVERLAP}" + (f", {world} GPUs: queries sharded by read id, " + ("reads replicated, table sharded by key and adjacency by query range (remote shards read over NVLink)" if key_sharded else "table+reads replicated") if world > 1 else " (BASELINE config 2 when --reads 10000000)"),
+                   "partition": (args.partition if world > 1 else "single"),
                    "reads": n, "reads_per_gpu": args.reads, "read_len": READ_LEN, "min_overlap": MIN_OVERLAP,
                    "max_edge_per_kmer": 4, "l2": "inputs larger than L2 (packed reads + table > 126 MB), no flush needed"},
         "e2e": {"value": n / (ms_e2e / 1000.0), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -399,6 +405,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--workload", default="single", choices=["single", "metagenome"],
                     help="single = BASELINE config 2 (headline); metagenome = config 3 shape (200 genomes, log-normal abundance)")
+    ap.add_argument("--partition", default=os.environ.get("DISCO_PARTITION", "replicated"), choices=["replicated", "key-sharded"],
+                    help="N > 1 only: replicated = Mode A (config 3), key-sharded = Mode B (config 5's partitioning)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

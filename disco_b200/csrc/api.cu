@@ -19,7 +19,7 @@ thread_local std::string g_create_error;
 
 enum Cursor { CUR_WORK = 0, CUR_WORK2, CUR_WORK3, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_COUNT };
 enum Ev { EV_T0 = 0, EV_TABLE_ALL, EV_CONTAINED, EV_FINISH, EV_TABLE_NC, EV_EDGES, EV_MARK, EV_EMIT, EV_EDGES_K0, EV_EDGES_K1,
-          EV_CONT_K0, EV_CONT_K1, EV_PROBE_K1, EV_VERIFY_K1, EV_COUNT };
+          EV_CONT_K0, EV_CONT_K1, EV_PROBE_K1, EV_VERIFY_K1, EV_MARK_K0, EV_EMIT_K0, EV_COUNT };
 } // namespace
 
 struct disco_ctx {
@@ -66,6 +66,7 @@ struct disco_ctx {
     float acc_probe = 0.f, acc_verify = 0.f, acc_exact = 0.f, acc_edges = 0.f; // edge-pass kernel times summed over parts
     // key-sharded mode (Mode B): this context holds shard `shard_rank` of `shard_world` of the table and the adjacency
     // rows of its own query range; the other shards are reached through peer-mapped pointers (CUDA IPC)
+    bool own_slots = true, own_rows = true; // false: caller-owned memory (disco_gpu_adopt_buffer), never freed or grown here
     uint32_t shard_world = 1, shard_rank = 0;
     struct PeerSet {
         const uint64_t **d_ptrs = nullptr;         // device array [DISCO_MAX_SHARDS]
@@ -119,8 +120,13 @@ int pick_stride(int max_len)
 
 void free_run_buffers(disco_ctx *c)
 {
-    dfree(c->d_slots); dfree(c->d_filter); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
-    dfree(c->d_rowinfo); dfree(c->d_rows); dfree(c->d_edges);
+    if (c->own_slots) dfree(c->d_slots);
+    if (c->own_rows) dfree(c->d_rows);
+    c->d_slots = nullptr; c->d_rows = nullptr;
+    c->own_slots = c->own_rows = true;
+    c->peer_table.ready = c->peer_rows.ready = false; // whatever the peers mapped is gone
+    dfree(c->d_filter); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
+    dfree(c->d_rowinfo); dfree(c->d_edges);
     c->d_rows_active = nullptr;
     c->rows_cap = c->edges_cap = c->crows_cap = c->run_n = 0;
     c->begun = c->have_contained = c->have_edges = c->have_reduced = false;
@@ -484,6 +490,7 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
             break;
         }
         if (attempt >= 2) return fail(ctx, DISCO_E_NOMEM, "adjacency buffer overflow after retry (%llu entries needed)", cur[1]);
+        if (!ctx->own_rows) return fail(ctx, DISCO_E_NOMEM, "adopted adjacency buffer too small: %llu entries needed, %llu given", cur[1], (unsigned long long)ctx->rows_cap);
         // grow (keeping earlier parts) and redo this part.  Slices are handed out per warp, so the slack differs between
         // runs: add one slice per resident warp; scale for the parts still to come
         uint64_t need = cur[1] + (uint64_t)ctx->num_sms * 64 * 1024;
@@ -514,6 +521,7 @@ int reduce_params(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi, ReduceParams &p)
     p.reads = ctx->reads; p.rows = ctx->d_rows_active; p.rowinfo = ctx->d_rowinfo; p.u_lo = u_lo; p.u_hi = u_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_e;
     p.peer_rows = ctx->peer_rows.d_ptrs; p.bounds = ctx->d_bounds; p.world = ctx->shard_world;
+    if (const char *e = getenv("DISCO_PEER_LOAD")) p.peer_load = atoi(e);
     p.maxdeg = (int)std::max<uint64_t>(ctx->stats.max_degree, 1);
     if ((size_t)p.maxdeg * 25 + 512 > 200 * 1024) return fail(ctx, DISCO_E_LIMIT, "max degree %d too large for the reduction kernel", p.maxdeg);
     return DISCO_OK;
@@ -528,6 +536,7 @@ int disco_gpu_phase_reduce_mark(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
+    if ((rc = record(ctx, EV_MARK_K0))) return rc;
     if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_mark(p, ctx->num_sms, ctx->stream));
     return record(ctx, EV_MARK);
 }
@@ -549,7 +558,9 @@ int disco_gpu_phase_reduce_emit(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
         CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_cursors + CUR_EDGES, 0, sizeof(unsigned long long), ctx->stream));
         p.edges_out = ctx->d_edges; p.edges_cap = ctx->edges_cap; p.edges_cursor = ctx->d_cursors + CUR_EDGES;
+        if ((rc = record(ctx, EV_EMIT_K0))) return rc;
         if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_emit(p, ctx->num_sms, ctx->stream));
+        if ((rc = record(ctx, EV_EMIT))) return rc;
         unsigned long long ne = 0;
         CK(cudaMemcpyAsync(&ne, ctx->d_cursors + CUR_EDGES, sizeof ne, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
@@ -562,7 +573,7 @@ int disco_gpu_phase_reduce_emit(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
     }
     ctx->stats.n_edges = ctx->n_edges;
     ctx->have_reduced = true;
-    return record(ctx, EV_EMIT);
+    return DISCO_OK;
 }
 
 int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
@@ -670,6 +681,38 @@ int disco_gpu_import_peer_ptrs(disco_ctx *ctx, int which, const void *const *dev
 }
 
 void *disco_gpu_dev_table(disco_ctx *ctx) { return ctx ? ctx->d_slots : nullptr; }
+uint64_t disco_gpu_table_words(disco_ctx *ctx) { return ctx && ctx->begun ? ctx->nbuckets * 4 : 0; }
+
+// Caller-owned device memory for the table shard (after disco_gpu_begin, at least disco_gpu_table_words u64) or the
+// adjacency (before the edge pass; n_u64 = capacity in entries, never grown here: the edge pass fails with
+// DISCO_E_NOMEM when it is too small).  For memory that other GPUs map by other means than CUDA IPC handles (symmetric
+// memory: VMM allocations with 2 MB pages).
+int disco_gpu_adopt_buffer(disco_ctx *ctx, int which, void *d_ptr, uint64_t n_u64)
+{
+    if (!ctx || !d_ptr) return DISCO_E_ARG;
+    if (!ctx->begun) return fail(ctx, DISCO_E_ARG, "call disco_gpu_begin first");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (which == DISCO_MEM_TABLE) {
+        if (n_u64 < ctx->nbuckets * 4) return fail(ctx, DISCO_E_ARG, "table buffer too small: %llu u64 needed", (unsigned long long)(ctx->nbuckets * 4));
+        if (ctx->own_slots) dfree(ctx->d_slots);
+        ctx->d_slots = static_cast<uint64_t *>(d_ptr);
+        ctx->own_slots = false;
+        ctx->peer_table.ready = false;
+    } else if (which == DISCO_MEM_ROWS) {
+        if (n_u64 < (1u << 16)) return fail(ctx, DISCO_E_ARG, "adjacency buffer too small");
+        if (ctx->own_rows) dfree(ctx->d_rows);
+        ctx->d_rows = ctx->d_rows_active = static_cast<uint64_t *>(d_ptr);
+        ctx->rows_cap = n_u64;
+        ctx->rows_used = 0;
+        ctx->own_rows = false;
+        ctx->have_edges = ctx->have_reduced = false;
+        ctx->peer_rows.ready = false;
+    } else {
+        return fail(ctx, DISCO_E_ARG, "bad buffer selector %d", which);
+    }
+    return DISCO_OK;
+}
 
 int disco_gpu_build_graph(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_kmer)
 {
@@ -775,6 +818,7 @@ int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out)
     s.ms_total = ms(EV_T0, EV_EMIT);
     s.ms_edges_kernel = ctx->acc_edges; s.ms_contained_kernel = ms(EV_CONT_K0, EV_CONT_K1);
     s.ms_edges_probe = ctx->acc_probe; s.ms_edges_verify = ctx->acc_verify; s.ms_edges_exact = ctx->acc_exact;
+    s.ms_mark_kernel = ms(EV_MARK_K0, EV_MARK); s.ms_emit_kernel = ms(EV_EMIT_K0, EV_EMIT);
     *out = s;
     return DISCO_OK;
 }

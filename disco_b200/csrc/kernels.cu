@@ -1446,7 +1446,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_reduce_mark(ReduceParams p) // 
                 n_rows += (lane == 0); n_ent += (lane == 0) ? (unsigned long long)vd : 0ULL;
                 __syncwarp();
                 for (int q = lane; q < vd; q += 32) {
-                    const uint64_t e = __ldcg(vrow + q); // other warps may be setting eliminated bits: ignored
+                    const uint64_t e = (SHARDED && p.peer_load == 1) ? __ldg(vrow + q) : __ldcg(vrow + q); // other warps may be setting eliminated bits: ignored
                     if (!chain_ok(t1, entry_orient(e))) continue;
                     // is w also a neighbour of u?  (markedNodes->find(read3), OverlapGraph.cpp:701)
                     const uint32_t w = (uint32_t)entry_nbr(e);
@@ -1519,7 +1519,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_reduce_emit(ReduceParams p) // 
                         const int q = q0 + lane;
                         uint64_t te = 0;
                         bool hit = false;
-                        if (q < wd) { te = __ldcg(wrow + q); hit = entry_nbr(te) == u; }
+                        if (q < wd) { te = (SHARDED && p.peer_load == 1) ? __ldg(wrow + q) : __ldcg(wrow + q); hit = entry_nbr(te) == u; }
                         const unsigned hm = __ballot_sync(FULL, hit);
                         if (hm) {
                             const uint64_t t = __shfl_sync(FULL, te, __ffs(hm) - 1);

@@ -79,6 +79,7 @@ struct ReduceParams {
     const uint64_t *const *peer_rows; // device array [world]
     const uint64_t *bounds;           // device array [world + 1]
     uint32_t world;
+    int peer_load; // how remote rows are read (env DISCO_PEER_LOAD, tuning): 0 ld.cg, 1 ld.nc
     uint64_t u_lo, u_hi;
     unsigned long long *work_counter;
     unsigned long long *stats;

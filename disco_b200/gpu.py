@@ -21,7 +21,7 @@ EXPORTS = [
     "disco_gpu_adopt_rows", "disco_gpu_set_max_degree", "disco_gpu_sync", "disco_gpu_reserve_rows", "disco_gpu_move_rows",
     "disco_gpu_set_rows_used", "disco_gpu_use_rows", "disco_gpu_phase_edges_part", "disco_gpu_phase_reduce_mark",
     "disco_gpu_phase_reduce_emit", "disco_gpu_set_shard", "disco_gpu_export_mem", "disco_gpu_import_peers",
-    "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table",
+    "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table", "disco_gpu_table_words", "disco_gpu_adopt_buffer",
 ]
 MAX_SHARDS, IPC_HANDLE_BYTES, MEM_TABLE, MEM_ROWS = 8, 64, 0, 1
 
@@ -33,7 +33,8 @@ class Stats(C.Structure):
         "verified_contained", "verified_edges", "max_degree", "reduce_rows_fetched", "reduce_entries_fetched",
         "table_buckets", "edge_capacity", "queries_contained", "queries_edges")] + [(n, C.c_float) for n in (
             "ms_table_all", "ms_contained", "ms_finish_contained", "ms_table_nc", "ms_edges", "ms_mark", "ms_emit", "ms_total",
-            "ms_edges_kernel", "ms_contained_kernel", "ms_edges_probe", "ms_edges_verify", "ms_edges_exact")]
+            "ms_edges_kernel", "ms_contained_kernel", "ms_edges_probe", "ms_edges_verify", "ms_edges_exact",
+            "ms_mark_kernel", "ms_emit_kernel")]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
@@ -81,6 +82,9 @@ def lib():
         L.disco_gpu_import_peer_ptrs.argtypes = [vp, i32, vp, vp]
         L.disco_gpu_dev_table.argtypes = [vp]
         L.disco_gpu_dev_table.restype = vp
+        L.disco_gpu_table_words.argtypes = [vp]
+        L.disco_gpu_table_words.restype = u64
+        L.disco_gpu_adopt_buffer.argtypes = [vp, i32, vp, u64]
         for f in ("disco_gpu_dev_contained_keys", "disco_gpu_dev_rowinfo"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = vp
@@ -207,6 +211,12 @@ class GpuBuildGraph:
 
     def dev_table(self) -> int:
         return self._L.disco_gpu_dev_table(self._h)
+
+    def table_words(self) -> int:
+        return self._L.disco_gpu_table_words(self._h)
+
+    def adopt_buffer(self, which: int, d_ptr: int, n_u64: int):
+        self._ck(self._L.disco_gpu_adopt_buffer(self._h, which, C.c_void_p(d_ptr), n_u64), "adopt_buffer")
 
     def dev_contained_keys(self) -> int:
         return self._L.disco_gpu_dev_contained_keys(self._h)

@@ -72,6 +72,8 @@ typedef struct {
     float ms_table_all, ms_contained, ms_finish_contained, ms_table_nc, ms_edges, ms_mark, ms_emit, ms_total;
     float ms_edges_kernel, ms_contained_kernel; /* the search kernels alone (edge pass = probe + verify + exact) */
     float ms_edges_probe, ms_edges_verify, ms_edges_exact; /* the three kernels of the edge pass */
+    float ms_mark_kernel, ms_emit_kernel;                   /* the two reduction kernels alone (ms_mark / ms_emit include
+                                                             * whatever the caller did between the phases) */
 } disco_stats;
 
 /* ---- life cycle ---------------------------------------------------------------------------------------------- */
@@ -165,6 +167,13 @@ int disco_gpu_import_peers(disco_ctx *ctx, int which, const void *handles, const
  * disco_gpu_dev_table, the adjacency from disco_gpu_dev_rows); peer access between the devices is the caller's job */
 int disco_gpu_import_peer_ptrs(disco_ctx *ctx, int which, const void *const *device_ptrs, const uint64_t *bounds);
 void *disco_gpu_dev_table(disco_ctx *ctx);
+/* Caller-owned device memory instead of the library's own: the table shard (after disco_gpu_begin; at least
+ * disco_gpu_table_words() u64) or the adjacency (before the edge pass; capacity in entries -- never grown by the
+ * library, the edge pass returns DISCO_E_NOMEM when it is too small).  Meant for memory the peers map by other means
+ * than CUDA IPC handles, e.g. symmetric memory (VMM allocations, 2 MB pages: legacy IPC mappings thrash the requester's
+ * TLB once the remote footprint exceeds ~1-2 GB). */
+uint64_t disco_gpu_table_words(disco_ctx *ctx);
+int disco_gpu_adopt_buffer(disco_ctx *ctx, int which, void *d_ptr, uint64_t n_u64);
 /* largest row length over all ranks (sizes the reduction kernel's shared memory) */
 int disco_gpu_set_max_degree(disco_ctx *ctx, uint64_t max_degree);
 /* wait for everything queued on the context's stream */
