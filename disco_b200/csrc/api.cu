@@ -32,6 +32,7 @@ struct disco_ctx {
     // reads
     uint64_t *d_words = nullptr;
     uint16_t *d_len = nullptr;
+    uint64_t *d_words_rc = nullptr; // reverse complement of every read (verify kernel: suffix overlaps read a prefix); optional
     uint64_t *d_stage = nullptr; // host rows arrive here when their pitch differs from the device row
     uint64_t stage_words = 0;
     ReadsView reads{};
@@ -134,7 +135,7 @@ void free_run_buffers(disco_ctx *c)
 
 void free_reads(disco_ctx *c)
 {
-    dfree(c->d_words); dfree(c->d_len); dfree(c->d_stage);
+    dfree(c->d_words); dfree(c->d_words_rc); dfree(c->d_len); dfree(c->d_stage);
     c->stage_words = 0;
     c->reads = ReadsView{};
 }
@@ -182,7 +183,14 @@ int alloc_reads(disco_ctx *ctx, uint64_t n, int min_len, int max_len)
     const int stride = pick_stride(max_len);
     CK(cudaMalloc(&ctx->d_words, n * (uint64_t)stride * sizeof(uint64_t)));
     CK(cudaMalloc(&ctx->d_len, n * sizeof(uint16_t)));
-    ctx->reads.words = ctx->d_words; ctx->reads.len = ctx->d_len; ctx->reads.n = n; ctx->reads.stride = stride;
+    // Optional second copy, reverse-complemented (DISCO_RC_COPY=1; rows of 32..128 bytes): the verify kernel then reads a
+    // candidate's overlapping suffix as the leading sector(s) of this copy instead of the whole 64-byte row.  Measured on
+    // B200, 10M x 150 bp: verify 16.5 -> 15.3 ms on the single genome, but slower on the metagenome shape and 64 bytes
+    // per read more memory -- off by default.
+    if (stride >= 4 && stride <= 16 && getenv("DISCO_RC_COPY") && atoi(getenv("DISCO_RC_COPY")) == 1) {
+        if (cudaMalloc(&ctx->d_words_rc, n * (uint64_t)stride * sizeof(uint64_t)) != cudaSuccess) { ctx->d_words_rc = nullptr; cudaGetLastError(); }
+    }
+    ctx->reads.words = ctx->d_words; ctx->reads.words_rc = ctx->d_words_rc; ctx->reads.len = ctx->d_len; ctx->reads.n = n; ctx->reads.stride = stride;
     ctx->reads.min_len = min_len; ctx->reads.max_len = max_len;
     ctx->reads.uniform_len = (min_len == max_len) ? max_len : 0;
     return DISCO_OK;
@@ -363,7 +371,10 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
     for (auto &d : ctx->ev_done) d = false;
     ctx->n_contained = ctx->n_edges = 0;
     ctx->begun = true;
-    return record(ctx, EV_T0);
+    int rc0 = record(ctx, EV_T0);
+    if (rc0) return rc0;
+    if (ctx->d_words_rc) CK(launch_revcomp_rows(ctx->reads, ctx->d_words_rc, ctx->stream)); // part of the timed run
+    return DISCO_OK;
 }
 
 int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained)

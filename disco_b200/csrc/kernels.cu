@@ -138,11 +138,12 @@ struct RegMatcher<0> {
 };
 
 // Verify-kernel compare: the candidate's words are parked in shared memory, transposed (word w of lane l at
-// cw[w * 32 + l], conflict-free), so that the compare is a plain loop over exactly the words the overlap touches --
+// cw[w * GW + l], GW = lanes per group, conflict-free), so that the compare is a plain loop over exactly the words the overlap touches --
 // no per-word range selects, no unrolling over the longest read.
+template <int GW>
 struct SmemMatcher {
     const uint64_t *cw; // + lane already applied
-    __device__ __forceinline__ uint64_t word(int w) const { return cw[w * 32]; }
+    __device__ __forceinline__ uint64_t word(int w) const { return cw[w * GW]; }
     __device__ __forceinline__ bool operator()(const uint32_t *P, int a, int b, int n) const
     {
         const int q0 = a - b + 32;           // query base (in padded coordinates) facing candidate base 0
@@ -180,6 +181,18 @@ __device__ __forceinline__ void stage_read(const ReadsView &rv, uint64_t r, int 
     __syncwarp();
 }
 
+// group versions (GW lanes of a warp work on one read; gmask = the group's lanes)
+template <int GW>
+__device__ __forceinline__ void stage_read_g(const ReadsView &rv, uint64_t r, int L, uint32_t *A, uint32_t *R, int WP, int lane, unsigned gmask)
+{
+    const int W = (L + 31) >> 5;
+    const uint64_t *src = rv.words + r * (uint64_t)rv.stride;
+    for (int w = lane; w < WP; w += GW) pstore(A, w, (w >= 1 && w <= W) ? __ldg(src + (w - 1)) : 0ULL);
+    __syncwarp(gmask);
+    for (int w = lane; w < WP; w += GW) pstore(R, w, (w >= 1 && w <= W) ? rc_word(A, L, W, w - 1) : 0ULL);
+    __syncwarp(gmask);
+}
+
 // same, with the forward words already in registers (lane w holds word w; reads of up to 32 words = 1024 bases)
 __device__ __forceinline__ void stage_read_pre(uint64_t myword, int L, uint32_t *A, uint32_t *R, int WP, int lane)
 {
@@ -207,6 +220,20 @@ __device__ __forceinline__ bool grab_chunk(unsigned long long *counter, uint64_t
     unsigned long long c = 0;
     if (lane == 0) c = atomicAdd(counter, (unsigned long long)kChunk);
     c = __shfl_sync(FULL, c, 0);
+    uint64_t b = lo + c;
+    if (b >= hi) return false;
+    *begin = b;
+    *end = (b + kChunk < hi) ? b + kChunk : hi;
+    return true;
+}
+
+template <int GW>
+__device__ __forceinline__ bool grab_chunk_g(unsigned long long *counter, uint64_t lo, uint64_t hi, int lane, unsigned gmask,
+                                             uint64_t *begin, uint64_t *end)
+{
+    unsigned long long c = 0;
+    if (lane == 0) c = atomicAdd(counter, (unsigned long long)kChunk);
+    c = __shfl_sync(gmask, c, 0, GW);
     uint64_t b = lo + c;
     if (b >= hi) return false;
     *begin = b;
@@ -854,10 +881,10 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
 //                    candidates)
 // ---------------------------------------------------------------------------------------------------------------
 __host__ __device__ inline size_t probe_words_per_warp(int WP, int npos, int hcap) { return 2 * (size_t)WP + (size_t)npos + ((size_t)npos + 1) / 2 + (size_t)hcap + 4; }
-__host__ __device__ inline size_t verify_words_per_warp(int WP, int npos, int hcap, int hset)
-{   // A, R, candidate queue, id set + per-position counters, transposed candidate words (32 x up to 16), control
+__host__ __device__ inline size_t verify_words_per_group(int WP, int npos, int hcap, int hset, int gw)
+{   // A, R, candidate queue, id set + per-position counters, transposed candidate words (gw x up to 16), control
     const int nw = WP - 2 <= 16 ? ((WP - 2 + 1) / 2) * 2 : 0;
-    return 2 * (size_t)WP + (size_t)hcap + ((size_t)hset + (size_t)npos + 1) / 2 + (size_t)32 * nw + 2;
+    return 2 * (size_t)WP + (size_t)hcap + ((size_t)hset + (size_t)npos + 1) / 2 + (size_t)gw * nw + 2;
 }
 __host__ __device__ inline size_t exact_words_per_warp(int WP, int rowcap) { return 2 * (size_t)WP + (size_t)rowcap + kBestMax + 2; }
 
@@ -1032,20 +1059,24 @@ __global__ void __launch_bounds__(kThreads, 6) k_edges_probe(SearchParams p)
     warp_stat_add(p.stats, ST_BUCKETS, n_buckets);
 }
 
-template <int NW>
-__global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges_verify(SearchParams p)
+// GW = lanes that work on one read (32, or 16: two reads per warp side by side -- a read has ~36 candidates, so 32-lane
+// rounds leave the second one almost empty; 16-lane groups keep ~80% of the lanes busy and halve the per-read overhead)
+template <int NW, int GW>
+__global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? (GW == 32 ? 5 : 4) : 1) k_edges_verify(SearchParams p)
 {
     extern __shared__ uint64_t smem[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & (GW - 1), gib = threadIdx.x / GW;   // lane in the group, group in the block
+    const int gshift = (threadIdx.x & 31) & ~(GW - 1);                 // the group's first lane within the warp
+    const unsigned gmask = GW == 32 ? FULL : (((1u << GW) - 1u) << gshift);
     const int WP = ((p.reads.max_len + 31) >> 5) + 2;
     const int K = p.K;
     WarpSmem s;
-    uint64_t *w0 = smem + wib * verify_words_per_warp(WP, p.npos, p.hcap, p.hset);
+    uint64_t *w0 = smem + gib * verify_words_per_group(WP, p.npos, p.hcap, p.hset, GW);
     s.A = reinterpret_cast<uint32_t *>(w0); s.R = s.A + 2 * WP; s.p_u32 = 2 * WP;
     s.hits = w0 + 2 * WP;
     uint32_t *hset = reinterpret_cast<uint32_t *>(s.hits + p.hcap);
     int *cntj = reinterpret_cast<int *>(hset + p.hset);
-    s.ctrl = reinterpret_cast<int *>(w0 + verify_words_per_warp(WP, p.npos, p.hcap, p.hset) - 2);
+    s.ctrl = reinterpret_cast<int *>(w0 + verify_words_per_group(WP, p.npos, p.hcap, p.hset, GW) - 2);
     uint64_t *cw = w0 + 2 * WP + p.hcap + (p.hset + p.npos + 1) / 2 + lane; // transposed candidate words, this lane's column
     s.row = nullptr; s.best = nullptr; s.ph = nullptr; s.pj = nullptr;
     const unsigned lt_mask = (1u << lane) - 1;
@@ -1053,7 +1084,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
     unsigned n_verified = 0, n_hits = 0, maxdeg = 0;
     unsigned long long n_entries = 0;
     uint64_t rb, re;
-    while (grab_chunk(p.work_counter + 1, p.q_lo, p.q_hi, lane, &rb, &re)) {
+    while (grab_chunk_g<GW>(p.work_counter + 1, p.q_lo, p.q_hi, lane, gmask, &rb, &re)) {
         for (uint64_t r1 = rb; r1 < re; r1++) {
             const uint64_t ri = p.rowinfo[r1];
             const int nc = (int)rowinfo_deg(ri);
@@ -1062,13 +1093,13 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
             const int L1 = read_len(p.reads, r1);
             if (nc > p.hcap) {
                 // ---- big row (high coverage, up to kParkMax candidates): same steps, but the candidates stay in the
-                // parked row in global memory and are taken 32 at a time
-                stage_read(p.reads, r1, L1, s.A, s.R, WP, lane);
+                // parked row in global memory and are taken GW at a time
+                stage_read_g<GW>(p.reads, r1, L1, s.A, s.R, WP, lane, gmask);
                 const bool count_pos = (ri & kInfoCrowded) != 0;
-                if (count_pos) for (int k = lane; k < L1 - K; k += 32) cntj[k] = 0;
-                __syncwarp();
+                if (count_pos) for (int k = lane; k < L1 - K; k += GW) cntj[k] = 0;
+                __syncwarp(gmask);
                 bool over = false;
-                for (int i0 = 0; i0 < nc; i0 += 32) {
+                for (int i0 = 0; i0 < nc; i0 += GW) {
                     const int i = i0 + lane;
                     if (i < nc) {
                         const uint64_t c = p.rows[start + i];
@@ -1078,12 +1109,12 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
                     }
                 }
                 n_verified += (lane == 0) ? (unsigned)nc : 0u;
-                if (__any_sync(FULL, over)) { // a position with more than cap partners: redo exactly
+                if (__any_sync(gmask, over)) { // a position with more than cap partners: redo exactly
                     if (lane == 0) p.rowinfo[r1] = kInfoExact;
-                    __syncwarp();
+                    __syncwarp(gmask);
                     continue;
                 }
-                __syncwarp();
+                __syncwarp(gmask);
                 // first hit per neighbour (OverlapGraph.cpp:656): neighbour ids go through a shared-memory set in two
                 // passes (one hash bit each) so that 512 slots are enough; an id seen twice marks the read for the
                 // quadratic clean-up below
@@ -1091,9 +1122,9 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
                 const int slots = 2 * p.hcap + p.hset;                    // u32 slots (hits is u64[hcap])
                 bool dup = false, full = false;
                 for (int pass = 0; pass < 2; pass++) {
-                    for (int k = lane; k < slots; k += 32) bigset[k] = 0xFFFFFFFFu;
-                    __syncwarp();
-                    for (int i0 = 0; i0 < nc; i0 += 32) {
+                    for (int k = lane; k < slots; k += GW) bigset[k] = 0xFFFFFFFFu;
+                    __syncwarp(gmask);
+                    for (int i0 = 0; i0 < nc; i0 += GW) {
                         const int i = i0 + lane;
                         const uint64_t hk = (i < nc) ? __ldcg(p.rows + start + i) : ~0ULL;
                         if (hk == ~0ULL) continue;
@@ -1109,11 +1140,11 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
                             hh = (hh + 1 == (uint32_t)slots) ? 0 : hh + 1;
                         }
                     }
-                    __syncwarp();
+                    __syncwarp(gmask);
                 }
-                if (__any_sync(FULL, dup || full)) {
+                if (__any_sync(gmask, dup || full)) {
                     unsigned drop = 0;
-                    for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++) {
+                    for (int i0 = 0, rd = 0; i0 < nc; i0 += GW, rd++) {
                         const int i = i0 + lane;
                         const uint64_t hk = (i < nc) ? __ldcg(p.rows + start + i) : ~0ULL;
                         if (hk == ~0ULL) continue;
@@ -1123,49 +1154,55 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
                             if (o != ~0ULL && hit_read(o) == r2 && o < hk) { drop |= 1u << rd; break; }
                         }
                     }
-                    __syncwarp();
-                    for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++)
+                    __syncwarp(gmask);
+                    for (int i0 = 0, rd = 0; i0 < nc; i0 += GW, rd++)
                         if ((drop >> rd) & 1) p.rows[start + i0 + lane] = ~0ULL;
-                    __syncwarp();
+                    __syncwarp(gmask);
                 }
                 // compact the survivors at the front of the row, as adjacency entries
                 int off = 0;
-                for (int i0 = 0; i0 < nc; i0 += 32) {
+                for (int i0 = 0; i0 < nc; i0 += GW) {
                     const int i = i0 + lane;
                     const uint64_t hk = (i < nc) ? __ldcg(p.rows + start + i) : ~0ULL;
                     const bool valid = hk != ~0ULL;
-                    const unsigned m = __ballot_sync(FULL, valid); // everybody has read before anybody writes
+                    const unsigned m = (__ballot_sync(gmask, valid) >> gshift); // everybody has read before anybody writes
                     if (valid) {
                         int orient, ovl;
                         type_to_edge(hit_type(hk), L1, K, hit_j(hk), &orient, &ovl);
                         p.rows[start + off + __popc(m & lt_mask)] = make_entry(L1 - ovl, hit_read(hk), orient);
                     }
                     off += __popc(m);
-                    __syncwarp();
+                    __syncwarp(gmask);
                 }
                 if (lane == 0) p.rowinfo[r1] = off ? make_rowinfo(start, (uint32_t)off) : 0ULL;
                 n_hits += (lane == 0) ? (unsigned)off : 0u;
                 n_entries += (lane == 0) ? (unsigned long long)off : 0ULL;
                 if ((unsigned)off > maxdeg) maxdeg = off;
-                __syncwarp();
+                __syncwarp(gmask);
                 continue;
             }
             // candidates first (their rows are the long-latency loads of this kernel), then the query
-            for (int i = lane; i < nc; i += 32) {
+            // (split: a candidate whose suffix overlaps is read from the reverse-complement copy, where that suffix is
+            // the prefix -- so only the leading sector(s) the overlap reaches are touched at all)
+            const bool split = NW >= 4 && p.reads.words_rc != nullptr;
+            for (int i = lane; i < nc; i += GW) {
                 const uint64_t c = p.rows[start + i];
                 s.hits[i] = c;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.reads.words + (uint64_t)hit_read(c) * (uint64_t)p.reads.stride));
+                const int t = hit_type(c);
+                const uint64_t *row = ((split && (t == 1 || t == 2)) ? p.reads.words_rc : p.reads.words) + (uint64_t)hit_read(c) * (uint64_t)p.reads.stride;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(row));
+                if (split && NW > 4 && ((t == 0 || t == 2) ? L1 - hit_j(c) : K + hit_j(c)) > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(row + 4));
             }
-            stage_read(p.reads, r1, L1, s.A, s.R, WP, lane);
+            stage_read_g<GW>(p.reads, r1, L1, s.A, s.R, WP, lane, gmask);
             const bool count_pos = (ri & kInfoCrowded) != 0; // only reads with a crowded position pay for per-position counts
             int hsz = 64;
             while (hsz < 2 * nc) hsz <<= 1;         // <= p.hset
             const uint32_t hm = (uint32_t)hsz - 1;
-            for (int k = lane; k < hsz; k += 32) hset[k] = 0xFFFFFFFFu;
-            if (count_pos) for (int k = lane; k < L1 - K; k += 32) cntj[k] = 0;
-            __syncwarp();
+            for (int k = lane; k < hsz; k += GW) hset[k] = 0xFFFFFFFFu;
+            if (count_pos) for (int k = lane; k < L1 - K; k += GW) cntj[k] = 0;
+            __syncwarp(gmask);
             bool dup = false, over = false;
-            for (int i0 = 0; i0 < nc; i0 += 32) {
+            for (int i0 = 0; i0 < nc; i0 += GW) {
                 const int i = i0 + lane;
                 if (i < nc) {
                     const uint64_t c = s.hits[i];
@@ -1173,16 +1210,39 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
                     bool ok;
                     if (NW == 0) {
                         ok = verify_dovetail<NW>(p, s, L1, hit_j(c), hit_type(c), r2);
+                    } else if (split) {
+                        const int L2 = read_len(p.reads, r2), t = hit_type(c);
+                        int use_rc, a, b, n;
+                        ok = dovetail_window(t, L1, hit_j(c), K, L2, &use_rc, &a, &b, &n);
+                        if (ok) {
+                            const uint64_t *row = p.reads.words;
+                            // s2[L2-n..L2) == X  <=>  rc(s2)[0..n) == rc(X): swap the query array, mirror the window
+                            if (t == 1 || t == 2) { row = p.reads.words_rc; use_rc ^= 1; a = L1 - a - n; }
+                            row += (uint64_t)r2 * (uint64_t)p.reads.stride;
+                            const uint64_t pol = policy_evict_first();
+#pragma unroll
+                            for (int sct = 0; sct < ((NW > 0 ? NW : 4) + 3) / 4; sct++) {
+                                if (sct * 128 < n) { // one 32-byte sector = 128 bases, one LDG.E.256
+                                    uint64_t v[4];
+                                    asm volatile("ld.global.nc.L2::cache_hint.v4.u64 {%0,%1,%2,%3}, [%4], %5;"
+                                                 : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(row + 4 * sct), "l"(pol));
+#pragma unroll
+                                    for (int k = 0; k < 4; k++)
+                                        if (4 * sct + k < NW) cw[(4 * sct + k) * GW] = v[k];
+                                }
+                            }
+                            ok = SmemMatcher<GW>{cw}(use_rc ? s.R : s.A, a, 0, n);
+                        }
                     } else {
                         RegMatcher<(NW > 0 ? NW : 2)> m;
                         m.stride = p.reads.stride;
                         m.load(p.reads.words, r2);
                         const int L2 = read_len(p.reads, r2);
 #pragma unroll
-                        for (int w = 0; w < (NW > 0 ? NW : 2); w++) cw[w * 32] = m.v[w];
+                        for (int w = 0; w < (NW > 0 ? NW : 2); w++) cw[w * GW] = m.v[w];
                         int use_rc, a, b, n;
                         ok = dovetail_window(hit_type(c), L1, hit_j(c), K, L2, &use_rc, &a, &b, &n) &&
-                             SmemMatcher{cw}(use_rc ? s.R : s.A, a, b, n);
+                             SmemMatcher<GW>{cw}(use_rc ? s.R : s.A, a, b, n);
                     }
                     if (ok) {
                         // first hit per neighbour: insert r2 into the warp's id set
@@ -1200,9 +1260,9 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
                 }
             }
             n_verified += (lane == 0) ? (unsigned)nc : 0u;
-            over = __any_sync(FULL, over); // a position with more than cap partners: redo exactly
-            dup = __any_sync(FULL, dup);
-            __syncwarp();
+            over = __any_sync(gmask, over); // a position with more than cap partners: redo exactly
+            dup = __any_sync(gmask, dup);
+            __syncwarp(gmask);
             if (over) {
                 if (lane == 0) p.rowinfo[r1] = kInfoExact;
                 continue;
@@ -1211,7 +1271,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
                 // rare (tandem repeats, circular overlaps): a neighbour reached through two positions keeps the
                 // first one in (position, record) order (OverlapGraph.cpp:656)
                 unsigned drop = 0;
-                for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++) {
+                for (int i0 = 0, rd = 0; i0 < nc; i0 += GW, rd++) {
                     const int i = i0 + lane;
                     const uint64_t hk = (i < nc) ? s.hits[i] : ~0ULL;
                     if (hk == ~0ULL) continue;
@@ -1221,19 +1281,19 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
                         if (o != ~0ULL && hit_read(o) == r2 && o < hk) { drop |= 1u << rd; break; }
                     }
                 }
-                __syncwarp();
-                for (int i0 = 0, rd = 0; i0 < nc; i0 += 32, rd++)
+                __syncwarp(gmask);
+                for (int i0 = 0, rd = 0; i0 < nc; i0 += GW, rd++)
                     if ((drop >> rd) & 1) s.hits[i0 + lane] = ~0ULL;
-                __syncwarp();
+                __syncwarp(gmask);
             }
             // survivors become adjacency entries, ballot-compacted at the front of the same row (unsorted: the
             // reduction picks neighbours in offset order itself)
             int off = 0;
-            for (int i0 = 0; i0 < nc; i0 += 32) {
+            for (int i0 = 0; i0 < nc; i0 += GW) {
                 const int i = i0 + lane;
                 const uint64_t hk = (i < nc) ? s.hits[i] : ~0ULL;
                 const bool valid = hk != ~0ULL;
-                const unsigned m = __ballot_sync(FULL, valid);
+                const unsigned m = (__ballot_sync(gmask, valid) >> gshift);
                 if (valid) {
                     int orient, ovl;
                     type_to_edge(hit_type(hk), L1, K, hit_j(hk), &orient, &ovl);
@@ -1245,7 +1305,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 5 : 1) k_edges
             n_hits += (lane == 0) ? (unsigned)off : 0u;
             n_entries += (lane == 0) ? (unsigned long long)off : 0ULL;
             if ((unsigned)off > maxdeg) maxdeg = off;
-            __syncwarp();
+            __syncwarp(gmask);
         }
     }
     warp_stat_add(p.stats, ST_VERIFIED, n_verified);
@@ -1347,6 +1407,29 @@ __global__ void k_restride(const uint64_t *src, int src_stride, int src_words, u
     const uint64_t r = i / dst_stride;
     const int w = (int)(i - r * dst_stride);
     if (r < n) dst[i] = (w < src_words) ? src[r * src_stride + w] : 0ULL;
+}
+
+// reverse complement of every read, same row layout.  A dovetail overlap always covers a prefix or a suffix of the
+// candidate; the suffix of a read is the prefix of its reverse complement, so with this copy the verify kernel only ever
+// needs the leading 32-byte sector(s) of a row -- one random 32-byte access instead of a 64-byte one for overlaps of up
+// to 128 bases (measured random-access rates: 39 G/s at 32 bytes, 22 G/s at 64 bytes).
+__global__ void k_revcomp_rows(ReadsView rv, uint64_t *out)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rv.n) return;
+    const int L = read_len(rv, r), W = (L + 31) >> 5, S = rv.stride;
+    const uint64_t *src = rv.words + r * (uint64_t)S;
+    uint64_t *dst = out + r * (uint64_t)S;
+    const int sh = (32 * W - L) * 2; // pad bases of the last word, shifted out of the reversed string
+    for (int w = 0; w < S; w++) {
+        uint64_t v = 0;
+        if (w < W) {
+            const uint64_t z0 = revcomp64(__ldg(src + (W - 1 - w)));
+            const uint64_t z1 = (sh && w + 1 < W) ? revcomp64(__ldg(src + (W - 2 - w))) : 0ULL;
+            v = sh ? ((z0 << sh) | (z1 >> (64 - sh))) : z0;
+        }
+        dst[w] = v;
+    }
 }
 
 __global__ void k_rebase_rowinfo(uint64_t *rowinfo, uint64_t lo, uint64_t hi, uint64_t base)
@@ -1751,11 +1834,14 @@ cudaError_t launch_search_edges(const SearchParams &p_in, int num_sms, cudaStrea
     cudaError_t e = p.table.world > 1 ? launch_warps(k_edges_probe<true>, p, pb, num_sms, s) : launch_warps(k_edges_probe<false>, p, pb, num_sms, s);
     if (e != cudaSuccess) return e;
     if (ev_probe_done) cudaEventRecord(ev_probe_done, s);
-    const size_t vb = verify_words_per_warp(WP, p.npos, p.hcap, p.hset) * sizeof(uint64_t);
+    // short reads: two 16-lane groups per warp in the verify kernel (DISCO_VERIFY_GW=32 selects one read per warp)
+    const int gw = (getenv("DISCO_VERIFY_GW") ? atoi(getenv("DISCO_VERIFY_GW")) : 16) == 16 && (p.reads.max_len + 31) / 32 <= 8 ? 16 : 32;
+    const size_t vb = verify_words_per_group(WP, p.npos, p.hcap, p.hset, gw) * sizeof(uint64_t) * (32 / gw);
     const size_t xb = exact_words_per_warp(WP, p.rowcap) * sizeof(uint64_t);
 #define DISCO_LAUNCH_E(NWV)                                                          \
     {                                                                                \
-        e = launch_warps(k_edges_verify<NWV>, p, vb, num_sms, s);                    \
+        e = gw == 16 ? launch_warps(k_edges_verify<NWV, (NWV > 0 && NWV <= 8) ? 16 : 32>, p, vb, num_sms, s)   \
+                     : launch_warps(k_edges_verify<NWV, 32>, p, vb, num_sms, s);     \
         if (e != cudaSuccess) return e;                                              \
         if (ev_verify_done) cudaEventRecord(ev_verify_done, s);                      \
         e = launch_warps(k_edges_exact<NWV>, p, xb, num_sms, s);                     \
@@ -1797,6 +1883,13 @@ cudaError_t launch_restride(const uint64_t *src, int src_stride, int src_words, 
     if (n == 0) return cudaSuccess;
     const uint64_t total = n * (uint64_t)dst_stride;
     k_restride<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, src_stride, src_words, dst, dst_stride, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_revcomp_rows(const ReadsView &r, uint64_t *out, cudaStream_t s)
+{
+    if (r.n == 0) return cudaSuccess;
+    k_revcomp_rows<<<(unsigned)((r.n + 255) / 256), 256, 0, s>>>(r, out);
     return cudaGetLastError();
 }
 

@@ -27,6 +27,7 @@ enum StatSlot {
 
 struct ReadsView {
     const uint64_t *words; // n * stride, 16-byte aligned rows
+    const uint64_t *words_rc; // the reverse complement of every read in the same layout, or null (see k_edges_verify)
     const uint16_t *len;   // n
     uint64_t n;
     int stride;            // words per read (even)
@@ -79,7 +80,7 @@ struct ReduceParams {
     const uint64_t *const *peer_rows; // device array [world]
     const uint64_t *bounds;           // device array [world + 1]
     uint32_t world;
-    int peer_load; // how remote rows are read (env DISCO_PEER_LOAD, tuning): 0 ld.cg, 1 ld.nc
+    int peer_load; // how remote rows are read (env DISCO_PEER_LOAD, tuning; no measurable difference): 0 ld.cg, 1 ld.nc
     uint64_t u_lo, u_hi;
     unsigned long long *work_counter;
     unsigned long long *stats;
@@ -104,6 +105,8 @@ cudaError_t launch_contained_rows(const unsigned long long *best, const ReadsVie
 cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t s);
 cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t s);
 cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s);
+// out[r] = reverse complement of read r, same row layout as r.words
+cudaError_t launch_revcomp_rows(const ReadsView &r, uint64_t *out, cudaStream_t s);
 // copy n rows of src_words u64 (pitch src_stride) into rows of dst_stride u64, zero-filling the tail (dst_stride >= src_words)
 cudaError_t launch_restride(const uint64_t *src, int src_stride, int src_words, uint64_t *dst, int dst_stride, uint64_t n, cudaStream_t s);
 // smem bytes a search / reduce block needs for the given shape (0 = does not fit)
