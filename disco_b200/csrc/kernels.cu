@@ -55,6 +55,13 @@ __device__ __forceinline__ void load_bucket(const uint64_t *slots, uint64_t b, u
                  : "l"(slots + 4 * b), "l"(pol));
 }
 
+// pull the adjacency row described by `ri` into L2 (one 128-byte line per lane; rows longer than 512 entries: the head)
+__device__ __forceinline__ void prefetch_row(const uint64_t *rows, uint64_t ri, int lane)
+{
+    const int deg = (int)rowinfo_deg(ri);
+    if (lane * 16 < deg) asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + rowinfo_start(ri) + lane * 16));
+}
+
 // where the chain of fingerprint h starts: the shard (a peer pointer when the table is key-sharded) and the bucket in it
 struct Home {
     const uint64_t *slots;
@@ -1439,13 +1446,6 @@ __global__ void k_rebase_rowinfo(uint64_t *rowinfo, uint64_t lo, uint64_t hi, ui
         const uint64_t ri = rowinfo[i];
         if (rowinfo_deg(ri)) rowinfo[i] = make_rowinfo(rowinfo_start(ri) + base, rowinfo_deg(ri));
     }
-}
-
-// pull the adjacency row described by `ri` into L2 (one 128-byte line per lane; rows longer than 512 entries: the head)
-__device__ __forceinline__ void prefetch_row(const uint64_t *rows, uint64_t ri, int lane)
-{
-    const int deg = (int)rowinfo_deg(ri);
-    if (lane * 16 < deg) asm volatile("prefetch.global.L2 [%0];" ::"l"(rows + rowinfo_start(ri) + lane * 16));
 }
 
 // the buffer that holds the row of read v: local, or (range-partitioned adjacency) the owning GPU's through NVLink

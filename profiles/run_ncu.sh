@@ -5,8 +5,8 @@
 READS=${1:-10000000}
 TAG=${2:-r01}
 mkdir -p gpurun_out
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/${TAG}_launches.csv \
+timeout 150 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 40 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python profiles/profile_step.py $READS 1 > gpurun_out/${TAG}_launch.log 2>&1 < /dev/null
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"k_edges|k_reduce_mark|k_reduce_emit|k_table_insert|k_contain_uniform" -s 8 -c 8 -f -o gpurun_out/${TAG}_prof \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"k_edges|k_reduce_mark|k_reduce_emit|k_table_insert|k_contain_uniform" -s 8 -c 8 -f -o gpurun_out/${TAG}_prof \
     python profiles/profile_step.py $READS 1 > gpurun_out/${TAG}_full.log 2>&1 < /dev/null
 ls -la gpurun_out
