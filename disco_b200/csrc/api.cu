@@ -4,6 +4,10 @@
 #include "dna.cuh"
 #include "kernels.cuh"
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -74,7 +78,7 @@ struct disco_ctx {
         void *opened[DISCO_MAX_SHARDS] = {};       // mappings this context opened (to close them again)
         cudaIpcMemHandle_t handle[DISCO_MAX_SHARDS] = {};
         bool ready = false;
-    } peer_table, peer_rows;
+    } peer_table, peer_rows, peer_keys;
     uint64_t *d_bounds = nullptr; // read-id bounds of the ranks' query ranges [shard_world + 1]
     cudaEvent_t ev[EV_COUNT] = {};
     bool ev_done[EV_COUNT] = {};
@@ -269,7 +273,7 @@ void disco_gpu_destroy(disco_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     close_peers(ctx->peer_table); close_peers(ctx->peer_rows);
-    dfree(ctx->peer_table.d_ptrs); dfree(ctx->peer_rows.d_ptrs); dfree(ctx->d_bounds);
+    dfree(ctx->peer_table.d_ptrs); dfree(ctx->peer_rows.d_ptrs); dfree(ctx->peer_keys.d_ptrs); dfree(ctx->d_bounds);
     free_run_buffers(ctx);
     free_reads(ctx);
     dfree(ctx->d_cursors); dfree(ctx->d_stats_c); dfree(ctx->d_stats_e);
@@ -608,6 +612,7 @@ int disco_gpu_set_shard(disco_ctx *ctx, uint32_t world, uint32_t rank)
     if (world > 1) {
         if (!ctx->peer_table.d_ptrs) CK(cudaMalloc(&ctx->peer_table.d_ptrs, DISCO_MAX_SHARDS * sizeof(uint64_t *)));
         if (!ctx->peer_rows.d_ptrs) CK(cudaMalloc(&ctx->peer_rows.d_ptrs, DISCO_MAX_SHARDS * sizeof(uint64_t *)));
+        if (!ctx->peer_keys.d_ptrs) CK(cudaMalloc(&ctx->peer_keys.d_ptrs, DISCO_MAX_SHARDS * sizeof(uint64_t *)));
         if (!ctx->d_bounds) CK(cudaMalloc(&ctx->d_bounds, (DISCO_MAX_SHARDS + 1) * sizeof(uint64_t)));
     }
     return DISCO_OK;
@@ -722,6 +727,119 @@ int disco_gpu_adopt_buffer(disco_ctx *ctx, int which, void *d_ptr, uint64_t n_u6
     } else {
         return fail(ctx, DISCO_E_ARG, "bad buffer selector %d", which);
     }
+    return DISCO_OK;
+}
+
+// ---- several GPUs driven by ONE process (what `buildG -g 0,1,...` uses): Mode B with one host thread per context.
+// The ranks' buffers are mapped by peer access (same address space), the containment keys are min-reduced by a kernel
+// that reads the peers' arrays, the row infos are copied range by range -- no NCCL, no MPI.
+namespace {
+struct HostBarrier {
+    std::mutex m;
+    std::condition_variable cv;
+    unsigned n, waiting = 0, generation = 0;
+    explicit HostBarrier(unsigned n_) : n(n_) {}
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        const unsigned g = generation;
+        if (++waiting == n) { waiting = 0; generation++; cv.notify_all(); }
+        else cv.wait(lk, [&] { return generation != g; });
+    }
+};
+} // namespace
+
+int disco_gpu_build_graph_multi(disco_ctx *const *ctxs, uint32_t world, uint32_t min_overlap, uint32_t max_edge_per_kmer)
+{
+    if (!ctxs || world < 1 || world > DISCO_MAX_SHARDS) return DISCO_E_ARG;
+    for (uint32_t r = 0; r < world; r++) if (!ctxs[r]) return DISCO_E_ARG;
+    if (world == 1) {
+        int rc = disco_gpu_set_shard(ctxs[0], 1, 0);
+        return rc ? rc : disco_gpu_build_graph(ctxs[0], min_overlap, max_edge_per_kmer);
+    }
+    disco_ctx *c0 = ctxs[0];
+    const uint64_t n = c0->reads.n;
+    for (uint32_t r = 0; r < world; r++) {
+        disco_ctx *c = ctxs[r];
+        if (!c->d_words) return fail(c, DISCO_E_ARG, "load reads first");
+        if (c->reads.n != n || c->reads.max_len != c0->reads.max_len || c->reads.min_len != c0->reads.min_len)
+            return fail(c, DISCO_E_ARG, "every context must hold the same read set (reads are replicated)");
+        for (uint32_t q = 0; q < r; q++) if (ctxs[q] == c) return fail(c, DISCO_E_ARG, "the same context twice");
+    }
+    // peer access between every pair of distinct devices
+    for (uint32_t a = 0; a < world; a++)
+        for (uint32_t b = 0; b < world; b++) {
+            const int da = ctxs[a]->device, db = ctxs[b]->device;
+            if (da == db) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, da, db);
+            if (!can) return fail(ctxs[a], DISCO_E_CUDA, "device %d cannot access device %d: no peer path", da, db);
+            cudaSetDevice(da);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(ctxs[a], DISCO_E_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", da, db, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    uint64_t bounds[DISCO_MAX_SHARDS + 1];
+    for (uint32_t r = 0; r <= world; r++) bounds[r] = ((uint64_t)r * n) / world; // n < 2^31: no overflow; = multigpu.partition
+    const void *tables[DISCO_MAX_SHARDS] = {}, *rows[DISCO_MAX_SHARDS] = {}, *keys[DISCO_MAX_SHARDS] = {};
+    uint64_t maxdeg[DISCO_MAX_SHARDS] = {};
+    int rcs[DISCO_MAX_SHARDS] = {};
+    std::atomic<bool> failed{false};
+    HostBarrier bar(world);
+
+    auto body = [&](uint32_t r) {
+        disco_ctx *ctx = ctxs[r];
+        const uint64_t lo = bounds[r], hi = bounds[r + 1];
+        auto run = [&](auto &&fn) { // skipped once any rank failed; the barriers are always kept
+            if (failed.load()) return;
+            const int rc = fn();
+            if (rc) { rcs[r] = rc; failed.store(true); }
+        };
+        auto cuda = [&](cudaError_t e, const char *what) -> int {
+            return e == cudaSuccess ? DISCO_OK : fail(ctx, DISCO_E_CUDA, "%s: %s", what, cudaGetErrorString(e));
+        };
+        run([&] { return disco_gpu_set_shard(ctx, world, r); });
+        run([&] { return disco_gpu_begin(ctx, min_overlap, max_edge_per_kmer); });
+        run([&] { return disco_gpu_phase_table(ctx, 0); });
+        run([&] { return disco_gpu_sync(ctx); });
+        tables[r] = ctx->d_slots; keys[r] = ctx->d_best;
+        bar.wait();                                   // every shard complete, every pointer published
+        run([&] { return disco_gpu_import_peer_ptrs(ctx, DISCO_MEM_TABLE, tables, nullptr); });
+        run([&] { return cuda(cudaMemcpy(ctx->peer_keys.d_ptrs, keys, sizeof keys, cudaMemcpyHostToDevice), "publish key pointers"); });
+        run([&] { return disco_gpu_phase_contained(ctx, lo, hi); });
+        run([&] { return disco_gpu_sync(ctx); });
+        bar.wait();                                   // every rank's keys written
+        run([&] { return cuda(launch_min_keys(ctx->d_best, ctx->peer_keys.d_ptrs, world, r, n, ctx->stream), "min-reduce of the containment keys"); });
+        run([&] { return disco_gpu_phase_finish_contained(ctx); });
+        bar.wait();                                   // nobody probes the old table (or reads our keys) any more
+        run([&] { return disco_gpu_phase_table(ctx, 1); });
+        run([&] { return disco_gpu_sync(ctx); });
+        bar.wait();
+        run([&] { return disco_gpu_phase_edges(ctx, lo, hi); });
+        rows[r] = ctx->d_rows; maxdeg[r] = ctx->stats.max_degree;
+        bar.wait();                                   // every rank's rows and row infos complete
+        run([&] {
+            for (uint32_t q = 0; q < world; q++) {    // row infos: each rank's own range is final, copy it over
+                if (q == r || bounds[q + 1] == bounds[q]) continue;
+                const int rc = cuda(cudaMemcpyPeerAsync(ctx->d_rowinfo + bounds[q], ctx->device, ctxs[q]->d_rowinfo + bounds[q], ctxs[q]->device,
+                                                        (bounds[q + 1] - bounds[q]) * sizeof(uint64_t), ctx->stream), "row info exchange");
+                if (rc) return rc;
+            }
+            return DISCO_OK;
+        });
+        run([&] { return disco_gpu_set_max_degree(ctx, *std::max_element(maxdeg, maxdeg + world)); });
+        run([&] { return disco_gpu_import_peer_ptrs(ctx, DISCO_MEM_ROWS, rows, bounds); });
+        run([&] { return disco_gpu_phase_reduce_mark(ctx, lo, hi); });
+        run([&] { return disco_gpu_sync(ctx); });
+        bar.wait();                                   // emission reads the marks of remote neighbours
+        run([&] { return disco_gpu_phase_reduce_emit(ctx, lo, hi); });
+        bar.wait();                                   // nobody reads a peer's rows after this point
+    };
+    std::vector<std::thread> threads;
+    for (uint32_t r = 1; r < world; r++) threads.emplace_back(body, r);
+    body(0);
+    for (auto &t : threads) t.join();
+    for (uint32_t r = 0; r < world; r++) if (rcs[r]) return rcs[r];
     return DISCO_OK;
 }
 

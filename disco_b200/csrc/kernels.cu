@@ -1886,6 +1886,26 @@ cudaError_t launch_restride(const uint64_t *src, int src_stride, int src_words, 
     return cudaGetLastError();
 }
 
+// in-place MIN over the ranks' containment keys (single-process multi-GPU: the peers' arrays are read through NVLink).
+// Every rank runs this on its own array at the same time; values only ever decrease towards the global minimum, so a
+// peer's half-reduced value is as good as its original one.
+__global__ void k_min_keys(unsigned long long *mine, const uint64_t *const *peers, uint32_t world, uint32_t rank, uint64_t n)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long v = mine[i];
+    for (uint32_t r = 0; r < world; r++)
+        if (r != rank) { const unsigned long long o = __ldcg(reinterpret_cast<const unsigned long long *>(peers[r]) + i); v = o < v ? o : v; }
+    mine[i] = v;
+}
+
+cudaError_t launch_min_keys(unsigned long long *mine, const uint64_t *const *peers, uint32_t world, uint32_t rank, uint64_t n, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    k_min_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mine, peers, world, rank, n);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_revcomp_rows(const ReadsView &r, uint64_t *out, cudaStream_t s)
 {
     if (r.n == 0) return cudaSuccess;

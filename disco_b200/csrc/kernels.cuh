@@ -105,6 +105,8 @@ cudaError_t launch_contained_rows(const unsigned long long *best, const ReadsVie
 cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t s);
 cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t s);
 cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s);
+// mine[i] = min over ranks of peers[r][i] (peers = device array of the ranks' key arrays, [rank] == mine)
+cudaError_t launch_min_keys(unsigned long long *mine, const uint64_t *const *peers, uint32_t world, uint32_t rank, uint64_t n, cudaStream_t s);
 // out[r] = reverse complement of read r, same row layout as r.words
 cudaError_t launch_revcomp_rows(const ReadsView &r, uint64_t *out, cudaStream_t s);
 // copy n rows of src_words u64 (pitch src_stride) into rows of dst_stride u64, zero-filling the tail (dst_stride >= src_words)

@@ -22,6 +22,7 @@ EXPORTS = [
     "disco_gpu_set_rows_used", "disco_gpu_use_rows", "disco_gpu_phase_edges_part", "disco_gpu_phase_reduce_mark",
     "disco_gpu_phase_reduce_emit", "disco_gpu_set_shard", "disco_gpu_export_mem", "disco_gpu_import_peers",
     "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table", "disco_gpu_table_words", "disco_gpu_adopt_buffer",
+    "disco_gpu_build_graph_multi",
 ]
 MAX_SHARDS, IPC_HANDLE_BYTES, MEM_TABLE, MEM_ROWS = 8, 64, 0, 1
 
@@ -85,6 +86,7 @@ def lib():
         L.disco_gpu_table_words.argtypes = [vp]
         L.disco_gpu_table_words.restype = u64
         L.disco_gpu_adopt_buffer.argtypes = [vp, i32, vp, u64]
+        L.disco_gpu_build_graph_multi.argtypes = [vp, u32, u32, u32]
         for f in ("disco_gpu_dev_contained_keys", "disco_gpu_dev_rowinfo"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = vp
@@ -284,6 +286,17 @@ class GpuBuildGraph:
         self._ck(self._L.disco_gpu_get_stats(self._h, C.byref(s)), "get_stats")
         return s.as_dict()
 
+
+def build_graph_multi(graphs, min_overlap: int, max_edge_per_kmer: int = 4):
+    """Mode B over several contexts of THIS process (one per GPU, or several on one GPU), all holding the same reads:
+    one host thread per context inside the library, peer access between the devices, no NCCL.  Afterwards graphs[r]
+    holds the edges whose lower endpoint lies in rank r's read range; every context holds all contained rows."""
+    L = lib()
+    arr = (C.c_void_p * len(graphs))(*[g._h for g in graphs])
+    rc = L.disco_gpu_build_graph_multi(arr, len(graphs), min_overlap, max_edge_per_kmer)
+    if rc:
+        msgs = [L.disco_gpu_last_error(g._h).decode() for g in graphs]
+        raise DiscoError(f"build_graph_multi -> {rc}: " + " | ".join(m for m in msgs if m))
 
 def sort_edges(e: np.ndarray) -> np.ndarray:
     return e[np.lexsort((e["orient"], e["offset"], e["dst"], e["src"]))]

@@ -2,7 +2,7 @@
 // same options, same config key, same input formats, same output files; the stage itself runs on a B200 through the
 // C ABI of include/disco_gpu.h.
 //
-//   buildG [-pe f1,f2,...] [-se f1,...] -f <prefix> -p <cfg> [-t <threads/shards>] [-m <GB>] [-w <n>] [-g <gpu>]
+//   buildG [-pe f1,f2,...] [-se f1,...] -f <prefix> -p <cfg> [-t <threads/shards>] [-m <GB>] [-w <n>] [-g <gpu>[,<gpu>...]]
 //
 // Mirrors: parseArguments (main.cpp:79-150: unknown option -> usage + exit 1; no args / -h -> usage + exit 0),
 // readOverlapParameter (main.cpp:152-176: MinOverlap4BuildGraph, default 30, missing file -> exit 1),
@@ -10,7 +10,9 @@
 // the file set runDisco.sh lists for -n <t>.  -t is the number of output shards (and host threads); all
 // edges and rows go to shard 0 with mark flag 2, the other shards are created empty (accepted by parsimplify /
 // fullsimplify).  -m and -w are accepted and ignored (the reference ignores -w too, OverlapGraph.cpp:59-81).
-// New, optional: -g <device> (or env DISCO_GPU), default 0.  Fatal errors print the reference's message and, unlike the
+// New, optional: -g <device>[,<device>...] (or env DISCO_GPUS / DISCO_GPU), default 0.  Several devices = the key-sharded
+// partitioning of buildG-MPIRMA inside this one process (disco_gpu_build_graph_multi: reads replicated, table sharded
+// by key, adjacency by read range, remote shards read over NVLink).  Fatal errors print the reference's message and, unlike the
 // reference (exit(0), Common.h:64), return 1.
 #include "../../include/disco_host.h"
 #include <algorithm>
@@ -51,7 +53,7 @@ static void usage()
     cerr << "  -f\tAll file name prefix" << endl;
     cerr << "  -t\tmaximum threads used (= number of output shards)" << endl;
     cerr << "  -m\tmaximum memory usage allowed (accepted for compatibility)" << endl;
-    cerr << "  -g\tCUDA device to run on (default 0 or $DISCO_GPU)" << endl;
+    cerr << "  -g\tCUDA device(s) to run on, comma separated (default 0 or $DISCO_GPUS)" << endl;
 }
 
 [[noreturn]] static void die(const string &msg)
@@ -74,7 +76,7 @@ int main(int argc, char **argv)
     vector<string> pe, se;
     string prefix, cfg;
     unsigned long long threads = 1;
-    int device = getenv("DISCO_GPU") ? atoi(getenv("DISCO_GPU")) : 0;
+    string devices = getenv("DISCO_GPUS") ? getenv("DISCO_GPUS") : getenv("DISCO_GPU") ? getenv("DISCO_GPU") : "0";
     cout << "PRINTING ARGUMENTS" << endl;
     for (int i = 0; i < argc; i++) cout << argv[i] << ' ';
     cout << endl;
@@ -89,7 +91,7 @@ int main(int argc, char **argv)
         else if (a == "-w") (void)next();
         else if (a == "-m") (void)next();
         else if (a == "-p") cfg = next();
-        else if (a == "-g") device = atoi(next().c_str());
+        else if (a == "-g") devices = next();
         else {
             usage();
             if (a == "-h" || a == "--help") return 0;
@@ -152,24 +154,48 @@ int main(int argc, char **argv)
     if (n == 0) die("No reads found in the read files provided! Please check if the filename(s) and path(s) are correct.");
     cout << "Function Dataset() finished in " << now() - t0 << " Seconds." << endl << endl;
 
-    // ---- hot path on the GPU
+    // ---- hot path on the GPU(s)
     t0 = now();
-    disco_ctx *ctx = nullptr;
-    if (disco_gpu_create(&ctx, device)) die(string("GPU context: ") + disco_gpu_last_error(nullptr));
-    if (disco_gpu_load_reads(ctx, disco_reads_packed(reads), disco_reads_len(reads), n, disco_reads_words_per_read(reads)))
-        die(string("load reads: ") + disco_gpu_last_error(ctx));
-    if (disco_gpu_build_graph(ctx, (uint32_t)min_overlap, 4 /* MAX_EDGE_PER_KMER, Common.h:62 */))
-        die(string("build graph: ") + disco_gpu_last_error(ctx));
-    uint64_t n_contained = 0, n_edges = 0;
-    disco_gpu_counts(ctx, &n_contained, &n_edges);
+    vector<int> devs;
+    for (auto &d : split_tok(devices, ',')) if (!trimmed(d).empty()) devs.push_back(atoi(trimmed(d).c_str()));
+    if (devs.empty()) devs.push_back(0);
+    if (devs.size() > DISCO_MAX_SHARDS) die("at most " + to_string(DISCO_MAX_SHARDS) + " GPUs");
+    vector<disco_ctx *> ctxs(devs.size(), nullptr);
+    for (size_t r = 0; r < devs.size(); r++) {
+        if (disco_gpu_create(&ctxs[r], devs[r])) die(string("GPU context: ") + disco_gpu_last_error(nullptr));
+        if (disco_gpu_load_reads(ctxs[r], disco_reads_packed(reads), disco_reads_len(reads), n, disco_reads_words_per_read(reads)))
+            die(string("load reads: ") + disco_gpu_last_error(ctxs[r]));
+    }
+    if (ctxs.size() == 1) {
+        if (disco_gpu_build_graph(ctxs[0], (uint32_t)min_overlap, 4 /* MAX_EDGE_PER_KMER, Common.h:62 */))
+            die(string("build graph: ") + disco_gpu_last_error(ctxs[0]));
+    } else if (disco_gpu_build_graph_multi(ctxs.data(), (uint32_t)ctxs.size(), (uint32_t)min_overlap, 4)) {
+        string msg = "build graph:";
+        for (auto c : ctxs) if (*disco_gpu_last_error(c)) msg += string(" [") + disco_gpu_last_error(c) + "]";
+        die(msg);
+    }
+    // contained rows: every context holds all of them; edges: each context holds those of its read range
+    uint64_t n_contained = 0, n_edges = 0, w = 0;
+    disco_gpu_counts(ctxs[0], &n_contained, nullptr);
     vector<disco_crow> rows(n_contained);
+    if (disco_gpu_get_contained(ctxs[0], rows.data(), rows.size(), &w)) die(disco_gpu_last_error(ctxs[0]));
+    vector<uint64_t> first(ctxs.size() + 1, 0);
+    for (size_t r = 0; r < ctxs.size(); r++) { uint64_t ne = 0; disco_gpu_counts(ctxs[r], nullptr, &ne); first[r + 1] = first[r] + ne; }
+    n_edges = first.back();
     vector<disco_edge> edges(n_edges);
-    uint64_t w = 0;
-    if (disco_gpu_get_contained(ctx, rows.data(), rows.size(), &w)) die(disco_gpu_last_error(ctx));
-    if (disco_gpu_get_edges(ctx, edges.data(), edges.size(), &w)) die(disco_gpu_last_error(ctx));
-    disco_stats st;
-    disco_gpu_get_stats(ctx, &st);
-    disco_gpu_destroy(ctx);
+    disco_stats st{};
+    for (size_t r = 0; r < ctxs.size(); r++) {
+        if (disco_gpu_get_edges(ctxs[r], edges.data() + first[r], first[r + 1] - first[r], &w)) die(disco_gpu_last_error(ctxs[r]));
+        disco_stats sr;
+        disco_gpu_get_stats(ctxs[r], &sr);
+        if (r == 0) st = sr;
+        else {
+            st.raw_directed_edges += sr.raw_directed_edges; st.cap_fired += sr.cap_fired;
+            st.multi_overlap_pairs += sr.multi_overlap_pairs; st.one_sided_edges += sr.one_sided_edges;
+            st.ms_total = max(st.ms_total, sr.ms_total);
+        }
+    }
+    for (auto c : ctxs) disco_gpu_destroy(c);
     const double t_gpu = now() - t0;
     cout << "Hash Table size set to: " << st.table_buckets * 4 << endl;
     cout << "Function insertDataset() finished in " << (st.ms_table_all + st.ms_table_nc) / 1000.0 << " Seconds." << endl;

@@ -174,6 +174,12 @@ void *disco_gpu_dev_table(disco_ctx *ctx);
  * TLB once the remote footprint exceeds ~1-2 GB). */
 uint64_t disco_gpu_table_words(disco_ctx *ctx);
 int disco_gpu_adopt_buffer(disco_ctx *ctx, int which, void *d_ptr, uint64_t n_u64);
+/* The whole of Mode B for several GPUs driven by ONE process (`buildG -g 0,1,...`): one context per GPU (or several on
+ * one GPU), every context holding the same reads; one host thread per context, peer access instead of IPC, the
+ * containment keys min-reduced and the row infos copied over NVLink by the library itself -- no NCCL, no MPI.
+ * Afterwards context r holds the edges whose lower endpoint lies in [r*n/world, (r+1)*n/world) and every context holds
+ * all contained rows.  Returns the first failing rank's code (its message: disco_gpu_last_error of that context). */
+int disco_gpu_build_graph_multi(disco_ctx *const *ctxs, uint32_t world, uint32_t min_overlap, uint32_t max_edge_per_kmer);
 /* largest row length over all ranks (sizes the reduction kernel's shared memory) */
 int disco_gpu_set_max_degree(disco_ctx *ctx, uint64_t max_degree);
 /* wait for everything queued on the context's stream */

@@ -57,3 +57,27 @@ def test_files_match_reference(tmp_path, name):
     assert open(prefix + "_CheckpointInfo.txt").read().split() == ["CCR=Complete", "GC=Complete"]
     r2 = _run(["-se", str(fa), "-f", prefix, "-p", str(cfg)])
     assert r2.returncode == 0 and "Graph already exists" in r2.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["paired_800x2x250_m30", "dup_contained_3000_m50"])
+def test_several_gpus_in_one_process(tmp_path, name):
+    """-g a,b,c = the key-sharded partitioning inside one process (disco_gpu_build_graph_multi).  With one GPU in the box
+    the three contexts share device 0; the files must still equal the reference's."""
+    g = load_golden([p for p in GOLDEN if name in p][0])
+    fa = tmp_path / "reads.fa"
+    fa.write_text("".join(f">{i + 1}\n{s}\n" for i, s in enumerate(g["records"])))
+    cfg = tmp_path / "disco.cfg"
+    cfg.write_text(f"MinOverlap4BuildGraph = {g['min_overlap']}\n")
+    prefix = str(tmp_path / "graph" / "out")
+    os.makedirs(os.path.dirname(prefix))
+    import torch
+    devs = "0,1,0" if torch.cuda.device_count() >= 2 else "0,0,0"
+    r = _run(["-pe" if "paired" in name else "-se", str(fa), "-f", prefix, "-p", str(cfg), "-t", "2", "-g", devs])
+    assert r.returncode == 0, r.stdout + r.stderr
+    edges = sorted(l.rstrip("\n") for t in range(2) for l in open(f"{prefix}_{t}_parGraph.txt"))
+    assert edges == sorted(l + ",2" for l in g["ref_edges"])
+    rows = [l.rstrip("\n") for t in range(2) for l in open(f"{prefix}_{t}_containedReads.txt")]
+    assert rows == g["ref_crows"]
+    r = _run(["-se", str(fa), "-f", str(tmp_path / "x"), "-p", str(cfg), "-g", "0,1,2,3,4,5,6,7,8"])
+    assert r.returncode == 1 and "at most 8 GPUs" in r.stdout

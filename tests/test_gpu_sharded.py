@@ -139,3 +139,64 @@ def test_shard_argument_checks():
     g.build_graph(50, 4)
     assert g.counts()[1] > 0
     g.close()
+
+
+def _multi(packed, lens, m, devices):
+    gs = []
+    for d in devices:
+        g = gpu.GpuBuildGraph(d)
+        g.load_reads(packed, lens)
+        gs.append(g)
+    gpu.build_graph_multi(gs, m, 4)
+    n = gs[0].n
+    parts = [multigpu.partition(n, r, len(gs)) for r in range(len(gs))]
+    edges = [g.edges() for g in gs]
+    for e, (lo, hi) in zip(edges, parts):
+        assert ((e["src"] >= lo) & (e["src"] < hi)).all()
+    crows = [np.sort(g.contained(), order=["contained"]) for g in gs]
+    raw = sum(g.stats()["raw_directed_edges"] for g in gs)
+    for g in gs:
+        g.close()
+    return gpu.sort_edges(np.concatenate(edges)), crows, raw
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_single_process_driver_matches_single_table(world):
+    """disco_gpu_build_graph_multi (what `buildG -g a,b,...` calls): host threads + peer pointers, here with every
+    context on device 0"""
+    rs = synth.dup_contained(12000, 150, 60.0, seed=41)
+    packed, lens = host.pack_codes(rs.codes, rs.off)
+    g1 = gpu.GpuBuildGraph(0)
+    g1.load_reads(packed, lens)
+    g1.build_graph(35, 4)
+    e1, c1, raw1 = gpu.sort_edges(g1.edges()), np.sort(g1.contained(), order=["contained"]), g1.stats()["raw_directed_edges"]
+    g1.close()
+    e, crows, raw = _multi(packed, lens, 35, [0] * world)
+    assert len(e1) > 0 and np.array_equal(e, e1) and raw == raw1
+    for c in crows:
+        assert np.array_equal(c, c1)
+
+
+def test_single_process_driver_two_devices():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rs = synth.single_genome(300_000, 150, 30.0, seed=43)
+    packed, lens = host.pack_codes(rs.codes, rs.off)
+    g1 = gpu.GpuBuildGraph(0)
+    g1.load_reads(packed, lens)
+    g1.build_graph(50, 4)
+    e1, c1 = gpu.sort_edges(g1.edges()), np.sort(g1.contained(), order=["contained"])
+    g1.close()
+    e, crows, _ = _multi(packed, lens, 50, [0, 1])
+    assert np.array_equal(e, e1) and all(np.array_equal(c, c1) for c in crows)
+
+
+def test_single_process_driver_rejects_mismatched_reads():
+    rs = synth.single_genome(3000, 150, 20.0, seed=44)
+    packed, lens = host.pack_codes(rs.codes, rs.off)
+    a, b = gpu.GpuBuildGraph(0), gpu.GpuBuildGraph(0)
+    a.load_reads(packed, lens)
+    b.load_reads(packed[:2000], lens[:2000])
+    with pytest.raises(gpu.DiscoError):
+        gpu.build_graph_multi([a, b], 50, 4)
+    a.close(); b.close()
