@@ -379,7 +379,14 @@ def run_ours(args):
         "roofline_probe": roof("k_edges_probe", alg_probe, ms_probe, traffic.get("k_edges_probe") if isinstance(traffic, dict) else None),
         "roofline_edge_pass": roof("k_edges_probe+k_edges_verify+k_edges_exact", alg_pass, ms_pass,
                                    traffic.get("edge_pass") if isinstance(traffic, dict) else None),
-        "random_access_peak": {"accesses_per_s": 39.4e9, "source": "profiles/gather_bench.cu on B200: 39.4 G independent <=128 B line accesses/s",
+        # the yardstick that fits this path: random-access rates measured with profiles/gather_bench.cu on the same B200
+        # (profiles/r01_gather_microbench.txt): 39.4 G/s for 32-byte accesses (buckets), 22.3 G/s for 64-byte ones (read rows)
+        "random_access_peak": {"accesses_per_s_32B": 39.4e9, "accesses_per_s_64B": 22.3e9,
+                               "source": "profiles/gather_bench.cu on B200 (profiles/r01_gather_microbench.txt)",
+                               "verify_rows_per_s": vf / (ms_verify / 1000.0) if ms_verify > 0 else None,
+                               "verify_frac_of_64B_peak": (vf / (ms_verify / 1000.0) / 22.3e9) if ms_verify > 0 else None,
+                               "probe_buckets_per_s": bk / (ms_probe / 1000.0) if ms_probe > 0 else None,
+                               "probe_frac_of_32B_peak": (bk / (ms_probe / 1000.0) / 39.4e9) if ms_probe > 0 else None,
                                "edge_pass_accesses_per_s": (bk + vf) / (ms_pass / 1000.0) if ms_pass > 0 else None},
         "edges_per_s": {"raw_directed": tot_raw / (ms_step / 1000.0), "reduced": tot_edges / (ms_step / 1000.0)},
         "phase_ms": {k: float(np.mean([s[k] for s in stats_acc])) for k in st if k.startswith("ms_")},
