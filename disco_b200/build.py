@@ -46,7 +46,7 @@ def build_host(force=False, verbose=False):
     deps = srcs + [os.path.join(HOST, f) for f in os.listdir(HOST) if f.endswith(".h")] + \
         [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
     if force or _newer(HOST_LIB, deps):
-        _run(["g++", "-O3", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB] + srcs + ["-lz"], verbose)
+        _run(["g++", "-O3", "-mpopcnt", "-std=c++17", "-fopenmp", "-fPIC", "-shared", "-Wall", "-o", HOST_LIB] + srcs + ["-lz"], verbose)
     main = os.path.join(HOST, "buildg_main.cpp")
     if os.path.exists(main) and (force or _newer(BUILDG, deps + [main, GPU_LIB])):
         os.makedirs(os.path.dirname(BUILDG), exist_ok=True)

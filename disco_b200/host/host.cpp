@@ -9,6 +9,10 @@
 #include <vector>
 #include <zlib.h>
 #include <chrono>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 namespace {
 thread_local std::string g_err;
@@ -32,96 +36,158 @@ const char *kFilterStrings[] = {
 // merCheckStrings (Dataset.cpp:87): AC AG AT CG CT GT AAT ATA TAA AAC ACA CAA AAG AGA GAA GGGGCC -- see short_repeat_hit()
 constexpr uint64_t kMinReadSize = 30; // Dataset.h:15
 
-uint64_t count_substring(const char *s, uint64_t n, const char *sub, uint64_t m)
-{ // Common.h:171-181: std::string::find from the end of the previous match (non-overlapping)
-    uint64_t cnt = 0, i = 0;
-    while (i + m <= n) {
-        const void *p = memmem(s + i, n - i, sub, m);
-        if (!p) break;
-        cnt++;
-        i = (const char *)p - s + m;
-    }
-    return cnt;
-}
+// ---- testRead (Dataset.cpp:403-452) on the 2-bit packed read ----------------------------------------------------------
+// The reference works on std::string (count per base, 38 x 2 string compares, fifteen countSubstring() passes).  Here a
+// record is packed in ONE pass over its characters (which also finds non-ACGT letters); everything else is word
+// arithmetic on the packed form: base counts and pattern counts are popcounts of per-base equality masks, the two
+// 29-base ends are 58-bit integers looked up among the packed filter strings.  Same decisions, ~4x fewer cycles.
+constexpr uint64_t kEven = 0x5555555555555555ULL;
 
-// base class table: A C G T -> 0 1 2 3 (the packing code, HashTable.h:16-22), everything else 255
-const struct BaseTab {
+// A C G T (either case) -> 0 1 2 3 (the packing code, HashTable.h:16-22), everything else 255.  The reference
+// upper-cases first (Dataset.cpp:303-304), so lower-case letters are accepted as their upper-case form.
+const struct CodeTab {
     uint8_t t[256];
-    BaseTab() { for (int i = 0; i < 256; i++) t[i] = 255; t['A'] = 0; t['C'] = 1; t['G'] = 2; t['T'] = 3; }
-} kBase;
-
-// The di-/tri-mer repeat test of Dataset.cpp:431-438 for all fifteen short patterns in ONE pass over the base codes.
-// countSubstring() counts greedily from the left without overlap; of the listed patterns only ATA, ACA and AGA can
-// overlap themselves, so they carry a "next allowed start", the others are plain occurrence counts.
-bool short_repeat_hit(const uint8_t *c, uint64_t n, uint64_t thr)
-{
-    uint32_t di[16] = {0}, tri[64] = {0};
-    uint32_t next_xyx[16] = {0}; // indexed by (x, y) of an xyx pattern
-    int c0 = c[0], c1 = n > 1 ? c[1] : 0;
-    if (n > 1) di[c0 * 4 + c1]++;
-    for (uint64_t i = 2; i < n; i++) {
-        const int c2 = c[i];
-        di[c1 * 4 + c2]++;
-        const int t = (c0 * 4 + c1) * 4 + c2;
-        if (c0 == c2) { // xyx patterns: greedy, non-overlapping
-            const uint32_t start = (uint32_t)(i - 2);
-            uint32_t &nx = next_xyx[c0 * 4 + c1];
-            if (start >= nx) { tri[t]++; nx = start + 3; }
-        } else tri[t]++;
-        c0 = c1; c1 = c2;
+    CodeTab()
+    {
+        for (int i = 0; i < 256; i++) t[i] = 255;
+        t['A'] = t['a'] = 0; t['C'] = t['c'] = 1; t['G'] = t['g'] = 2; t['T'] = t['t'] = 3;
     }
-    // A0 C1 G2 T3 -- "AC","AG","AT","CG","CT","GT"
-    const int dimers[6] = {0 * 4 + 1, 0 * 4 + 2, 0 * 4 + 3, 1 * 4 + 2, 1 * 4 + 3, 2 * 4 + 3};
-    for (int d : dimers) if ((uint64_t)di[d] * 2 >= thr) return true;
-    // "AAT","ATA","TAA","AAC","ACA","CAA","AAG","AGA","GAA"
-    const int trimers[9] = {(0 * 4 + 0) * 4 + 3, (0 * 4 + 3) * 4 + 0, (3 * 4 + 0) * 4 + 0, (0 * 4 + 0) * 4 + 1, (0 * 4 + 1) * 4 + 0,
-                            (1 * 4 + 0) * 4 + 0, (0 * 4 + 0) * 4 + 2, (0 * 4 + 2) * 4 + 0, (2 * 4 + 0) * 4 + 0};
-    for (int t : trimers) if ((uint64_t)tri[t] * 3 >= thr) return true;
-    return false;
+} kCode;
+
+// the 38 filter strings as 58-bit integers (29 bases, first base in the top bits)
+const struct FilterKeys {
+    uint64_t k[sizeof(kFilterStrings) / sizeof(kFilterStrings[0])];
+    FilterKeys()
+    {
+        for (size_t f = 0; f < sizeof(k) / sizeof(k[0]); f++) {
+            uint64_t v = 0;
+            for (int i = 0; i < 29; i++) v = (v << 2) | kCode.t[(unsigned char)kFilterStrings[f][i]];
+            k[f] = v;
+        }
+    }
+    bool has(uint64_t key) const
+    {
+        bool hit = false;
+        for (uint64_t x : k) hit |= (x == key);
+        return hit;
+    }
+} kFilterKeys;
+
+// Pack a raw record (upper- or lower-case, optionally with embedded newlines that are dropped, Dataset.cpp:276) into
+// `out` (base i at bits 62 - 2 (i mod 32) of word i / 32, HashTable.cpp:458-470; the tail of the last word is zero).
+// Returns the number of bases; *bad is set when a character other than A C G T was seen (its code is then garbage).
+inline uint64_t pack_raw(const char *p, uint64_t n, bool strip_nl, uint64_t *out, bool *bad)
+{
+    uint64_t w = 0, L = 0, k = 0;
+    uint8_t acc = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const unsigned char ch = (unsigned char)p[i];
+        if (strip_nl && ch == '\n') continue;
+        const uint8_t c = kCode.t[ch];
+        acc |= c;
+        w = (w << 2) | (c & 3);
+        if ((++L & 31) == 0) { out[k++] = w; w = 0; }
+    }
+    if (L & 31) out[k++] = w << (2 * (32 - (L & 31)));
+    *bad = (acc & 0x80) != 0;
+    return L;
 }
 
-// s = upper-cased read, codes = scratch of n bytes that receives the base codes (valid when the function returns true)
-bool test_read_codes(const char *s, uint64_t n, uint8_t *codes)
+// bits 2j (j = 31 - position in the word) set where the base equals x; `valid` masks the real bases of the word
+inline uint64_t eq_mask(uint64_t w, int x, uint64_t valid)
 {
-    if (n < kMinReadSize) return false;
+    const uint64_t hi = (w >> 1) & kEven, lo = w & kEven;
+    const uint64_t h = (x & 2) ? hi : ~hi, l = (x & 1) ? lo : ~lo;
+    return h & l & valid;
+}
+
+// 29 bases starting at base `start` as a 58-bit integer
+inline uint64_t key29(const uint64_t *w, uint64_t start)
+{
+    const uint64_t wi = start >> 5, off = start & 31;
+    uint64_t v = w[wi] << (2 * off);
+    if (off > 3) v |= w[wi + 1] >> (64 - 2 * off);
+    return v >> 6;
+}
+
+// testRead on a packed read of L bases (W = ceil(L / 32) words).  eq = scratch of 4 * (W + 1) words.
+bool test_packed(const uint64_t *w, uint64_t L, uint64_t *eq)
+{
+    if (L < kMinReadSize) return false;
+    const uint64_t W = (L + 31) / 32;
+    // per-base equality masks, E[x][k]; one extra zero word so that shifted reads never run off the end
+    uint64_t *E[4] = {eq, eq + (W + 1), eq + 2 * (W + 1), eq + 3 * (W + 1)};
     uint64_t cnt[4] = {0, 0, 0, 0};
-    uint8_t bad = 0;
-    for (uint64_t i = 0; i < n; i++) {
-        const uint8_t c = kBase.t[(unsigned char)s[i]];
-        codes[i] = c;
-        bad |= c;
-        cnt[c & 3]++;
+    for (uint64_t k = 0; k < W; k++) {
+        const uint64_t nb = (k + 1 < W || (L & 31) == 0) ? 32 : (L & 31);
+        const uint64_t valid = nb == 32 ? kEven : (kEven << (2 * (32 - nb)));
+        for (int x = 0; x < 4; x++) { E[x][k] = eq_mask(w[k], x, valid); cnt[x] += (uint64_t)__builtin_popcountll(E[x][k]); }
     }
-    if (bad & 0x80) return false; // something other than A C G T (Dataset.cpp:411)
-    // (the reference counts with (ch >> 1) & 3 = A0 C1 T2 G3: the same four counters in another order)
-    uint64_t thr = (uint64_t)((double)n * .7); // Dataset.cpp:415
+    for (int x = 0; x < 4; x++) E[x][W] = 0;
+    uint64_t thr = (uint64_t)((double)L * .7); // Dataset.cpp:415
     if (cnt[0] >= thr || cnt[1] >= thr || cnt[2] >= thr || cnt[3] >= thr) return false;
-    for (const char *f : kFilterStrings) {
-        const uint64_t len = 29;
-        if (n < len) return false;
-        if (f[0] == s[0] && memcmp(f, s, len) == 0) return false;
-        if (f[0] == s[n - len] && memcmp(f, s + n - len, len) == 0) return false;
+    // either end equal to one of the 38 micro-repeat strings (Dataset.cpp:420-429; L >= 30 > 29 here)
+    if (kFilterKeys.has(key29(w, 0)) || kFilterKeys.has(key29(w, L - 29))) return false;
+    thr = (uint64_t)((double)L * .5);          // Dataset.cpp:431
+    // mask of base x at position i + s, aligned to position i (s bases further on = 2s bits lower)
+    auto sh = [&](int x, uint64_t k, int s) -> uint64_t { return (E[x][k] << (2 * s)) | (E[x][k + 1] >> (64 - 2 * s)); };
+    enum { A = 0, C = 1, G = 2, T = 3 };
+    // countSubstring() (Common.h:171-181) counts from the left without overlap; only the x-y-x patterns (ATA ACA AGA) can
+    // overlap themselves, for every other pattern that is the plain number of occurrences.  One sweep over the words
+    // counts all sixteen patterns: di[] = AC AG AT CG CT GT, tri[] = AAT AAC AAG | TAA CAA GAA | ATA ACA AGA (overlapping)
+    uint64_t di[6] = {0}, tri[9] = {0}, c6 = 0;
+    auto pc = [](uint64_t v) { return (uint64_t)__builtin_popcountll(v); };
+    for (uint64_t k = 0; k < W; k++) {
+        const uint64_t e[4] = {E[A][k], E[C][k], E[G][k], E[T][k]};
+        const uint64_t s1[4] = {sh(A, k, 1), sh(C, k, 1), sh(G, k, 1), sh(T, k, 1)};
+        const uint64_t s2[4] = {sh(A, k, 2), sh(C, k, 2), sh(G, k, 2), sh(T, k, 2)};
+        di[0] += pc(e[A] & s1[C]); di[1] += pc(e[A] & s1[G]); di[2] += pc(e[A] & s1[T]);
+        di[3] += pc(e[C] & s1[G]); di[4] += pc(e[C] & s1[T]); di[5] += pc(e[G] & s1[T]);
+        const uint64_t aa_ = e[A] & s1[A], _aa = s1[A] & s2[A], a_a = e[A] & s2[A];
+        tri[0] += pc(aa_ & s2[T]); tri[1] += pc(aa_ & s2[C]); tri[2] += pc(aa_ & s2[G]);
+        tri[3] += pc(e[T] & _aa); tri[4] += pc(e[C] & _aa); tri[5] += pc(e[G] & _aa);
+        tri[6] += pc(a_a & s1[T]); tri[7] += pc(a_a & s1[C]); tri[8] += pc(a_a & s1[G]);
+        c6 += pc(e[G] & s1[G] & s2[G] & sh(G, k, 3) & sh(C, k, 4) & sh(C, k, 5)); // GGGGCC
     }
-    thr = (uint64_t)((double)n * .5); // Dataset.cpp:431
-    if (short_repeat_hit(codes, n, thr)) return false;
-    if (count_substring(s, n, "GGGGCC", 6) * 6 >= thr) return false;
+    for (uint64_t d : di) if (d * 2 >= thr) return false;
+    for (int t = 0; t < 6; t++) if (tri[t] * 3 >= thr) return false;
+    if (c6 * 6 >= thr) return false;
+    const int mid[3] = {T, C, G};
+    for (int t = 0; t < 3; t++) { // the greedy count is at most the overlapping count -- walk only when that is large
+        if (tri[6 + t] * 3 < thr) continue;
+        uint64_t greedy = 0;
+        for (uint64_t i = 0; i + 3 <= L;) {
+            const uint64_t k = i >> 5, bit = 62 - 2 * (i & 31);
+            const bool hit = ((E[A][k] & sh(mid[t], k, 1) & sh(A, k, 2)) >> bit) & 1;
+            if (hit) { greedy++; i += 3; } else i++;
+        }
+        if (greedy * 3 >= thr) return false;
+    }
     return true;
+}
+
+// accept / reject one raw record the way Dataset::readDataset does (Dataset.cpp:305: longer than minOverlap, then
+// testRead); on acceptance `words` holds the packed read.  scratch vectors are per thread.
+inline uint64_t filter_record(const char *p, uint64_t n, bool strip_nl, uint32_t min_overlap, std::vector<uint64_t> &words,
+                              std::vector<uint64_t> &eq)
+{
+    const uint64_t wmax = n / 32 + 2;
+    if (words.size() < wmax) words.resize(wmax);
+    if (eq.size() < 4 * (wmax + 1)) eq.resize(4 * (wmax + 1));
+    bool bad = false;
+    const uint64_t L = pack_raw(p, n, strip_nl, words.data(), &bad);
+    if (bad || L <= min_overlap || L > 32767) return 0;
+    return test_packed(words.data(), L, eq.data()) ? L : 0;
 }
 
 bool test_read(const char *s, uint64_t n)
 {
-    std::vector<uint8_t> codes(n ? n : 1);
-    return test_read_codes(s, n, codes.data());
-}
-
-void pack_codes_into(const uint8_t *c, uint64_t n, uint64_t *out)
-{
-    for (uint64_t w = 0; w * 32 < n; w++) {
-        const uint64_t e = std::min<uint64_t>(n, w * 32 + 32);
-        uint64_t v = 0;
-        for (uint64_t i = w * 32; i < e; i++) v = (v << 2) | c[i];
-        out[w] = v << (2 * (w * 32 + 32 - e)); // HashTable.cpp:458-470: base i at bits 62 - 2 (i mod 32)
-    }
+    std::vector<uint64_t> words, eq;
+    bool bad = false;
+    words.resize(n / 32 + 2);
+    eq.resize(4 * (n / 32 + 3));
+    const uint64_t L = pack_raw(s, n, false, words.data(), &bad);
+    return !bad && test_packed(words.data(), L, eq.data());
 }
 
 } // namespace
@@ -145,64 +211,49 @@ namespace {
 // the input buffer into the variable-length 2-bit store (no per-read heap objects)
 struct RawRec { const char *p; uint64_t n; bool strip_nl; };
 
-inline uint64_t clean_into(const RawRec &rec, std::string &buf)
-{
-    static const struct Upper { char t[256]; Upper() { for (int i = 0; i < 256; i++) t[i] = (char)toupper(i); } } up;
-    buf.resize(rec.n);
-    uint64_t o = 0;
-    const char *p = rec.p;
-    if (rec.strip_nl) {
-        for (uint64_t k = 0; k < rec.n; k++) { const char c = p[k]; if (c != '\n') buf[o++] = up.t[(unsigned char)c]; } // Dataset.cpp:276 removes only '\n'
-    } else {
-        for (uint64_t k = 0; k < rec.n; k++) buf[o++] = up.t[(unsigned char)p[k]];                                   // Dataset.cpp:303-304
-    }
-    return o;
-}
-
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 void absorb(disco_reads *r, const std::vector<RawRec> &batch)
 {
+    const bool trace = getenv("DISCO_HOST_TRACE") != nullptr;
+    double t0 = trace ? now_s() : 0.0;
     const size_t m = batch.size();
     std::vector<uint16_t> clen(m, 0); // 0 = rejected
 #pragma omp parallel num_threads(r->threads)
     {
-        std::string buf;
-        std::vector<uint8_t> codes;
+        std::vector<uint64_t> words, eq;
 #pragma omp for schedule(dynamic, 2048)
-        for (size_t i = 0; i < m; i++) {
-            const uint64_t o = clean_into(batch[i], buf);
-            if (codes.size() < o) codes.resize(o);
-            if (o > r->min_overlap && o <= 32767 && test_read_codes(buf.data(), o, codes.data())) clen[i] = (uint16_t)o; // Dataset.cpp:305
-        }
+        for (size_t i = 0; i < m; i++)
+            clen[i] = (uint16_t)filter_record(batch[i].p, batch[i].n, batch[i].strip_nl, r->min_overlap, words, eq);
     }
+    if (trace) { fprintf(stderr, "[host]   filter %.3fs (%d threads)\n", now_s() - t0, r->threads); t0 = now_s(); }
     // accepted records get consecutive read ids in file order (Dataset.cpp:133-134 after the file-order sort)
     const size_t n0 = r->vlen.size();
     std::vector<uint64_t> slot(m);
     uint64_t k = n0, w = r->woff.back();
+    for (size_t i = 0; i < m; i++) { slot[i] = k; k += clen[i] != 0; }
+    r->file_index.resize(k); r->vlen.resize(k); r->woff.resize(k + 1);
+    const uint64_t rec0 = r->records;
+    for (size_t i = 0; i < m; i++) { // word offsets: a running sum over the accepted reads
+        if (!clen[i]) continue;
+        w += (clen[i] + 31) / 32;
+        r->woff[slot[i] + 1] = w;
+    }
+#pragma omp parallel for schedule(static) num_threads(r->threads)
     for (size_t i = 0; i < m; i++) {
-        r->records++;
-        slot[i] = k;
-        if (clen[i]) {
-            r->file_index.push_back(r->records);
-            r->vlen.push_back(clen[i]);
-            w += (clen[i] + 31) / 32;
-            r->woff.push_back(w);
-            k++;
-        }
+        if (!clen[i]) continue;
+        r->file_index[slot[i]] = rec0 + i + 1; // fileIndex counts every record (Dataset.cpp:294)
+        r->vlen[slot[i]] = clen[i];
     }
+    r->records += m;
     r->vwords.resize(w, 0);
-#pragma omp parallel num_threads(r->threads)
-    {
-        std::string buf;
-        std::vector<uint8_t> codes;
-#pragma omp for schedule(dynamic, 2048)
-        for (size_t i = 0; i < m; i++) {
-            if (!clen[i]) continue;
-            const uint64_t o = clean_into(batch[i], buf);
-            if (codes.size() < o) codes.resize(o);
-            for (uint64_t q = 0; q < o; q++) codes[q] = kBase.t[(unsigned char)buf[q]];
-            pack_codes_into(codes.data(), o, r->vwords.data() + r->woff[slot[i]]);
-        }
+    if (trace) { fprintf(stderr, "[host]   number %.3fs\n", now_s() - t0); t0 = now_s(); }
+#pragma omp parallel for schedule(dynamic, 2048) num_threads(r->threads)
+    for (size_t i = 0; i < m; i++) {
+        if (!clen[i]) continue;
+        bool bad;
+        pack_raw(batch[i].p, batch[i].n, batch[i].strip_nl, r->vwords.data() + r->woff[slot[i]], &bad); // exactly (clen + 31) / 32 words
     }
+    if (trace) fprintf(stderr, "[host]   pack %.3fs\n", now_s() - t0);
 }
 } // namespace
 
@@ -231,29 +282,47 @@ int disco_reads_add_records(disco_reads *r, const char *seqs, const uint64_t *of
     return 0;
 }
 
-static double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int disco_reads_add_file(disco_reads *r, const char *path)
 {
     const bool trace = getenv("DISCO_HOST_TRACE") != nullptr;
     double t0 = now_s();
     if (!r || r->finalized) return fail("reads object already finalized");
-    std::string data;
+    std::string data;            // gz: the inflated text
+    const char *base = nullptr;  // the text to parse: the mapping of a plain file, or data
+    size_t size = 0;
+    struct Mapping {
+        void *p = MAP_FAILED; size_t n = 0;
+        ~Mapping() { if (p != MAP_FAILED) munmap(p, n); }
+    } map;
     {
         FILE *f = fopen(path, "rb");
         if (!f) return fail(std::string("Unable to open file: ") + path);
         unsigned char magic[2] = {0, 0};
         const size_t got = fread(magic, 1, 2, f);
         const bool gz = got == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
-        if (!gz) { // plain text: one read of the whole file
-            fseek(f, 0, SEEK_END);
-            const long sz = ftell(f);
-            fseek(f, 0, SEEK_SET);
-            data.resize(sz > 0 ? (size_t)sz : 0);
-            if (sz > 0 && fread(&data[0], 1, (size_t)sz, f) != (size_t)sz) { fclose(f); return fail(std::string("read error in ") + path); }
-            fclose(f);
+        fclose(f);
+        if (!gz) { // plain text: map the file, the parser works on the page cache directly
+            const int fd = open(path, O_RDONLY);
+            struct stat st;
+            if (fd < 0 || fstat(fd, &st) != 0) { if (fd >= 0) close(fd); return fail(std::string("Unable to open file: ") + path); }
+            if (st.st_size > 0) {
+                map.n = (size_t)st.st_size;
+                map.p = mmap(nullptr, map.n, PROT_READ, MAP_PRIVATE | MAP_POPULATE, fd, 0);
+                if (map.p != MAP_FAILED) {
+                    madvise(map.p, map.n, MADV_SEQUENTIAL);
+                    madvise(map.p, map.n, MADV_WILLNEED);
+                    base = static_cast<const char *>(map.p); size = map.n;
+                } else { // no mmap on this file system: read it
+                    data.resize(map.n);
+                    size_t off = 0;
+                    while (off < map.n) { const ssize_t g = read(fd, &data[off], map.n - off); if (g <= 0) break; off += (size_t)g; }
+                    if (off != map.n) { close(fd); return fail(std::string("read error in ") + path); }
+                    base = data.data(); size = data.size();
+                }
+            }
+            close(fd);
         } else {
-            fclose(f);
             gzFile fp = gzopen(path, "rb");
             if (!fp) return fail(std::string("Unable to open file: ") + path);
             gzbuffer(fp, 1 << 20);
@@ -262,43 +331,67 @@ int disco_reads_add_file(disco_reads *r, const char *path)
             while ((n = gzread(fp, buf.data(), (unsigned)buf.size())) > 0) data.append(buf.data(), (size_t)n);
             if (n < 0) { gzclose(fp); return fail(std::string("read error in ") + path); }
             gzclose(fp);
+            base = data.data(); size = data.size();
         }
     }
     if (trace) { fprintf(stderr, "[host] read %.3fs\n", now_s() - t0); t0 = now_s(); }
     const uint64_t before = r->records;
-    if (!data.empty()) {
-        const char *b = data.data(), *e = b + data.size();
+    if (size) {
+        const char *b = base, *e = b + size;
         std::vector<RawRec> batch;
+        // every position of `ch`, found by all threads at once (the text is hundreds of MB; one memchr pass per thread)
+        auto find_all = [&](char ch, std::vector<uint64_t> &pos) {
+            const int T = std::max(1, r->threads);
+            std::vector<std::vector<uint64_t>> part(T);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+            for (int t = 0; t < T; t++) {
+                const char *lo = b + size * (uint64_t)t / T, *hi = b + size * (uint64_t)(t + 1) / T;
+                for (const char *q = lo; q < hi;) {
+                    q = (const char *)memchr(q, ch, hi - q);
+                    if (!q) break;
+                    part[t].push_back((uint64_t)(q - b));
+                    q++;
+                }
+            }
+            size_t total = 0;
+            std::vector<size_t> first(T + 1, 0);
+            for (int t = 0; t < T; t++) { total += part[t].size(); first[t + 1] = total; }
+            pos.resize(total);
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+            for (int t = 0; t < T; t++) std::copy(part[t].begin(), part[t].end(), pos.begin() + first[t]);
+        };
         if (*b == '>') { // FASTA (Dataset.cpp:270-281): header line, then everything up to the next '>'
+            std::vector<uint64_t> gt;
+            find_all('>', gt);
+            // a '>' inside a header line does not start a record: walk the candidates in order (cheap: one short memchr each)
+            size_t gi = 0;
             const char *p = b;
+            batch.reserve(gt.size());
             while (p < e) {
                 const char *nl = (const char *)memchr(p, '\n', e - p);
                 if (!nl) { batch.push_back(RawRec{e, 0, true}); break; } // header without sequence
                 const char *s = nl + 1;
-                const char *nx = (const char *)memchr(s, '>', e - s);
-                if (!nx) nx = e;
+                const uint64_t so = (uint64_t)(s - b);
+                while (gi < gt.size() && gt[gi] < so) gi++;
+                const char *nx = gi < gt.size() ? b + gt[gi] : e;
                 batch.push_back(RawRec{s, (uint64_t)(nx - s), true});
-                p = nx + (nx < e ? 1 : 0);
                 if (nx == e) break;
+                p = nx + 1;
             }
         } else if (*b == '@') { // FASTQ (Dataset.cpp:282-293): four lines per record, sequence on the second
-            const char *p = b;
-            auto next_line = [&](const char *&ls, const char *&le) { // std::getline semantics
-                if (p >= e) return false;
-                ls = p;
-                const char *nl = (const char *)memchr(p, '\n', e - p);
-                le = nl ? nl : e;
-                p = nl ? nl + 1 : e;
-                return true;
-            };
-            const char *ls, *le;
-            while (next_line(ls, le)) {
-                const char *ss = e, *se = e;
-                if (!next_line(ss, se)) { ss = se = e; }
-                const char *d0, *d1;
-                next_line(d0, d1);
-                next_line(d0, d1);
-                batch.push_back(RawRec{ss, (uint64_t)(se - ss), false});
+            std::vector<uint64_t> nl;
+            find_all('\n', nl);
+            // std::getline semantics: a last line without a newline still counts
+            const uint64_t lines = nl.size() + ((nl.empty() ? size > 0 : nl.back() + 1 < size) ? 1 : 0);
+            const uint64_t nrec = (lines + 3) / 4;
+            batch.resize(nrec);
+#pragma omp parallel for schedule(static) num_threads(r->threads)
+            for (uint64_t i = 0; i < nrec; i++) {
+                const uint64_t j = 4 * i + 1; // the sequence line
+                if (j >= lines) { batch[i] = RawRec{e, 0, false}; continue; }
+                const char *ss = b + nl[j - 1] + 1;
+                const char *se = j < nl.size() ? b + nl[j] : e;
+                batch[i] = RawRec{ss, (uint64_t)(se - ss), false};
             }
         } else {
             return fail("Unknown input file format."); // Dataset.cpp:267

@@ -78,6 +78,62 @@ def test_filter_edge_cases():
         assert host.test_read(s) == oracle.test_read(s), s
 
 
+def test_filter_fuzz_against_oracle():
+    """The host filter decides on the 2-bit packed read with popcounts; the oracle restates Dataset::testRead on strings.
+    Adversarial inputs: pattern repeats around the 50 % threshold (also straddling 32-base word boundaries), self-
+    overlapping x-y-x runs, ends equal or nearly equal to the 38 filter strings, one base around 70 %, lower case, N."""
+    import re
+    from oracle import oracle
+    rng = np.random.default_rng(123)
+    pats = ["AC", "AG", "AT", "CG", "CT", "GT", "AAT", "ATA", "TAA", "AAC", "ACA", "CAA", "AAG", "AGA", "GAA", "GGGGCC",
+            "A", "C", "G", "T", "ATATA", "ACAACA", "AGAGA", "TTC", "AATT"]
+    filt = re.findall(r'"([ACGT]{29})"', open(os.path.join(ROOT, "disco_b200", "host", "host.cpp")).read())
+    assert len(filt) == 38
+
+    def rand_seq(L, p=None):
+        return "".join(rng.choice(list("ACGT"), size=L, p=p))
+
+    def mutate(s, rate):
+        return "".join("ACGT"[rng.integers(4)] if rng.random() < rate else c for c in s)
+
+    cases = []
+    for _ in range(8000):
+        L = int(rng.integers(25, 330))
+        kind = int(rng.integers(0, 7))
+        if kind == 0:
+            s = rand_seq(L, rng.dirichlet([0.3] * 4))
+        elif kind == 1:
+            pat = pats[rng.integers(len(pats))]
+            rep = (pat * (L // len(pat) + 1))[:int(L * rng.uniform(0.3, 0.8))]
+            rest = rand_seq(L - len(rep))
+            cut = int(rng.integers(0, len(rest) + 1))
+            s = mutate(rest[:cut] + rep + rest[cut:], rng.choice([0, 0, 0.01, 0.03]))
+        elif kind == 2:
+            f = mutate(filt[rng.integers(38)], rng.choice([0, 0, 0.04]))
+            body = rand_seq(max(L - 29, 1))
+            s = f + body if rng.random() < 0.5 else body + f
+        elif kind == 3:
+            b, frac = "ACGT"[rng.integers(4)], rng.uniform(0.6, 0.8)
+            s = "".join(b if rng.random() < frac else "ACGT"[rng.integers(4)] for _ in range(L))
+        elif kind == 4:
+            p1, p2, k = pats[rng.integers(len(pats))], pats[rng.integers(len(pats))], int(rng.integers(0, L))
+            s = (p1 * L)[:k] + (p2 * L)[:L - k]
+        elif kind == 5:
+            s = rand_seq(L)
+            if rng.random() < 0.5:
+                s = s.lower()
+            if rng.random() < 0.3:
+                i = int(rng.integers(L))
+                s = s[:i] + "N" + s[i + 1:]
+        else:
+            s = (pats[rng.integers(len(pats))] * L)[:L]
+        cases.append(s)
+    got = [host.test_read(s) for s in cases]
+    want = [oracle.test_read(s.upper()) for s in cases]   # the reference upper-cases before testing (Dataset.cpp:303)
+    assert 0.1 < sum(want) / len(want) < 0.9               # both outcomes well represented
+    assert [s for s, a, b in zip(cases, got, want) if a != b] == []
+
+
 def _write(path, text, gz=False):
     if gz:
         with gzip.open(path, "wt") as f:
