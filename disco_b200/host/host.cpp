@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <omp.h>
+#include <parallel/algorithm>
 #include <string>
 #include <vector>
 #include <zlib.h>
@@ -480,7 +481,7 @@ int disco_host_sort_contained(disco_crow *rows, uint64_t n, const uint16_t *len,
 
 int disco_host_sort_edges(disco_edge *edges, uint64_t n)
 {
-    std::sort(edges, edges + n, [](const disco_edge &a, const disco_edge &b) {
+    __gnu_parallel::sort(edges, edges + n, [](const disco_edge &a, const disco_edge &b) {
         if (a.src != b.src) return a.src < b.src;
         if (a.dst != b.dst) return a.dst < b.dst;
         if (a.offset != b.offset) return a.offset < b.offset;
@@ -489,40 +490,94 @@ int disco_host_sort_edges(disco_edge *edges, uint64_t n)
     return 0;
 }
 
-int disco_write_pargraph(const char *path, const disco_edge *edges, uint64_t n, const uint64_t *file_index,
-                         const uint16_t *len, int flag, int append)
+} // extern "C"
+
+namespace {
+// decimal digits of v appended at p; returns the new end (the writers below format ~10^8 integers per graph)
+inline char *put_u64(char *p, uint64_t v)
+{
+    char tmp[20];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+inline char *put_str(char *p, const char *s) { while (*s) *p++ = *s++; return p; }
+
+// Format n lines with `line(i, p) -> new end` on all cores (each thread fills its own buffer, at most max_line bytes
+// per line), then write the buffers in order.
+template <typename Line>
+int write_lines(const char *path, int append, uint64_t n, size_t max_line, const Line &line)
 {
     FILE *f = fopen(path, append ? "a" : "w");
     if (!f) return fail(std::string("Unable to open file: ") + path);
-    std::vector<char> buf(1 << 22);
-    setvbuf(f, buf.data(), _IOFBF, buf.size());
-    for (uint64_t i = 0; i < n; i++) {
-        const disco_edge &e = edges[i];
-        const unsigned long long sl = len[e.src], dl = len[e.dst], off = e.offset, ovl = sl - off;
-        // src dst orient,ovl,0,0,srcLen,offset,srcLen-1,dstLen,0,ovl-1,NA,flag   (OverlapGraph.cpp:811-867)
-        fprintf(f, "%llu\t%llu\t%u,%llu,0,0,%llu,%llu,%llu,%llu,0,%llu,NA,%d\n", (unsigned long long)file_index[e.src],
-                (unsigned long long)file_index[e.dst], e.orient, ovl, sl, off, sl - 1, dl, ovl - 1, flag);
+    const uint64_t block = 1 << 16; // lines per buffer
+    const int T = std::max(1, omp_get_max_threads());
+    std::vector<std::vector<char>> buf(T);
+    std::vector<size_t> used(T, 0);
+    bool ok = true;
+    for (uint64_t base = 0; base < n && ok; base += block * (uint64_t)T) {
+#pragma omp parallel for schedule(static, 1) num_threads(T)
+        for (int t = 0; t < T; t++) {
+            const uint64_t lo = base + block * (uint64_t)t, hi = std::min<uint64_t>(n, lo + block);
+            used[t] = 0;
+            if (lo >= hi) continue;
+            if (buf[t].size() < (hi - lo) * max_line) buf[t].resize((hi - lo) * max_line);
+            char *p = buf[t].data();
+            for (uint64_t i = lo; i < hi; i++) p = line(i, p);
+            used[t] = (size_t)(p - buf[t].data());
+        }
+        for (int t = 0; t < T && ok; t++)
+            if (used[t]) ok = fwrite(buf[t].data(), 1, used[t], f) == used[t];
     }
-    fclose(f);
-    return 0;
+    if (fclose(f) != 0) ok = false;
+    return ok ? 0 : fail(std::string("write error in ") + path);
+}
+} // namespace
+
+extern "C" {
+
+int disco_write_pargraph(const char *path, const disco_edge *edges, uint64_t n, const uint64_t *file_index,
+                         const uint16_t *len, int flag, int append)
+{
+    // src dst orient,ovl,0,0,srcLen,offset,srcLen-1,dstLen,0,ovl-1,NA,flag   (OverlapGraph.cpp:811-867)
+    return write_lines(path, append, n, 160, [&](uint64_t i, char *p) {
+        const disco_edge &e = edges[i];
+        const uint64_t sl = len[e.src], dl = len[e.dst], off = e.offset, ovl = sl - off;
+        p = put_u64(p, file_index[e.src]); *p++ = '\t';
+        p = put_u64(p, file_index[e.dst]); *p++ = '\t';
+        p = put_u64(p, e.orient); *p++ = ',';
+        p = put_u64(p, ovl); p = put_str(p, ",0,0,");
+        p = put_u64(p, sl); *p++ = ',';
+        p = put_u64(p, off); *p++ = ',';
+        p = put_u64(p, sl - 1); *p++ = ',';
+        p = put_u64(p, dl); p = put_str(p, ",0,");
+        p = put_u64(p, ovl - 1); p = put_str(p, ",NA,");
+        if (flag < 0) { *p++ = '-'; p = put_u64(p, (uint64_t)(-(long long)flag)); } else p = put_u64(p, (uint64_t)flag);
+        *p++ = '\n';
+        return p;
+    });
 }
 
 int disco_write_contained(const char *path, const disco_crow *rows, uint64_t n, const uint64_t *file_index,
                           const uint16_t *len, int append)
 {
-    FILE *f = fopen(path, append ? "a" : "w");
-    if (!f) return fail(std::string("Unable to open file: ") + path);
-    std::vector<char> buf(1 << 22);
-    setvbuf(f, buf.data(), _IOFBF, buf.size());
-    for (uint64_t i = 0; i < n; i++) {
+    // contained container orient,L2,0,0,L2,0,L2,L1,start,start+L2   (OverlapGraph.cpp:438-447)
+    return write_lines(path, append, n, 160, [&](uint64_t i, char *p) {
         const disco_crow &r = rows[i];
-        const unsigned long long l2 = len[r.contained], l1 = len[r.container], st = r.start;
-        // contained container orient,L2,0,0,L2,0,L2,L1,start,start+L2   (OverlapGraph.cpp:438-447)
-        fprintf(f, "%llu\t%llu\t%u,%llu,0,0,%llu,0,%llu,%llu,%llu,%llu\n", (unsigned long long)file_index[r.contained],
-                (unsigned long long)file_index[r.container], r.orient, l2, l2, l2, l1, st, st + l2);
-    }
-    fclose(f);
-    return 0;
+        const uint64_t l2 = len[r.contained], l1 = len[r.container], st = r.start;
+        p = put_u64(p, file_index[r.contained]); *p++ = '\t';
+        p = put_u64(p, file_index[r.container]); *p++ = '\t';
+        p = put_u64(p, r.orient); *p++ = ',';
+        p = put_u64(p, l2); p = put_str(p, ",0,0,");
+        p = put_u64(p, l2); p = put_str(p, ",0,");
+        p = put_u64(p, l2); *p++ = ',';
+        p = put_u64(p, l1); *p++ = ',';
+        p = put_u64(p, st); *p++ = ',';
+        p = put_u64(p, st + l2);
+        *p++ = '\n';
+        return p;
+    });
 }
 
 } // extern "C"

@@ -201,3 +201,40 @@ def test_writers_match_reference_format(tmp_path):
     host.write_contained(cr, rows, np.array(fi), lens)
     assert [l.rstrip("\n") for l in open(pg)] == [l + ",2" for l in g["ref_edges"]]
     assert [l.rstrip("\n") for l in open(cr)] == g["ref_crows"]
+
+
+def test_writers_many_lines_and_append(tmp_path):
+    """the writers format blocks of lines on all cores: more lines than one round of blocks, order kept, append works"""
+    rng = np.random.default_rng(5)
+    n, ne = 50_000, 1_200_000
+    fi = np.cumsum(rng.integers(1, 4, n)).astype(np.uint64)
+    lens = rng.integers(60, 300, n).astype(np.uint16)
+    e = np.zeros(ne, dtype=gpu.EDGE_DTYPE)
+    e["src"] = rng.integers(0, n - 1, ne)
+    e["dst"] = rng.integers(0, n, ne)
+    e["offset"] = rng.integers(1, 59, ne)
+    e["orient"] = rng.integers(0, 4, ne)
+    path = str(tmp_path / "pg.txt")
+    host.write_pargraph(path, e[:1_000_000], fi, lens, flag=2)
+    host.write_pargraph(path, e[1_000_000:], fi, lens, flag=1, append=True)
+    lines = open(path).read().split("\n")
+    assert lines[-1] == "" and len(lines) == ne + 1
+    for k in list(rng.integers(0, ne, 2000)) + [0, 65535, 65536, 999_999, 1_000_000, ne - 1]:
+        s, d, off, o = (int(e[k][f]) for f in ("src", "dst", "offset", "orient"))
+        sl, dl = int(lens[s]), int(lens[d])
+        ovl = sl - off
+        assert lines[k] == f"{fi[s]}\t{fi[d]}\t{o},{ovl},0,0,{sl},{off},{sl - 1},{dl},0,{ovl - 1},NA,{2 if k < 1_000_000 else 1}"
+    r = np.zeros(200_000, dtype=gpu.CROW_DTYPE)
+    r["contained"] = rng.integers(0, n, len(r)); r["container"] = rng.integers(0, n, len(r))
+    r["orient"] = rng.integers(0, 4, len(r)); r["start"] = rng.integers(0, 50, len(r))
+    cpath = str(tmp_path / "cr.txt")
+    host.write_contained(cpath, r, fi, lens)
+    cl = open(cpath).read().split("\n")
+    assert len(cl) == len(r) + 1
+    for k in list(rng.integers(0, len(r), 1000)) + [0, len(r) - 1]:
+        a, b, o, st = (int(r[k][f]) for f in ("contained", "container", "orient", "start"))
+        l2, l1 = int(lens[a]), int(lens[b])
+        assert cl[k] == f"{fi[a]}\t{fi[b]}\t{o},{l2},0,0,{l2},0,{l2},{l1},{st},{st + l2}"
+    e2 = e.copy()
+    host.sort_edges(e2)
+    assert np.array_equal(e2, gpu.sort_edges(e))
