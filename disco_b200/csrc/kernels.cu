@@ -1,15 +1,21 @@
 // kernels.cu -- hand-written sm_100a kernels of the BuildGraph hot path.  Integer / bit work only (hashing, 2-bit
-// compares, neighbour-list marking): bound by random 32-byte HBM sectors, not by math, so no tensor cores.
+// compares, neighbour-list marking): bound by random 32/64-byte HBM accesses and issued instructions, not by math, so
+// no tensor cores.
 //
-//   k_table_insert     HashTable::insertIntoTable  (HashTable.cpp:423-514)   2 records per read, quad-cooperative CAS
-//   k_search<CONTAIN>  markContainedReads          (OverlapGraph.cpp:333-505) + checkOverlapForContainedRead (:517)
-//   k_search<EDGES>    insertAllEdgesOfRead        (OverlapGraph.cpp:631-678) + checkOverlap (:567)
-//   k_reduce_mark      markTransitiveEdges         (OverlapGraph.cpp:687-723)
-//   k_reduce_emit      removeTransitiveEdges + canonical src<dst selection (OverlapGraph.cpp:731-761, :808)
+//   k_table_insert_lanes / k_table_insert   HashTable::insertIntoTable (HashTable.cpp:423-514): two records per read,
+//                                           quad-cooperative CAS; key-sharded mode inserts only this GPU's keys
+//   k_contain_uniform / k_search<CONTAIN>   markContainedReads (OverlapGraph.cpp:333-505) + checkOverlapForContainedRead (:517)
+//   k_edges_probe -> k_edges_verify -> k_edges_exact
+//                                           insertAllEdgesOfRead (OverlapGraph.cpp:631-678) + checkOverlap (:567);
+//                                           k_search<EDGES> is the older fused variant (DISCO_FUSED=1)
+//   k_reduce_mark                           markTransitiveEdges (OverlapGraph.cpp:687-723)
+//   k_reduce_emit                           removeTransitiveEdges + canonical src<dst selection (:731-761, :808)
+//   k_min_keys, k_revcomp_rows, k_restride, k_rebase_rowinfo, k_contained_finish/rows   small helpers
 //
-// Common shape: one warp per read, the read (forward + reverse complement) staged in shared memory, one lane per
-// k-mer position so that a warp keeps 32 independent table sectors in flight; reads are handed out in chunks through
-// an atomic work counter (persistent grid sized from the SM count).
+// Common shape: one warp (or a 16-lane half of one) per read, the read (forward + reverse complement) staged in shared
+// memory, one lane per k-mer position / per candidate so that a warp keeps 32 independent sectors in flight; reads are
+// handed out in chunks through an atomic work counter (persistent grid sized from the SM count).  <SHARDED> variants
+// read table buckets / adjacency rows of other GPUs through NVLink peer pointers.
 #include "dna.cuh"
 #include "kernels.cuh"
 #include <cstdlib>
