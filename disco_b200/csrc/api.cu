@@ -282,6 +282,13 @@ void disco_gpu_destroy(disco_ctx *ctx)
     delete ctx;
 }
 
+int disco_gpu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 const char *disco_gpu_last_error(const disco_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int disco_gpu_set_stream(disco_ctx *ctx, void *cuda_stream)

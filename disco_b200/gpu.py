@@ -22,7 +22,7 @@ EXPORTS = [
     "disco_gpu_set_rows_used", "disco_gpu_use_rows", "disco_gpu_phase_edges_part", "disco_gpu_phase_reduce_mark",
     "disco_gpu_phase_reduce_emit", "disco_gpu_set_shard", "disco_gpu_export_mem", "disco_gpu_import_peers",
     "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table", "disco_gpu_table_words", "disco_gpu_adopt_buffer",
-    "disco_gpu_build_graph_multi",
+    "disco_gpu_build_graph_multi", "disco_gpu_device_count",
 ]
 MAX_SHARDS, IPC_HANDLE_BYTES, MEM_TABLE, MEM_ROWS = 8, 64, 0, 1
 
@@ -87,6 +87,7 @@ def lib():
         L.disco_gpu_table_words.restype = u64
         L.disco_gpu_adopt_buffer.argtypes = [vp, i32, vp, u64]
         L.disco_gpu_build_graph_multi.argtypes = [vp, u32, u32, u32]
+        L.disco_gpu_device_count.argtypes = []
         for f in ("disco_gpu_dev_contained_keys", "disco_gpu_dev_rowinfo"):
             getattr(L, f).argtypes = [vp]
             getattr(L, f).restype = vp
@@ -285,6 +286,10 @@ class GpuBuildGraph:
         s = Stats()
         self._ck(self._L.disco_gpu_get_stats(self._h, C.byref(s)), "get_stats")
         return s.as_dict()
+
+
+def device_count() -> int:
+    return lib().disco_gpu_device_count()
 
 
 def build_graph_multi(graphs, min_overlap: int, max_edge_per_kmer: int = 4):

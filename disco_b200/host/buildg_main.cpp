@@ -2,7 +2,7 @@
 // same options, same config key, same input formats, same output files; the stage itself runs on a B200 through the
 // C ABI of include/disco_gpu.h.
 //
-//   buildG [-pe f1,f2,...] [-se f1,...] -f <prefix> -p <cfg> [-t <threads/shards>] [-m <GB>] [-w <n>] [-g <gpu>[,<gpu>...]]
+//   buildG [-pe f1,f2,...] [-se f1,...] -f <prefix> -p <cfg> [-t <threads/shards>] [-m <GB>] [-w <n>] [-g <gpu>[,<gpu>...] | all]
 //
 // Mirrors: parseArguments (main.cpp:79-150: unknown option -> usage + exit 1; no args / -h -> usage + exit 0),
 // readOverlapParameter (main.cpp:152-176: MinOverlap4BuildGraph, default 30, missing file -> exit 1),
@@ -53,7 +53,7 @@ static void usage()
     cerr << "  -f\tAll file name prefix" << endl;
     cerr << "  -t\tmaximum threads used (= number of output shards)" << endl;
     cerr << "  -m\tmaximum memory usage allowed (accepted for compatibility)" << endl;
-    cerr << "  -g\tCUDA device(s) to run on, comma separated (default 0 or $DISCO_GPUS)" << endl;
+    cerr << "  -g\tCUDA device(s) to run on, comma separated, or 'all' (default 0 or $DISCO_GPUS)" << endl;
 }
 
 [[noreturn]] static void die(const string &msg)
@@ -157,7 +157,13 @@ int main(int argc, char **argv)
     // ---- hot path on the GPU(s)
     t0 = now();
     vector<int> devs;
-    for (auto &d : split_tok(devices, ',')) if (!trimmed(d).empty()) devs.push_back(atoi(trimmed(d).c_str()));
+    if (trimmed(devices) == "all") {
+        const int nd = disco_gpu_device_count();
+        if (nd < 1) die("no CUDA device");
+        for (int d = 0; d < nd && d < DISCO_MAX_SHARDS; d++) devs.push_back(d);
+    } else {
+        for (auto &d : split_tok(devices, ',')) if (!trimmed(d).empty()) devs.push_back(atoi(trimmed(d).c_str()));
+    }
     if (devs.empty()) devs.push_back(0);
     if (devs.size() > DISCO_MAX_SHARDS) die("at most " + to_string(DISCO_MAX_SHARDS) + " GPUs");
     vector<disco_ctx *> ctxs(devs.size(), nullptr);

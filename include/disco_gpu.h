@@ -76,6 +76,8 @@ typedef struct {
                                                              * whatever the caller did between the phases) */
 } disco_stats;
 
+/* number of CUDA devices this process can use (0 when there is none or the driver is missing); `buildG -g all` */
+int disco_gpu_device_count(void);
 /* ---- life cycle ---------------------------------------------------------------------------------------------- */
 int disco_gpu_create(disco_ctx **out, int device);
 void disco_gpu_destroy(disco_ctx *ctx);

@@ -79,5 +79,10 @@ def test_several_gpus_in_one_process(tmp_path, name):
     assert edges == sorted(l + ",2" for l in g["ref_edges"])
     rows = [l.rstrip("\n") for t in range(2) for l in open(f"{prefix}_{t}_containedReads.txt")]
     assert rows == g["ref_crows"]
+    # -g all: every visible device
+    prefix2 = str(tmp_path / "graph" / "all")
+    r = _run(["-pe" if "paired" in name else "-se", str(fa), "-f", prefix2, "-p", str(cfg), "-g", "all"])
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert sorted(l.rstrip("\n") for l in open(f"{prefix2}_0_parGraph.txt")) == edges
     r = _run(["-se", str(fa), "-f", str(tmp_path / "x"), "-p", str(cfg), "-g", "0,1,2,3,4,5,6,7,8"])
     assert r.returncode == 1 and "at most 8 GPUs" in r.stdout
