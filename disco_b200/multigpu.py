@@ -206,7 +206,7 @@ class KeyShardedBuildGraph:
     What the host exchanges: the IPC handles (64 bytes per rank, once per allocation), the two all-reduces, and the
     barriers that order the phases across ranks."""
 
-    def __init__(self, g, rank: int, world: int, group=None, tensors=None, symmetric=None):
+    def __init__(self, g, rank: int, world: int, group=None, tensors=None, symmetric=None, alloc=None):
         """symmetric: allocate the table shards and the adjacency as torch symmetric memory (CUDA VMM allocations with
         2 MB pages, mapped into every peer at rendezvous) instead of exporting the library's cudaMalloc buffers through
         legacy CUDA IPC handles.  Measured on B200: through legacy IPC mappings, random remote reads collapse (8x
@@ -221,14 +221,19 @@ class KeyShardedBuildGraph:
         if symmetric is None:
             symmetric = os.environ.get("DISCO_SYMM", "1") != "0" and self.t.device.type == "cuda"
         self.symmetric = symmetric
-        self._symm = {}                      # which -> (tensor, peer pointers)
+        self.alloc = alloc                   # (n_u64) -> (int64 tensor, [peer pointers]); default: torch symmetric memory
+        self._symm = {}                      # which -> (tensor, peer pointers, handle)
         g.set_shard(world, rank)
 
     def _symm_buffer(self, which, n_u64):
         """Symmetric int64 buffer of n_u64 words for `which`, (re)allocated collectively when the size changes."""
-        import torch.distributed._symmetric_memory as symm
         cur = self._symm.get(which)
+        if (cur is None or cur[0].numel() != n_u64) and self.alloc is not None:
+            t, ptrs = self.alloc(n_u64)
+            cur = (t, [int(p) for p in ptrs], None)
+            self._symm[which] = cur
         if cur is None or cur[0].numel() != n_u64:
+            import torch.distributed._symmetric_memory as symm
             self._symm.pop(which, None)
             t = symm.empty(n_u64, dtype=torch.int64, device=self.t.device)
             grp = self.group if self.group is not None else dist.group.WORLD

@@ -190,3 +190,72 @@ def test_key_sharded_driver_gloo(world):
             handles, bounds = imported[which]
             assert handles == [bytes([which, r]) + bytes(62) for r in range(world)]   # rank order, every rank's handle
         assert list(imported[1][1]) == [p[0] for p in parts] + [N] and imported[0][1] is None
+
+
+# ---- Mode B with caller-provided (symmetric) buffers: adopt + collective retry when one rank's adjacency overflows ----
+class FakeSymmCtx(FakeShardCtx):
+    """phase_edges fails with the library's 'too small' error until the adopted buffer reaches `need` entries"""
+    class Err(RuntimeError):
+        pass
+
+    def __init__(self, rank, world, need):
+        super().__init__(rank, world)
+        self.need, self.table_ptr, self.rows_ptr, self.rows_cap, self.attempts = need, 0, 0, 0, 0
+    def table_words(self): return 4096
+    def dev_table(self): return self.table_ptr
+    def dev_rows(self): return (self.rows_ptr, 0)
+    def adopt_buffer(self, which, ptr, n):
+        self.log.append(f"adopt{which}")
+        if which == 0: self.table_ptr = ptr
+        else: self.rows_ptr, self.rows_cap = ptr, n
+    def import_peer_ptrs(self, which, ptrs, bounds=None):
+        self.log.append(f"import{which}")
+        self.imported = getattr(self, "imported", {})
+        self.imported[which] = (list(ptrs), bounds)
+    def phase_edges(self, lo, hi):
+        self.attempts += 1
+        if self.rows_cap < self.need:
+            raise FakeSymmCtx.Err("adopted adjacency buffer too small: %d entries needed, %d given" % (self.need, self.rows_cap))
+        super().phase_edges(lo, hi)
+
+
+def _worker_symm(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    from disco_b200 import multigpu
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    base_cap = ((N + world - 1) // world) * 48 + (16 << 20)
+    need = base_cap + 1 if rank == world - 1 else 1000        # only the last rank overflows the first buffer
+    g = FakeSymmCtx(rank, world, need)
+    allocs = []
+
+    def alloc(n):      # stands in for symmetric memory: a tensor and "peer pointers" every rank agrees on
+        allocs.append(n)
+        t = torch.zeros(1, dtype=torch.int64).expand(n)       # numel() == n without the memory
+        return t, [1000 * len(allocs) + r for r in range(world)]
+    drv = multigpu.KeyShardedBuildGraph(g, rank, world, tensors=FakeTensors(g), symmetric=True, alloc=alloc)
+    drv.DiscoError = FakeSymmCtx.Err
+    drv.build_graph(50, 4)
+    q.put((rank, g.attempts, allocs, g.log, g.imported, drv._rows_cap, base_cap))
+    dist.destroy_process_group()
+
+
+def test_key_sharded_symmetric_retry_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker_symm, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, attempts, allocs, log, imported, cap, base_cap in res:
+        assert attempts == 2                                   # every rank repeats the pass, not only the one that overflowed
+        assert allocs == [4096, base_cap, base_cap * 3 // 2] and cap == base_cap * 3 // 2
+        assert log.count("adopt0") == 1 and log.count("adopt1") == 2
+        assert imported[0][0] == [1000 + r for r in range(world)]          # table: first allocation
+        assert imported[1][0] == [3000 + r for r in range(world)]          # adjacency: the buffer that was large enough
+        assert [x for x in log if x in ("mark", "emit")] == ["mark", "emit"]
