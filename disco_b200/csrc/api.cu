@@ -21,7 +21,7 @@ using namespace disco;
 namespace {
 thread_local std::string g_create_error;
 
-enum Cursor { CUR_WORK = 0, CUR_WORK2, CUR_WORK3, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_COUNT };
+enum Cursor { CUR_WORK = 0, CUR_WORK2, CUR_WORK3, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_CANDS, CUR_TABLE_FULL, CUR_COUNT };
 enum Ev { EV_T0 = 0, EV_TABLE_ALL, EV_CONTAINED, EV_FINISH, EV_TABLE_NC, EV_EDGES, EV_MARK, EV_EMIT, EV_EDGES_K0, EV_EDGES_K1,
           EV_CONT_K0, EV_CONT_K1, EV_PROBE_K1, EV_VERIFY_K1, EV_MARK_K0, EV_EMIT_K0, EV_COUNT };
 } // namespace
@@ -61,6 +61,12 @@ struct disco_ctx {
     uint64_t *d_rows = nullptr;        // owned
     uint64_t *d_rows_active = nullptr; // what the reduction reads: d_rows, or a caller-owned gathered buffer (use_rows)
     uint64_t rows_cap = 0, rows_used = 0; // rows_used = cursor (includes warp-slice slack)
+    // flat edge pass: the batches' candidate lists (probe -> verify), internal to one launch
+    uint64_t *d_cands = nullptr;
+    uint64_t cands_cap = 0;
+    uint64_t *d_batchinfo = nullptr;
+    uint64_t batch_cap = 0; // batches d_batchinfo holds
+    unsigned long long launches_at_begin = 0;
     // output
     disco_edge *d_edges = nullptr;
     uint64_t edges_cap = 0, n_edges = 0;
@@ -131,9 +137,9 @@ void free_run_buffers(disco_ctx *c)
     c->own_slots = c->own_rows = true;
     c->peer_table.ready = c->peer_rows.ready = false; // whatever the peers mapped is gone
     dfree(c->d_filter); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
-    dfree(c->d_rowinfo); dfree(c->d_edges);
+    dfree(c->d_rowinfo); dfree(c->d_edges); dfree(c->d_cands); dfree(c->d_batchinfo);
     c->d_rows_active = nullptr;
-    c->rows_cap = c->edges_cap = c->crows_cap = c->run_n = 0;
+    c->rows_cap = c->edges_cap = c->crows_cap = c->run_n = c->cands_cap = c->batch_cap = 0;
     c->begun = c->have_contained = c->have_edges = c->have_reduced = false;
 }
 
@@ -159,6 +165,7 @@ TableView table_view(const disco_ctx *c)
     tv.slots = c->d_slots; tv.nbuckets = c->nbuckets; tv.filter = c->d_filter;
     tv.filter_mask = (uint32_t)(c->filter_bits ? c->filter_bits - 1 : 0);
     tv.peers = c->peer_table.d_ptrs; tv.world = c->shard_world; tv.rank = c->shard_rank;
+    tv.full = reinterpret_cast<unsigned int *>(c->d_cursors + CUR_TABLE_FULL);
     return tv;
 }
 
@@ -377,6 +384,7 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
     CK(cudaMemsetAsync(ctx->d_stats_c, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_stats_e, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
     ctx->stats = disco_stats{};
+    ctx->launches_at_begin = launches_total();
     ctx->stats.n_reads = n;
     ctx->stats.table_buckets = ctx->nbuckets * ctx->shard_world;
     for (auto &d : ctx->ev_done) d = false;
@@ -425,9 +433,11 @@ int disco_gpu_phase_finish_contained(disco_ctx *ctx)
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_cursors + CUR_NCONTAINED, 0, 2 * sizeof(unsigned long long), ctx->stream)); // + CUR_CROWS
     CK(launch_contained_finish(ctx->d_best, ctx->reads.n, ctx->d_bits, ctx->d_cursors + CUR_NCONTAINED, ctx->stream));
-    unsigned long long nc = 0;
+    unsigned long long nc = 0, full = 0;
     CK(cudaMemcpyAsync(&nc, ctx->d_cursors + CUR_NCONTAINED, sizeof nc, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&full, ctx->d_cursors + CUR_TABLE_FULL, sizeof full, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (full) return fail(ctx, DISCO_E_LIMIT, "hash table%s full: %llu buckets cannot hold this rank's keys (skewed k-mers)", ctx->shard_world > 1 ? " shard" : "", (unsigned long long)ctx->nbuckets);
     ctx->n_contained = nc;
     if (nc > ctx->crows_cap) {
         dfree(ctx->d_crows);
@@ -473,6 +483,31 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
         ctx->rows_cap = want;
     }
     ctx->d_rows_active = ctx->d_rows;
+    // flat kernels (short reads): candidate lists of this launch + four segment words per 32-read batch
+    const bool flat = edges_flat_supported(ctx->reads.max_len, ctx->reads.stride, ctx->K);
+    if (flat) {
+        const uint64_t nb = (np + 31) / 32;
+        if (nb > ctx->batch_cap) {
+            dfree(ctx->d_batchinfo);
+            ctx->batch_cap = 0;
+            CK(cudaMalloc(&ctx->d_batchinfo, std::max<uint64_t>(nb, 1) * 4 * sizeof(uint64_t)));
+            ctx->batch_cap = nb;
+        }
+        const uint64_t slack = std::min<uint64_t>(edges_flat_slack(ctx->num_sms), nb * 8192) + 8192;
+        const uint64_t want = std::max<uint64_t>((np + 1024) * 48, 1 << 16) + slack;
+        if (ctx->cands_cap < want) { // (a buffer a retry has grown is kept; parts of one pass differ by a read at most)
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const uint64_t lim = (uint64_t)((free_b + ctx->cands_cap * sizeof(uint64_t)) * 0.5) / sizeof(uint64_t);
+            const uint64_t take = std::min(want, std::max<uint64_t>(lim, 1 << 16));
+            if (take > ctx->cands_cap) {
+                dfree(ctx->d_cands);
+                ctx->cands_cap = 0;
+                CK(cudaMalloc(&ctx->d_cands, take * sizeof(uint64_t)));
+                ctx->cands_cap = take;
+            }
+        }
+    }
     const uint64_t cursor_before = first ? 0 : ctx->rows_used;
     unsigned long long st_before[ST_COUNT] = {};
     if (!first) {
@@ -481,26 +516,30 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
     }
     for (int attempt = 0;; attempt++) {
         CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, 3 * sizeof(unsigned long long), ctx->stream)); // 3 work counters
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_CANDS, 0, sizeof(unsigned long long), ctx->stream));
         const unsigned long long cb = cursor_before;
         CK(cudaMemcpyAsync(ctx->d_cursors + CUR_ROWS, &cb, sizeof cb, cudaMemcpyHostToDevice, ctx->stream));
         if (first) CK(cudaMemsetAsync(ctx->d_stats_e, 0, ST_COUNT * sizeof(unsigned long long), ctx->stream));
         else if (attempt) CK(cudaMemcpyAsync(ctx->d_stats_e, st_before, sizeof st_before, cudaMemcpyHostToDevice, ctx->stream));
         if (attempt) CK(cudaMemsetAsync(ctx->d_rowinfo + part_lo, 0, np * sizeof(uint64_t), ctx->stream));
         p.rows = ctx->d_rows; p.rows_cap = ctx->rows_cap;
+        p.cands = flat ? ctx->d_cands : nullptr; p.cands_cap = ctx->cands_cap;
+        p.cands_cursor = ctx->d_cursors + CUR_CANDS; p.batchinfo = ctx->d_batchinfo;
         { int rc = record(ctx, EV_EDGES_K0); if (rc) return rc; }
         if (np) {
             CK(launch_search_edges(p, ctx->num_sms, ctx->stream, ctx->ev[EV_PROBE_K1], ctx->ev[EV_VERIFY_K1]));
             ctx->ev_done[EV_PROBE_K1] = ctx->ev_done[EV_VERIFY_K1] = !getenv("DISCO_FUSED");
         }
         { int rc = record(ctx, EV_EDGES_K1); if (rc) return rc; }
-        unsigned long long cur[2] = {0, 0}, st[ST_COUNT];
-        CK(cudaMemcpyAsync(cur, ctx->d_cursors + CUR_WORK3, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream)); // [1] = CUR_ROWS
+        unsigned long long cur[CUR_COUNT] = {}, st[ST_COUNT];
+        CK(cudaMemcpyAsync(cur, ctx->d_cursors, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(st, ctx->d_stats_e, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
+        if (cur[CUR_TABLE_FULL]) return fail(ctx, DISCO_E_LIMIT, "hash table%s full: %llu buckets cannot hold this rank's keys (skewed k-mers)", ctx->shard_world > 1 ? " shard" : "", (unsigned long long)ctx->nbuckets);
         ctx->stats.raw_directed_edges = st[ST_ENTRIES];
         ctx->stats.max_degree = st[ST_MAXDEG];
         if (!st[ST_OVERFLOW]) {
-            ctx->rows_used = cur[1];
+            ctx->rows_used = cur[CUR_ROWS];
             if (first) ctx->acc_probe = ctx->acc_verify = ctx->acc_exact = ctx->acc_edges = 0.f;
             float t = 0.f;
             if (cudaEventElapsedTime(&t, ctx->ev[EV_EDGES_K0], ctx->ev[EV_EDGES_K1]) == cudaSuccess) ctx->acc_edges += t;
@@ -511,19 +550,28 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
             }
             break;
         }
-        if (attempt >= 2) return fail(ctx, DISCO_E_NOMEM, "adjacency buffer overflow after retry (%llu entries needed)", cur[1]);
-        if (!ctx->own_rows) return fail(ctx, DISCO_E_NOMEM, "adopted adjacency buffer too small: %llu entries needed, %llu given", cur[1], (unsigned long long)ctx->rows_cap);
-        // grow (keeping earlier parts) and redo this part.  Slices are handed out per warp, so the slack differs between
-        // runs: add one slice per resident warp; scale for the parts still to come
-        uint64_t need = cur[1] + (uint64_t)ctx->num_sms * 64 * 1024;
-        if (np && np < nq) need += (cur[1] - cursor_before) * ((q_hi - part_hi) / np + 1);
-        uint64_t *nr = nullptr;
-        CK(cudaMalloc(&nr, need * sizeof(uint64_t)));
-        if (cursor_before) CK(cudaMemcpyAsync(nr, ctx->d_rows, cursor_before * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        dfree(ctx->d_rows);
-        ctx->d_rows = ctx->d_rows_active = nr;
-        ctx->rows_cap = need;
+        if (attempt >= 3) return fail(ctx, DISCO_E_NOMEM, "edge pass buffers overflow after retries (%llu adjacency entries, %llu candidates needed)", cur[CUR_ROWS], cur[CUR_CANDS]);
+        if (st[ST_OVERFLOW] & 2) { // candidate lists: nothing to keep, the cursor says what this part needs
+            const uint64_t need = cur[CUR_CANDS] + edges_flat_slack(ctx->num_sms);
+            dfree(ctx->d_cands);
+            ctx->cands_cap = 0;
+            CK(cudaMalloc(&ctx->d_cands, need * sizeof(uint64_t)));
+            ctx->cands_cap = need;
+        }
+        if (st[ST_OVERFLOW] & 1) {
+            if (!ctx->own_rows) return fail(ctx, DISCO_E_NOMEM, "adopted adjacency buffer too small: %llu entries needed, %llu given", cur[CUR_ROWS], (unsigned long long)ctx->rows_cap);
+            // grow (keeping earlier parts) and redo this part.  Slices are handed out per warp, so the slack differs between
+            // runs: add one slice per resident warp; scale for the parts still to come
+            uint64_t need = cur[CUR_ROWS] + (uint64_t)ctx->num_sms * 64 * 1024;
+            if (np && np < nq) need += (cur[CUR_ROWS] - cursor_before) * ((q_hi - part_hi) / np + 1);
+            uint64_t *nr = nullptr;
+            CK(cudaMalloc(&nr, need * sizeof(uint64_t)));
+            if (cursor_before) CK(cudaMemcpyAsync(nr, ctx->d_rows, cursor_before * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            dfree(ctx->d_rows);
+            ctx->d_rows = ctx->d_rows_active = nr;
+            ctx->rows_cap = need;
+        }
         if (!first) st_before[ST_OVERFLOW] = 0;
     }
     ctx->stats.edge_capacity = ctx->rows_cap;
@@ -579,6 +627,8 @@ int disco_gpu_phase_reduce_emit(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
     for (int attempt = 0;; attempt++) {
         CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_cursors + CUR_EDGES, 0, sizeof(unsigned long long), ctx->stream));
+        // the emission kernel's own counters: zeroed per attempt, so that a retry after an edge-buffer overflow counts once
+        CK(cudaMemsetAsync(ctx->d_stats_e + ST_MULTI_OVERLAP, 0, (ST_COUNT - ST_MULTI_OVERLAP) * sizeof(unsigned long long), ctx->stream));
         p.edges_out = ctx->d_edges; p.edges_cap = ctx->edges_cap; p.edges_cursor = ctx->d_cursors + CUR_EDGES;
         if ((rc = record(ctx, EV_EMIT_K0))) return rc;
         if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_emit(p, ctx->num_sms, ctx->stream));
@@ -942,7 +992,8 @@ int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out)
     s.queries_contained = sc[ST_QUERIES]; s.queries_edges = se[ST_QUERIES];
     s.cap_fired = se[ST_CAP_FIRED]; s.slow_path_reads = se[ST_SLOW_READS];
     s.multi_overlap_pairs = se[ST_MULTI_OVERLAP]; s.one_sided_edges = se[ST_ONE_SIDED];
-    s.reduce_rows_fetched = se[ST_ROWS_FETCHED]; s.reduce_entries_fetched = se[ST_ENTRIES_FETCHED];
+    s.reduce_rows_fetched = se[ST_ROWS_FETCHED] + se[ST_EMIT_ROWS]; s.reduce_entries_fetched = se[ST_ENTRIES_FETCHED] + se[ST_EMIT_ENTRIES];
+    s.kernel_launches = launches_total() - ctx->launches_at_begin;
     auto ms = [&](int a, int b) {
         float t = 0.f;
         if (ctx->ev_done[a] && ctx->ev_done[b]) cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);

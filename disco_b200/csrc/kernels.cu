@@ -18,6 +18,7 @@
 // read table buckets / adjacency rows of other GPUs through NVLink peer pointers.
 #include "dna.cuh"
 #include "kernels.cuh"
+#include <atomic>
 #include <cstdlib>
 #include "../../include/disco_gpu.h"
 
@@ -94,6 +95,14 @@ __device__ __forceinline__ bool filter_test(const TableView &t, uint64_t h, uint
     uint32_t w;
     asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(w) : "l"(t.filter + (bit >> 5)), "l"(pol));
     return (w >> (bit & 31)) & 1;
+}
+
+// the same without a cache hint (measured, profiles/filter_bench.cu: evict_last / a persisting window change nothing)
+__device__ __forceinline__ bool filter_test(const TableView &t, uint64_t h)
+{
+    if (!t.filter) return true;
+    const uint32_t bit = (uint32_t)(h >> 13) & t.filter_mask;
+    return (__ldg(t.filter + (bit >> 5)) >> (bit & 31)) & 1;
 }
 
 // candidate read held in registers: NW = words loaded (even, >= words of the longest read); the row stride in memory
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
             }
             const bool mine = !(tv.world > 1 && shard_of(tv, h) != tv.rank); // else another GPU's key (uniform within the quad)
             uint64_t b = shard_bucket(tv, h);
-            while (mine) {
+            for (uint64_t walked = 0; mine; ) {
                 unsigned long long *slot = reinterpret_cast<unsigned long long *>(tv.slots) + 4 * b + sub;
                 const uint64_t cur = __ldcg(slot); // L2 (coherent) read: slots change under our feet
                 const unsigned empties = (__ballot_sync(qmask, cur == kEmptySlot) >> (quad * 4)) & 0xFu;
@@ -301,6 +310,7 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
                     ok = __shfl_sync(qmask, ok, quad * 4 + first);
                     if (ok) break; // otherwise somebody else took it: vote again on the same bucket
                 } else {
+                    if (++walked == tv.nbuckets) { if (sub == 0) atomicExch(tv.full, 1u); break; } // (shard) full: reported, not spun on
                     b = (b + 1 == tv.nbuckets) ? 0 : b + 1;
                 }
             }
@@ -373,7 +383,7 @@ __global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, T
             if (!ok_rec) continue; // uniform within the quad
             if (tv.world > 1 && shard_of(tv, hh) != tv.rank) continue; // another GPU's key
             uint64_t b = shard_bucket(tv, hh);
-            for (;;) {
+            for (uint64_t walked = 0;;) {
                 unsigned long long *slot = reinterpret_cast<unsigned long long *>(tv.slots) + 4 * b + sub;
                 const uint64_t cur = __ldcg(slot); // L2 (coherent) read: slots change under our feet
                 const unsigned empties = (__ballot_sync(qmask, cur == kEmptySlot) >> (quad * 4)) & 0xFu;
@@ -384,6 +394,7 @@ __global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, T
                     ok = __shfl_sync(qmask, ok, quad * 4 + first);
                     if (ok) break; // otherwise somebody else took it: vote again on the same bucket
                 } else {
+                    if (++walked == tv.nbuckets) { if (sub == 0) atomicExch(tv.full, 1u); break; } // (shard) full: reported, not spun on
                     b = (b + 1 == tv.nbuckets) ? 0 : b + 1;
                 }
             }
@@ -1377,6 +1388,10 @@ __global__ void __launch_bounds__(kThreads) k_edges_exact(SearchParams p)
     if (lane == 0 && maxdeg) atomicMax(p.stats + ST_MAXDEG, (unsigned long long)maxdeg);
 }
 
+} // namespace disco
+#include "edges_flat.cuh"
+namespace disco {
+
 // ---------------------------------------------------------------------------------------------------------------
 // containment bookkeeping
 // ---------------------------------------------------------------------------------------------------------------
@@ -1655,8 +1670,8 @@ __global__ void __launch_bounds__(kThreads, 8) k_reduce_emit(ReduceParams p) // 
         pos = __shfl_sync(FULL, pos, 0);
         if (lane < nbuf && pos + lane < p.edges_cap) out[pos + lane] = ebuf[lane];
     }
-    warp_stat_add(p.stats, ST_ROWS_FETCHED, n_rows);
-    warp_stat_add(p.stats, ST_ENTRIES_FETCHED, n_ent);
+    warp_stat_add(p.stats, ST_EMIT_ROWS, n_rows);
+    warp_stat_add(p.stats, ST_EMIT_ENTRIES, n_ent);
     warp_stat_add(p.stats, ST_MULTI_OVERLAP, n_multi);
     warp_stat_add(p.stats, ST_ONE_SIDED, n_one);
     warp_stat_add(p.stats, ST_EDGES_OUT, n_out);
@@ -1666,6 +1681,10 @@ __global__ void __launch_bounds__(kThreads, 8) k_reduce_emit(ReduceParams p) // 
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 static int wp_of(int max_len) { return ((max_len + 31) >> 5) + 2; }
+
+static std::atomic<unsigned long long> g_launches{0};
+unsigned long long launches_total() { return g_launches.load(); }
+#define DISCO_COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 constexpr size_t kSmemBudget = 200 * 1024; // per block; leaves room for the driver's reservation out of 227 KB
 
@@ -1708,6 +1727,7 @@ cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, c
             const uint64_t need = (r.n + kWarps * 32 - 1) / (kWarps * 32);
             if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
             k_table_insert_lanes<<<grid, kThreads, smem, s>>>(r, t, K, skip_bits);
+            DISCO_COUNT_LAUNCH();
             return cudaGetLastError();
         }
     }
@@ -1721,6 +1741,7 @@ cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, c
     const uint64_t need = (r.n + warps - 1) / warps;
     if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
     k_table_insert<<<grid, warps * 32, smem, s>>>(r, t, K, skip_bits);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -1774,6 +1795,7 @@ static cudaError_t launch_search(const SearchParams &p_in, int num_sms, cudaStre
         e = persistent_grid(k_search<NWV, MODE>, smem, num_sms, &grid, threads);     \
         if (e != cudaSuccess) return e;                                              \
         k_search<NWV, MODE><<<grid, threads, smem, s>>>(p);                          \
+        DISCO_COUNT_LAUNCH();                                                        \
         break;                                                                       \
     }
     const int words = (p.reads.max_len + 31) / 32; // registers hold an even number of words >= this
@@ -1803,6 +1825,7 @@ cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStre
         e = persistent_grid(k_contain_uniform<NWV>, smem, num_sms, &grid);           \
         if (e != cudaSuccess) return e;                                              \
         k_contain_uniform<NWV><<<grid, kThreads, smem, s>>>(p);                      \
+        DISCO_COUNT_LAUNCH();                                                        \
         break;                                                                       \
     }
         switch ((words + 1) / 2) {
@@ -1827,7 +1850,55 @@ static cudaError_t launch_warps(Kern kern, const SearchParams &p, size_t per_war
     cudaError_t e = persistent_grid(kern, per_warp_bytes * warps, num_sms, &grid, warps * 32);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, per_warp_bytes * warps, s>>>(p);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
+}
+
+bool edges_flat_supported(int max_len, int stride, int K)
+{
+    if (getenv("DISCO_LEGACY_EDGES") || getenv("DISCO_FUSED")) return false; // the warp-per-read kernels, for A/B timing
+    return stride <= 8 && max_len <= 32 * stride && (K + 31) / 32 <= 4;
+}
+
+uint64_t edges_flat_slack(int num_sms) { return (uint64_t)num_sms * 5 * kWarps * kFlatSlice; }
+
+// probe (one lane per read, then one lane per probe) -> verify (one lane per candidate) -> exact (flagged reads)
+static cudaError_t launch_edges_flat(SearchParams &p, int num_sms, cudaStream_t s, cudaEvent_t ev_probe_done, cudaEvent_t ev_verify_done)
+{
+    const int WP = wp_of(p.reads.max_len);
+    const size_t pb = probe_flat_words_per_warp(p.reads.stride) * sizeof(uint64_t);
+    const size_t vb = verify_flat_words_per_warp(p.reads.max_len) * sizeof(uint64_t);
+    const size_t xb = exact_words_per_warp(WP, p.rowcap) * sizeof(uint64_t);
+    const bool sharded = p.table.world > 1;
+    cudaError_t e;
+#define DISCO_LAUNCH_P(KWV)                                                                                       \
+    e = sharded ? launch_warps(k_probe_flat<KWV, true>, p, pb, num_sms, s) : launch_warps(k_probe_flat<KWV, false>, p, pb, num_sms, s); \
+    break;
+    switch ((p.K + 31) / 32) {
+    case 1: DISCO_LAUNCH_P(1)
+    case 2: DISCO_LAUNCH_P(2)
+    case 3: DISCO_LAUNCH_P(3)
+    default: DISCO_LAUNCH_P(4)
+    }
+#undef DISCO_LAUNCH_P
+    if (e != cudaSuccess) return e;
+    if (ev_probe_done) cudaEventRecord(ev_probe_done, s);
+#define DISCO_LAUNCH_V(NWV)                                                          \
+    {                                                                                \
+        e = launch_warps(k_verify_flat<NWV>, p, vb, num_sms, s);                     \
+        if (e != cudaSuccess) return e;                                              \
+        if (ev_verify_done) cudaEventRecord(ev_verify_done, s);                      \
+        e = launch_warps(k_edges_exact<NWV>, p, xb, num_sms, s);                     \
+        break;                                                                       \
+    }
+    switch (((p.reads.max_len + 31) / 32 + 1) / 2) {
+    case 1: DISCO_LAUNCH_V(2)
+    case 2: DISCO_LAUNCH_V(4)
+    case 3: DISCO_LAUNCH_V(6)
+    default: DISCO_LAUNCH_V(8)
+    }
+#undef DISCO_LAUNCH_V
+    return e;
 }
 
 cudaError_t launch_search_edges(const SearchParams &p_in, int num_sms, cudaStream_t s, cudaEvent_t ev_probe_done, cudaEvent_t ev_verify_done)
@@ -1835,6 +1906,7 @@ cudaError_t launch_search_edges(const SearchParams &p_in, int num_sms, cudaStrea
     if (getenv("DISCO_FUSED")) return launch_search<MODE_EDGES>(p_in, num_sms, s); // the single-kernel variant, for A/B timing
     SearchParams p = p_in;
     size_search(p, MODE_EDGES);
+    if (p.cands && edges_flat_supported(p.reads.max_len, p.reads.stride, p.K)) return launch_edges_flat(p, num_sms, s, ev_probe_done, ev_verify_done);
     const int WP = wp_of(p.reads.max_len);
     const size_t pb = probe_words_per_warp(WP, p.npos, p.hcap) * sizeof(uint64_t);
     cudaError_t e = p.table.world > 1 ? launch_warps(k_edges_probe<true>, p, pb, num_sms, s) : launch_warps(k_edges_probe<false>, p, pb, num_sms, s);
@@ -1872,6 +1944,7 @@ cudaError_t launch_contained_finish(const unsigned long long *best, uint64_t n, 
     if (n == 0) return cudaSuccess;
     const uint64_t blocks = (n + 255) / 256;
     k_contained_finish<<<(unsigned)blocks, 256, 0, s>>>(best, n, bits, count);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -1881,6 +1954,7 @@ cudaError_t launch_contained_rows(const unsigned long long *best, const ReadsVie
     if (r.n == 0) return cudaSuccess;
     const uint64_t blocks = (r.n + 255) / 256;
     k_contained_rows<<<(unsigned)blocks, 256, 0, s>>>(best, r, K, reinterpret_cast<disco_crow *>(rows_out), cursor);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -1889,6 +1963,7 @@ cudaError_t launch_restride(const uint64_t *src, int src_stride, int src_words, 
     if (n == 0) return cudaSuccess;
     const uint64_t total = n * (uint64_t)dst_stride;
     k_restride<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(src, src_stride, src_words, dst, dst_stride, n);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -1909,6 +1984,7 @@ cudaError_t launch_min_keys(unsigned long long *mine, const uint64_t *const *pee
 {
     if (n == 0) return cudaSuccess;
     k_min_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(mine, peers, world, rank, n);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -1916,6 +1992,7 @@ cudaError_t launch_revcomp_rows(const ReadsView &r, uint64_t *out, cudaStream_t 
 {
     if (r.n == 0) return cudaSuccess;
     k_revcomp_rows<<<(unsigned)((r.n + 255) / 256), 256, 0, s>>>(r, out);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -1924,6 +2001,7 @@ cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_h
     if (u_hi <= u_lo) return cudaSuccess;
     const uint64_t blocks = (u_hi - u_lo + 255) / 256;
     k_rebase_rowinfo<<<(unsigned)blocks, 256, 0, s>>>(rowinfo, u_lo, u_hi, base);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -1938,6 +2016,7 @@ cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t 
     cudaError_t e = persistent_grid(kern, smem, num_sms, &grid, warps * 32);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, smem, s>>>(p);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 
@@ -1948,6 +2027,7 @@ cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t 
     cudaError_t e = persistent_grid(kern, 0, num_sms, &grid);
     if (e != cudaSuccess) return e;
     kern<<<grid, kThreads, 0, s>>>(p);
+    DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
 

@@ -16,12 +16,14 @@ enum StatSlot {
     ST_CAP_FIRED,
     ST_SLOW_READS,
     ST_MAXDEG,        // atomicMax
-    ST_OVERFLOW,      // adjacency buffer too small (entries needed = rows cursor)
+    ST_OVERFLOW,      // bit 0: adjacency buffer too small (entries needed = rows cursor); bit 1: candidate buffer (its cursor)
     ST_ROWS_FETCHED,  // reduction: neighbour rows read
     ST_ENTRIES_FETCHED,
-    ST_MULTI_OVERLAP,
+    ST_MULTI_OVERLAP, // from here on: written by the emission kernel only (zeroed before each of its attempts)
     ST_ONE_SIDED,
     ST_EDGES_OUT,
+    ST_EMIT_ROWS,
+    ST_EMIT_ENTRIES,
     ST_COUNT
 };
 
@@ -40,6 +42,7 @@ struct TableView {
     uint64_t nbuckets; // buckets per shard
     uint32_t *filter;  // presence bitmap over a second slice of the k-mer hash, small enough to stay in L2 (or null)
     uint32_t filter_mask; // bits - 1 (power of two)
+    unsigned int *full;   // set by the insert kernels when a walk went round the whole (shard of the) table
     // key-sharded table (Mode B, BuildGraphMPIRMA's partitioning): shard = mulhi(hash, world); every GPU inserts the
     // keys of its own shard and probes the other shards through NVLink peer pointers.  world <= 1: single table.
     const uint64_t *const *peers; // device array [world] of shard base pointers (peer-mapped; [rank] == slots)
@@ -63,6 +66,11 @@ struct SearchParams {
     uint64_t rows_cap;
     unsigned long long *rows_cursor;
     uint64_t *rowinfo;
+    // flat edge pass (edges_flat.cuh): candidate list of every 32-read batch, in up to 4 segments per batch
+    uint64_t *cands;
+    uint64_t cands_cap;
+    unsigned long long *cands_cursor;
+    uint64_t *batchinfo; // 4 u64 per batch of the launch: (first candidate << 20) | count
     // shared-memory shape, filled in by the launcher
     int dbg;     // timing ablations (env DISCO_DBG, results are then wrong): 1 no compare, 2 stop after hashing, 4 stop after probing
     int npos;    // k-mer positions of the longest read (max_len - K)
@@ -113,5 +121,11 @@ cudaError_t launch_revcomp_rows(const ReadsView &r, uint64_t *out, cudaStream_t 
 cudaError_t launch_restride(const uint64_t *src, int src_stride, int src_words, uint64_t *dst, int dst_stride, uint64_t n, cudaStream_t s);
 // smem bytes a search / reduce block needs for the given shape (0 = does not fit)
 bool search_edges_fits(int max_len, int K, int cap);
+// the flat edge pass (one lane per read / probe / candidate) handles this shape; otherwise the warp-per-read kernels run
+bool edges_flat_supported(int max_len, int stride, int K);
+// candidate-buffer entries the flat probe kernel may leave unused (one partly filled slice per resident warp)
+uint64_t edges_flat_slack(int num_sms);
+// kernels launched by this library since it was loaded (every launcher counts its own)
+unsigned long long launches_total();
 
 } // namespace disco
