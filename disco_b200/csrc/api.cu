@@ -37,6 +37,7 @@ struct disco_ctx {
     uint64_t *d_words = nullptr;
     uint16_t *d_len = nullptr;
     uint64_t *d_words_rc = nullptr; // reverse complement of every read (verify kernel: suffix overlaps read a prefix); optional
+    uint64_t *d_tails = nullptr;    // last 128 bases of every read as one 32-byte sector (flat verify kernel); 64-byte rows only
     uint64_t *d_stage = nullptr; // host rows arrive here when their pitch differs from the device row
     uint64_t stage_words = 0;
     ReadsView reads{};
@@ -145,7 +146,7 @@ void free_run_buffers(disco_ctx *c)
 
 void free_reads(disco_ctx *c)
 {
-    dfree(c->d_words); dfree(c->d_words_rc); dfree(c->d_len); dfree(c->d_stage);
+    dfree(c->d_words); dfree(c->d_words_rc); dfree(c->d_tails); dfree(c->d_len); dfree(c->d_stage);
     c->stage_words = 0;
     c->reads = ReadsView{};
 }
@@ -201,6 +202,12 @@ int alloc_reads(disco_ctx *ctx, uint64_t n, int min_len, int max_len)
     if (stride >= 4 && stride <= 16 && getenv("DISCO_RC_COPY") && atoi(getenv("DISCO_RC_COPY")) == 1) {
         if (cudaMalloc(&ctx->d_words_rc, n * (uint64_t)stride * sizeof(uint64_t)) != cudaSuccess) { ctx->d_words_rc = nullptr; cudaGetLastError(); }
     }
+    // Tail-sector copy (32 bytes per read, rows of 64 bytes): lets the verify kernel fetch one 32-byte sector per candidate
+    // for overlaps of up to 128 bases.  Optional: skipped when memory is short or DISCO_TAILS=0.
+    if (stride == 8 && !(getenv("DISCO_TAILS") && atoi(getenv("DISCO_TAILS")) == 0)) {
+        if (cudaMalloc(&ctx->d_tails, n * 4 * sizeof(uint64_t)) != cudaSuccess) { ctx->d_tails = nullptr; cudaGetLastError(); }
+    }
+    ctx->reads.tails = nullptr; // set by disco_gpu_begin once the copy is filled
     ctx->reads.words = ctx->d_words; ctx->reads.words_rc = ctx->d_words_rc; ctx->reads.len = ctx->d_len; ctx->reads.n = n; ctx->reads.stride = stride;
     ctx->reads.min_len = min_len; ctx->reads.max_len = max_len;
     ctx->reads.uniform_len = (min_len == max_len) ? max_len : 0;
@@ -362,10 +369,12 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
             ctx->nbuckets = std::max<uint64_t>(1024, nb);
         }
         CK(cudaMalloc(&ctx->d_slots, ctx->nbuckets * 4 * sizeof(uint64_t)));
-        // presence filter: 16 bits per record, at most 64 MB so that it stays resident in the 126 MB L2; pointless
-        // once it has fewer bits than records
+        // presence filter: 16 bits per record, at most 32 MB: measured (profiles/filter_bench.cu, profiles/README.md) the
+        // look-ups run at full L2 speed up to 16 MB, -5% at 32 MB, -17% at 64 MB while 1.2 GB of buckets stream by; at
+        // 10 M reads 32 MB is the best trade between look-up speed and false-positive bucket reads.  Pointless once it
+        // has fewer bits than records.
         ctx->filter_bits = 1ULL << 16;
-        while (ctx->filter_bits < 32 * n && ctx->filter_bits < (1ULL << 29)) ctx->filter_bits <<= 1;
+        while (ctx->filter_bits < 32 * n && ctx->filter_bits < (1ULL << 28)) ctx->filter_bits <<= 1;
         if (const char *e = getenv("DISCO_FILTER_LOG2")) { // tuning knob: 0 disables the filter
             const int lg = atoi(e);
             ctx->filter_bits = lg >= 10 && lg <= 33 ? (1ULL << lg) : 0;
@@ -393,6 +402,11 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
     int rc0 = record(ctx, EV_T0);
     if (rc0) return rc0;
     if (ctx->d_words_rc) CK(launch_revcomp_rows(ctx->reads, ctx->d_words_rc, ctx->stream)); // part of the timed run
+    ctx->reads.tails = nullptr;
+    if (ctx->d_tails && ctx->reads.uniform_len > 128) { // (every read one length: the kernel knows the overlap before it fetches)
+        CK(launch_make_tails(ctx->reads, ctx->d_tails, ctx->stream));                         // part of the timed run
+        ctx->reads.tails = ctx->d_tails;
+    }
     return DISCO_OK;
 }
 

@@ -84,6 +84,49 @@ __host__ __device__ inline size_t verify_flat_words_per_warp(int max_len)
     return ((size_t)32 * flat_query_u32(max_len) + 1) / 2 + kFlatSet / 2 + 32 + 32 + 4;
 }
 
+// dovetail_window + type_to_edge (dna.cuh) without branches: a warp's lanes hold candidates of all four types
+__device__ __forceinline__ bool flat_window(int type, int L1, int j, int K, int L2, int *use_rc, int *a, int *b, int *n)
+{
+    const bool to_end = (type & 1) == 0;            // types 0, 2: the overlap runs to the end of read 1
+    const int ov = to_end ? L1 - j : K + j;
+    const bool ok = to_end ? (L1 - j < L2) : (j <= L2 - K);
+    *use_rc = type >> 1;
+    *a = type == 0 ? j : (type == 3 ? L1 - ov : 0);
+    *b = (type == 1 || type == 2) ? L2 - ov : 0;    // types 1, 2: the candidate's suffix overlaps
+    *n = ov;
+    return ok;
+}
+__device__ __forceinline__ int flat_orient(int type) { return (0x63 >> (2 * type)) & 3; } // 0->3 1->0 2->2 3->1 (OverlapGraph.cpp:660-666)
+
+// bases [a, a+n) of padded array P against bases [b, b+n) of NW candidate words held in registers (RegMatcher's compare)
+template <int NW>
+__device__ __forceinline__ bool match_regs(const uint64_t (&v)[NW], const uint32_t *P, int a, int b, int n, int p_u32)
+{
+    const int q0 = a - b + 32;
+    const int i0 = q0 >> 4, sh = (q0 & 15) * 2;
+    const int wlo = b >> 5, whi = (b + n - 1) >> 5;
+    const uint64_t head = ~0ULL >> (2 * (b & 31));
+    const int tb = (b + n) & 31;
+    const uint64_t tail = tb ? ~(~0ULL >> (2 * tb)) : ~0ULL;
+    uint64_t diff = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) {
+        int i = i0 + 2 * w;
+        i = max(0, min(i, p_u32 - 3));
+        const uint32_t w0 = P[i], w1 = P[i + 1], w2 = P[i + 2];
+        const uint64_t x = (((uint64_t)fsl32(w1, w0, sh) << 32) | fsl32(w2, w1, sh)) ^ v[w];
+        uint64_t m = (w >= wlo && w <= whi) ? ~0ULL : 0ULL;
+        if (w == wlo) m &= head;
+        if (w == whi) m &= tail;
+        diff |= x & m;
+    }
+    return diff == 0;
+}
+__device__ __forceinline__ void load_sector(const uint64_t *p, uint64_t &a, uint64_t &b, uint64_t &c, uint64_t &d, uint64_t pol)
+{
+    asm volatile("ld.global.nc.L2::cache_hint.L2::64B.v4.u64 {%0,%1,%2,%3}, [%4], %5;" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p), "l"(pol));
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 template <int KW, bool SHARDED>
 __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
@@ -95,7 +138,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
     uint64_t *w0 = smem + wib * probe_flat_words_per_warp(p.reads.stride);
     uint64_t *rw = w0 + lane * RS;                                   // this lane's read
     uint64_t *qh = w0 + 32 * RS;                                     // queue: fingerprints
-    uint32_t *qm = reinterpret_cast<uint32_t *>(qh + kFlatQueue);    // queue: (j << 6) | (canonical-is-forward << 5) | lane
+    uint32_t *qm = reinterpret_cast<uint32_t *>(qh + kFlatQueue);    // queue: [31..17 j][16 canonical-is-forward][15..11 lane][10..8 buckets walked][7..4 matches so far]
     uint32_t *cnt = qm + kFlatQueue;                                 // tag matches per read of the batch
     uint64_t *segs = reinterpret_cast<uint64_t *>(cnt + 32);
     uint32_t *ctrl = reinterpret_cast<uint32_t *>(segs + kFlatSegs); // [0] reads flagged for the exact path (bit per lane)
@@ -156,87 +199,92 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
         unsigned seg_cnt = 0;
 
         // one lane per queued probe: bucket walk, tag matches appended to the candidate list
+        // (a probe whose bucket has no hole goes back into the queue for the next bucket of its chain instead of
+        // keeping the whole warp in a second round for one or two lanes)
         auto flush = [&]() {
             const int n = qn < 32 ? qn : 32;
             const bool has = lane < n;
             const int qi = qn - n + lane;
             const uint64_t h = has ? qh[qi] : 0;
             const uint32_t meta = has ? qm[qi] : 0;
-            const int j = (int)(meta >> 6), fq = (int)((meta >> 5) & 1);
-            const uint32_t src = meta & 31;
+            const int j = (int)(meta >> 17), fq = (int)((meta >> 16) & 1);
+            const uint32_t src = (meta >> 11) & 31;
+            const int walked = (int)((meta >> 8) & 7);
+            int pushed = (int)((meta >> 4) & 15);
             const uint32_t self = (uint32_t)(r0 + src);
             const uint32_t tag = slot_tag(h);
             const uint64_t *slots = p.table.slots;
             uint64_t b;
             if (SHARDED) { const Home home = home_of(p.table, h); slots = home.slots; b = home.b; }
             else b = bucket_of(h, nbuckets);
-            bool cont = has;
-            int pushed = 0, walked = 0;
-            while (__any_sync(FULL, cont)) {
-                uint64_t v[4];
-                unsigned mbits = 0;
-                bool hole = true;
-                if (cont) {
-                    load_bucket(slots, b, v, policy_evict_first());
-                    n_buckets++;
-                    hole = false;
+            b += (uint64_t)walked;
+            if (b >= nbuckets) b -= nbuckets;
+            uint64_t v[4];
+            unsigned mbits = 0;
+            bool hole = true;
+            if (has) {
+                load_bucket(slots, b, v, policy_evict_first());
+                n_buckets++;
+                hole = false;
 #pragma unroll
-                    for (int q = 0; q < 4; q++) { // branch-free classification of the four slots
-                        const bool empty = v[q] == kEmptySlot;
-                        hole |= empty;
-                        const bool match = !empty && (uint32_t)(v[q] >> 33) == tag && ((uint32_t)v[q] >> 1) != self; // :655
-                        mbits |= (unsigned)match << q;
-                    }
-                    if (mbits && p.skip_contained) { // "ignore contained reads" (HashTable.cpp:533); the bitmap sits in L2
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (((mbits >> q) & 1) && is_contained(p.contained_bits, (uint32_t)v[q] >> 1)) mbits &= ~(1u << q);
-                    }
-                    if (mbits && cnt[src] > (uint32_t)kFlatParkMax) mbits = 0; // this read goes to the exact path anyway
+                for (int q = 0; q < 4; q++) { // branch-free classification of the four slots
+                    const bool empty = v[q] == kEmptySlot;
+                    hole |= empty;
+                    const bool match = !empty && (uint32_t)(v[q] >> 33) == tag && ((uint32_t)v[q] >> 1) != self; // :655
+                    mbits |= (unsigned)match << q;
                 }
-                const int c = __popc(mbits);
-                int incl = c;
+                if (mbits && p.skip_contained) { // "ignore contained reads" (HashTable.cpp:533); the bitmap sits in L2
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
-                const int tot = __shfl_sync(FULL, incl, 31);
-                if (tot && !dead) {
-                    if (blk_cur + tot > blk_end) { // next slice of the candidate buffer: the list continues in a new segment
-                        if (seg_cnt) {
-                            if (nseg < kFlatSegs) { if (lane == 0) segs[nseg] = make_seg(seg_start, seg_cnt); nseg++; }
-                            else dead = true;
-                        }
-                        const unsigned long long want = tot > kFlatSlice ? (unsigned long long)tot : (unsigned long long)kFlatSlice;
-                        if (lane == 0) blk_cur = atomicAdd(p.cands_cursor, want);
-                        blk_cur = __shfl_sync(FULL, blk_cur, 0);
-                        blk_end = blk_cur + want;
-                        seg_start = blk_cur; seg_cnt = 0;
+                    for (int q = 0; q < 4; q++)
+                        if (((mbits >> q) & 1) && is_contained(p.contained_bits, (uint32_t)v[q] >> 1)) mbits &= ~(1u << q);
+                }
+                if (mbits && cnt[src] > (uint32_t)kFlatParkMax) mbits = 0; // this read goes to the exact path anyway
+            }
+            const int c = __popc(mbits);
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, incl, o); if (lane >= o) incl += t; }
+            const int tot = __shfl_sync(FULL, incl, 31);
+            if (tot && !dead) {
+                if (blk_cur + tot > blk_end) { // next slice of the candidate buffer: the list continues in a new segment
+                    if (seg_cnt) {
+                        if (nseg < kFlatSegs) { if (lane == 0) segs[nseg] = make_seg(seg_start, seg_cnt); nseg++; }
+                        else dead = true;
                     }
-                    if (!dead) {
-                        if (blk_cur + tot <= p.cands_cap) {
-                            unsigned long long at = blk_cur + (unsigned)(incl - c);
+                    const unsigned long long want = tot > kFlatSlice ? (unsigned long long)tot : (unsigned long long)kFlatSlice;
+                    if (lane == 0) blk_cur = atomicAdd(p.cands_cursor, want);
+                    blk_cur = __shfl_sync(FULL, blk_cur, 0);
+                    blk_end = blk_cur + want;
+                    seg_start = blk_cur; seg_cnt = 0;
+                }
+                if (!dead) {
+                    if (blk_cur + tot <= p.cands_cap) {
+                        unsigned long long at = blk_cur + (unsigned)(incl - c);
 #pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                if ((mbits >> q) & 1) {
-                                    const uint32_t rec = (uint32_t)v[q];
-                                    p.cands[at++] = make_cand(src, j, rec, cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq));
-                                }
+                        for (int q = 0; q < 4; q++) {
+                            if ((mbits >> q) & 1) {
+                                const uint32_t rec = (uint32_t)v[q];
+                                p.cands[at++] = make_cand(src, j, rec, cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq));
                             }
-                        } else if (lane == 0) {
-                            atomicOr(p.stats + ST_OVERFLOW, 2ULL);
                         }
-                        if (c) atomicAdd(&cnt[src], (uint32_t)c);
-                        blk_cur += tot; seg_cnt += tot;
+                    } else if (lane == 0) {
+                        atomicOr(p.stats + ST_OVERFLOW, 2ULL);
                     }
-                }
-                pushed += c;
-                cont = cont && !hole;
-                if (cont) {
-                    if (++walked == kScanLimit) { atomicOr(&ctrl[0], 1u << src); cont = false; } // long chain: exact path
-                    else b = (b + 1 == nbuckets) ? 0 : b + 1;
+                    if (c) atomicAdd(&cnt[src], (uint32_t)c);
+                    blk_cur += tot; seg_cnt += tot;
                 }
             }
-            if (pushed > cap) atomicOr(&ctrl[0], 1u << src); // MAX_EDGE_PER_KMER may fire here: exact path
-            qn -= n;
+            pushed = min(pushed + c, 15);
+            bool cont = has && !hole;
+            if (cont && walked + 1 == kScanLimit) { atomicOr(&ctrl[0], 1u << src); cont = false; } // long chain: exact path
+            if (has && !cont && pushed > cap) atomicOr(&ctrl[0], 1u << src); // MAX_EDGE_PER_KMER may fire here: exact path
+            const unsigned cm = __ballot_sync(FULL, cont); // (also orders this round's queue reads before the writes below)
+            if (cont) {
+                const int pos = qn - n + __popc(cm & lt_mask);
+                qh[pos] = h;
+                qm[pos] = (meta & 0xFFFFF800u) | ((uint32_t)(walked + 1) << 8) | ((uint32_t)pushed << 4);
+            }
+            qn = qn - n + __popc(cm);
             __syncwarp();
         };
 
@@ -261,12 +309,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
                 if (pass) {
                     const int pos = qn + __popc(m & lt_mask);
                     qh[pos] = h;
-                    qm[pos] = ((uint32_t)j << 6) | ((uint32_t)fq << 5) | (uint32_t)lane;
+                    qm[pos] = ((uint32_t)j << 17) | ((uint32_t)fq << 16) | ((uint32_t)lane << 11);
                 }
                 qn += __popc(m);
                 __syncwarp();
             }
-            if (qn >= 32 || (j >= jtop && qn > 0)) flush();
+            while (qn >= 32 || (j >= jtop && qn > 0)) flush();
         }
         // ---- close the batch: candidate list segments, one row reserved per read (as long as its candidate count; the
         // verify kernel writes the survivors there and shortens the row), reads for the exact path flagged
@@ -300,7 +348,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <int NW>
+// SECT: every read has the same length (<= 256 bases) and the tail-sector copy exists -> sector-wise candidate fetches
+template <int NW, bool SECT>
 __global__ void __launch_bounds__(kThreads, 2) k_verify_flat(SearchParams p)
 {
     extern __shared__ uint64_t smem[];
@@ -316,6 +365,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_verify_flat(SearchParams p)
     uint32_t *ctrl = cnt + 32;                                                    // [0] reads with a neighbour seen twice
     const uint64_t nbatches = (p.q_hi - p.q_lo + 31) >> 5;
     const uint64_t pol_stream = policy_evict_first();
+    const int UL = p.reads.uniform_len;
     unsigned n_verified = 0, n_hits = 0, maxdeg = 0;
     unsigned long long n_entries = 0;
     for (;;) {
@@ -369,29 +419,55 @@ __global__ void __launch_bounds__(kThreads, 2) k_verify_flat(SearchParams p)
                 if (!sn) break;
                 const uint64_t *cl = p.cands + (seg >> 20);
                 for (uint32_t i0 = 0; i0 < sn; i0 += 64) {
-                    // two candidates per lane: both rows requested before either is compared
-                    uint64_t cd[2];
+                    // two candidates per lane: both rows requested before either is compared.  Equal-length reads with
+                    // the tail copy: an overlap of up to 128 bases is one 32-byte sector -- the head of the candidate's
+                    // row (its prefix overlaps) or its tail sector (its suffix overlaps); otherwise the whole row.
+                    uint64_t cd[2], v[2][NW];
                     bool act[2];
-                    RegMatcher<NW> m[2];
+                    int ua[2], ub[2], un[2], urc[2];
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         const uint32_t i = i0 + 32 * u + lane;
                         cd[u] = i < sn ? __ldg(cl + i) : 0ULL;
                         act[u] = i < sn && ((gmask >> cand_local(cd[u])) & 1);
-                        m[u].stride = p.reads.stride;
-                        if (act[u]) m[u].load(p.reads.words, cand_read(cd[u]));
+#pragma unroll
+                        for (int w = 0; w < NW; w++) v[u][w] = 0;
+                        if (act[u]) {
+                            const uint32_t local = cand_local(cd[u]), r2 = cand_read(cd[u]);
+                            const uint64_t *row = p.reads.words + (uint64_t)r2 * (uint64_t)p.reads.stride;
+                            if constexpr (SECT && NW >= 6) {
+                                const int type = cand_type(cd[u]);
+                                act[u] = flat_window(type, UL, cand_j(cd[u]), K, UL, &urc[u], &ua[u], &ub[u], &un[u]);
+                                const bool sfx = ub[u] != 0; // (types 1, 2; b = L2 - ov > 0 since ov < L2)
+                                if (act[u] && un[u] <= 128) {
+                                    if (sfx) { row = p.reads.tails + (uint64_t)r2 * 4; ub[u] = 128 - un[u]; }
+                                    load_sector(row, v[u][0], v[u][1], v[u][2], v[u][3], pol_stream);
+                                } else if (act[u]) {
+                                    load_sector(row, v[u][0], v[u][1], v[u][2], v[u][3], pol_stream);
+                                    if constexpr (NW == 6) asm volatile("ld.global.nc.L2::cache_hint.L2::64B.v2.u64 {%0,%1}, [%2], %3;" : "=l"(v[u][4]), "=l"(v[u][5]) : "l"(row + 4), "l"(pol_stream));
+                                    if constexpr (NW == 8) load_sector(row + 4, v[u][4], v[u][5], v[u][6], v[u][7], pol_stream);
+                                }
+                                (void)local;
+                            } else {
+#pragma unroll
+                                for (int w = 0; w < NW / 2; w++)
+                                    asm volatile("ld.global.nc.L2::cache_hint.L2::64B.v2.u64 {%0,%1}, [%2], %3;" : "=l"(v[u][2 * w]), "=l"(v[u][2 * w + 1]) : "l"(row + 2 * w), "l"(pol_stream));
+                            }
+                        }
                     }
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
                         if (!act[u]) continue;
                         const uint32_t local = cand_local(cd[u]), r2 = cand_read(cd[u]);
                         const int j = cand_j(cd[u]), type = cand_type(cd[u]);
-                        const int Lq = (int)rlen[local], L2 = read_len(p.reads, r2);
+                        const int Lq = SECT ? UL : (int)rlen[local];
                         n_verified++;
-                        int use_rc, a, b, n;
-                        if (!dovetail_window(type, Lq, j, K, L2, &use_rc, &a, &b, &n)) continue;
-                        const uint32_t *P = qbase + local * QS + (use_rc ? PU : 0);
-                        if (!m[u](P, a, b, n, PU)) continue;
+                        if (!SECT) {
+                            const int L2 = read_len(p.reads, r2);
+                            if (!flat_window(type, Lq, j, K, L2, &urc[u], &ua[u], &ub[u], &un[u])) continue;
+                        }
+                        const uint32_t *P = qbase + local * QS + (urc[u] ? PU : 0);
+                        if (!match_regs<NW>(v[u], P, ua[u], ub[u], un[u], PU)) continue;
                         // first hit per neighbour (OverlapGraph.cpp:656): a second verified overlap with the same read
                         // sends the query to the exact path
                         const uint32_t key = (r2 * 0x9E3779B1u) ^ (local * 0x85EBCA6Bu);
@@ -403,9 +479,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_verify_flat(SearchParams p)
                             hh = (hh + 1) & (kFlatSet - 1);
                         }
                         const uint32_t idx = atomicAdd(&cnt[local], 1u);
-                        int orient, ovl;
-                        type_to_edge(type, Lq, K, j, &orient, &ovl);
-                        p.rows[rstart[local] + idx] = make_entry(Lq - ovl, r2, orient);
+                        const int ovl = (type & 1) ? K + j : Lq - j;
+                        p.rows[rstart[local] + idx] = make_entry(Lq - ovl, r2, flat_orient(type));
                     }
                 }
             }
@@ -423,7 +498,6 @@ __global__ void __launch_bounds__(kThreads, 2) k_verify_flat(SearchParams p)
         }
         __syncwarp();
     }
-    (void)pol_stream;
     warp_stat_add(p.stats, ST_VERIFIED, n_verified);
     warp_stat_add(p.stats, ST_HITS, n_hits);
     warp_stat_add(p.stats, ST_ENTRIES, n_entries);

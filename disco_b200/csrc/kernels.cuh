@@ -30,6 +30,7 @@ enum StatSlot {
 struct ReadsView {
     const uint64_t *words; // n * stride, 16-byte aligned rows
     const uint64_t *words_rc; // the reverse complement of every read in the same layout, or null (see k_edges_verify)
+    const uint64_t *tails;    // u64[n][4]: the last 128 bases of every read (zero padded in front), or null (see k_verify_flat)
     const uint16_t *len;   // n
     uint64_t n;
     int stride;            // words per read (even)
@@ -115,6 +116,8 @@ cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t 
 cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s);
 // mine[i] = min over ranks of peers[r][i] (peers = device array of the ranks' key arrays, [rank] == mine)
 cudaError_t launch_min_keys(unsigned long long *mine, const uint64_t *const *peers, uint32_t world, uint32_t rank, uint64_t n, cudaStream_t s);
+// out[r][0..3] = the 128 bases that end read r (bases before the read: zero)
+cudaError_t launch_make_tails(const ReadsView &r, uint64_t *out, cudaStream_t s);
 // out[r] = reverse complement of read r, same row layout as r.words
 cudaError_t launch_revcomp_rows(const ReadsView &r, uint64_t *out, cudaStream_t s);
 // copy n rows of src_words u64 (pitch src_stride) into rows of dst_stride u64, zero-filling the tail (dst_stride >= src_words)
