@@ -120,6 +120,15 @@ void dfree(T *&p)
     p = nullptr;
 }
 
+// first guess of adjacency entries / candidates per query read (30x, 150 bp, minOverlap 50 needs ~37); a pass that
+// overflows is repeated with the exact size.  DISCO_ENTRIES_PER_READ: tests force the retry path with a tiny guess.
+uint64_t entries_per_read_guess()
+{
+    const char *e = getenv("DISCO_ENTRIES_PER_READ");
+    const long v = e ? atol(e) : 48;
+    return v >= 1 && v <= 4096 ? (uint64_t)v : 48;
+}
+
 int pick_stride(int max_len)
 {
     const int W = (max_len + 31) / 32;
@@ -490,7 +499,7 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
     if (!ctx->d_rows) {
         size_t free_b = 0, total_b = 0;
         CK(cudaMemGetInfo(&free_b, &total_b));
-        uint64_t want = std::max<uint64_t>(nq * 48, 1 << 20);
+        uint64_t want = std::max<uint64_t>(nq * entries_per_read_guess(), getenv("DISCO_ENTRIES_PER_READ") ? 1 << 10 : 1 << 20);
         const uint64_t lim = (uint64_t)(free_b * 0.6) / sizeof(uint64_t);
         if (want > lim) want = std::max<uint64_t>(lim, 1 << 16);
         CK(cudaMalloc(&ctx->d_rows, want * sizeof(uint64_t)));
@@ -507,8 +516,8 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
             CK(cudaMalloc(&ctx->d_batchinfo, std::max<uint64_t>(nb, 1) * 4 * sizeof(uint64_t)));
             ctx->batch_cap = nb;
         }
-        const uint64_t slack = std::min<uint64_t>(edges_flat_slack(ctx->num_sms), nb * 8192) + 8192;
-        const uint64_t want = std::max<uint64_t>((np + 1024) * 48, 1 << 16) + slack;
+        const uint64_t slack = getenv("DISCO_ENTRIES_PER_READ") ? 8192 : std::min<uint64_t>(edges_flat_slack(ctx->num_sms), nb * 8192) + 8192;
+        const uint64_t want = std::max<uint64_t>((np + 1024) * entries_per_read_guess(), getenv("DISCO_ENTRIES_PER_READ") ? 1 << 10 : 1 << 16) + slack;
         if (ctx->cands_cap < want) { // (a buffer a retry has grown is kept; parts of one pass differ by a read at most)
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
@@ -1008,6 +1017,7 @@ int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out)
     s.multi_overlap_pairs = se[ST_MULTI_OVERLAP]; s.one_sided_edges = se[ST_ONE_SIDED];
     s.reduce_rows_fetched = se[ST_ROWS_FETCHED] + se[ST_EMIT_ROWS]; s.reduce_entries_fetched = se[ST_ENTRIES_FETCHED] + se[ST_EMIT_ENTRIES];
     s.kernel_launches = launches_total() - ctx->launches_at_begin;
+    s.mark_rows_fetched = se[ST_ROWS_FETCHED]; s.mark_entries_fetched = se[ST_ENTRIES_FETCHED];
     auto ms = [&](int a, int b) {
         float t = 0.f;
         if (ctx->ev_done[a] && ctx->ev_done[b]) cudaEventElapsedTime(&t, ctx->ev[a], ctx->ev[b]);

@@ -81,7 +81,7 @@ __host__ __device__ inline size_t probe_flat_words_per_warp(int stride)
 __host__ __device__ inline int flat_query_u32(int max_len) { return 4 * (((max_len + 31) >> 5) + 2) + 1; } // A + R of one read, odd pitch
 __host__ __device__ inline size_t verify_flat_words_per_warp(int max_len)
 {   // staged queries, neighbour set, row starts, lengths + counters, control
-    return ((size_t)32 * flat_query_u32(max_len) + 1) / 2 + kFlatSet / 2 + 32 + 32 + 4;
+    return ((size_t)32 * flat_query_u32(max_len) + 1) / 2 + kFlatSet / 2 + 32 + 32 + 4 + 96;
 }
 
 // dovetail_window + type_to_edge (dna.cuh) without branches: a warp's lanes hold candidates of all four types
@@ -363,9 +363,13 @@ __global__ void __launch_bounds__(kThreads, 2) k_verify_flat(SearchParams p)
     uint32_t *rlen = reinterpret_cast<uint32_t *>(rstart + 32);                   // query lengths
     uint32_t *cnt = rlen + 32;                                                    // survivors per read
     uint32_t *ctrl = cnt + 32;                                                    // [0] reads with a neighbour seen twice
+    uint64_t *cq = reinterpret_cast<uint64_t *>(ctrl + 8);                        // compaction queue: 96 candidates
     const uint64_t nbatches = (p.q_hi - p.q_lo + 31) >> 5;
     const uint64_t pol_stream = policy_evict_first();
     const int UL = p.reads.uniform_len;
+    // a buffer overflowed in the probe kernel: its candidate lists are incomplete (and may point past the buffer); the host
+    // grows the buffers and repeats the pass
+    if (*reinterpret_cast<volatile unsigned long long *>(p.stats + ST_OVERFLOW)) return;
     unsigned n_verified = 0, n_hits = 0, maxdeg = 0;
     unsigned long long n_entries = 0;
     for (;;) {
@@ -413,23 +417,21 @@ __global__ void __launch_bounds__(kThreads, 2) k_verify_flat(SearchParams p)
             if (gtot == 0) continue;
             for (int k = lane; k < kFlatSet; k += 32) set[k] = 0xFFFFFFFFu;
             __syncwarp();
-            for (int sg = 0; sg < kFlatSegs; sg++) {
-                const uint64_t seg = __shfl_sync(FULL, mysegs, sg);
-                const uint32_t sn = (uint32_t)(seg & 0xFFFFF);
-                if (!sn) break;
-                const uint64_t *cl = p.cands + (seg >> 20);
-                for (uint32_t i0 = 0; i0 < sn; i0 += 64) {
-                    // two candidates per lane: both rows requested before either is compared.  Equal-length reads with
-                    // the tail copy: an overlap of up to 128 bases is one 32-byte sector -- the head of the candidate's
-                    // row (its prefix overlaps) or its tail sector (its suffix overlaps); otherwise the whole row.
+            // The group's candidates are compacted through a small queue (a batch whose reads have many candidates is
+            // verified in several groups, each of which picks its own reads' candidates out of the batch's list), so that
+            // the expensive part below always runs with every lane busy: 64 candidates at a time, two per lane.
+            int qn = 0;
+            auto process = [&](const int take) {
+                // two candidates per lane: both rows requested before either is compared.  Equal-length reads with
+                // the tail copy: an overlap of up to 128 bases is one 32-byte sector -- the head of the candidate's
+                // row (its prefix overlaps) or its tail sector (its suffix overlaps); otherwise the whole row.
                     uint64_t cd[2], v[2][NW];
                     bool act[2];
                     int ua[2], ub[2], un[2], urc[2];
 #pragma unroll
                     for (int u = 0; u < 2; u++) {
-                        const uint32_t i = i0 + 32 * u + lane;
-                        cd[u] = i < sn ? __ldg(cl + i) : 0ULL;
-                        act[u] = i < sn && ((gmask >> cand_local(cd[u])) & 1);
+                        act[u] = 32 * u + lane < take;
+                        cd[u] = act[u] ? cq[qn - take + 32 * u + lane] : 0ULL;
 #pragma unroll
                         for (int w = 0; w < NW; w++) v[u][w] = 0;
                         if (act[u]) {
@@ -482,7 +484,30 @@ __global__ void __launch_bounds__(kThreads, 2) k_verify_flat(SearchParams p)
                         const int ovl = (type & 1) ? K + j : Lq - j;
                         p.rows[rstart[local] + idx] = make_entry(Lq - ovl, r2, flat_orient(type));
                     }
+                __syncwarp();
+                qn -= take;
+            };
+            int sg = 0;
+            uint32_t i0 = 0;
+            bool more = true;
+            while (more || qn > 0) {
+                if (more) {
+                    const uint64_t seg = __shfl_sync(FULL, mysegs, sg);
+                    const uint32_t sn = (uint32_t)(seg & 0xFFFFF);
+                    if (!sn) { more = false; }
+                    else {
+                        const uint32_t i = i0 + lane;
+                        const uint64_t cnd = i < sn ? __ldg(p.cands + (seg >> 20) + i) : 0ULL;
+                        const bool mine = i < sn && ((gmask >> cand_local(cnd)) & 1);
+                        const unsigned m = __ballot_sync(FULL, mine);
+                        if (mine) cq[qn + __popc(m & ((1u << lane) - 1))] = cnd;
+                        qn += __popc(m);
+                        __syncwarp();
+                        i0 += 32;
+                        if (i0 >= sn) { i0 = 0; if (++sg == kFlatSegs) more = false; }
+                    }
                 }
+                if (qn >= 64 || (!more && qn > 0)) process(qn < 64 ? qn : 64);
             }
             __syncwarp();
         }

@@ -32,7 +32,7 @@ class Stats(C.Structure):
         "n_reads", "n_contained", "n_edges", "raw_directed_edges", "cap_fired", "multi_overlap_pairs", "one_sided_edges",
         "slow_path_reads", "probes_contained", "probes_edges", "buckets_contained", "buckets_edges",
         "verified_contained", "verified_edges", "max_degree", "reduce_rows_fetched", "reduce_entries_fetched",
-        "table_buckets", "edge_capacity", "queries_contained", "queries_edges", "kernel_launches")] + [(n, C.c_float) for n in (
+        "table_buckets", "edge_capacity", "queries_contained", "queries_edges", "kernel_launches", "mark_rows_fetched", "mark_entries_fetched")] + [(n, C.c_float) for n in (
             "ms_table_all", "ms_contained", "ms_finish_contained", "ms_table_nc", "ms_edges", "ms_mark", "ms_emit", "ms_total",
             "ms_edges_kernel", "ms_contained_kernel", "ms_edges_probe", "ms_edges_verify", "ms_edges_exact",
             "ms_mark_kernel", "ms_emit_kernel")]

@@ -55,6 +55,15 @@ class GpuTensors:
         self.g.set_rows_used(n)
 
 
+def _share_stream(g, t):
+    """The library launches on the context's stream, torch / NCCL on torch's current stream: the drivers below interleave
+    the two without host synchronisation, so both must be ONE stream.  Called by the constructors; a caller that switches
+    torch streams afterwards has to call g.set_stream() again."""
+    dev = getattr(t, "device", None)
+    if dev is not None and dev.type == "cuda" and hasattr(g, "set_stream"):
+        g.set_stream(torch.cuda.current_stream(dev).cuda_stream)
+
+
 def partition(n: int, rank: int, world: int):
     """Contiguous read-id block of a rank (BuildGraphMPI/src/OverlapGraph.cpp:524-529)."""
     return (rank * n) // world, ((rank + 1) * n) // world
@@ -119,6 +128,7 @@ class ShardedBuildGraph:
     def __init__(self, g, rank: int, world: int, group=None, tensors=None, parts: int = 4):
         self.g, self.rank, self.world, self.group = g, rank, world, group
         self.t = tensors or GpuTensors(g, torch.device("cuda", torch.cuda.current_device()))
+        _share_stream(g, self.t)
         self.parts = max(1, parts)
         self.big = None           # gathered adjacency, kept across calls
         self.comm = None
@@ -216,6 +226,7 @@ class KeyShardedBuildGraph:
         from . import gpu as _gpu
         self.g, self.rank, self.world, self.group = g, rank, world, group
         self.t = tensors or GpuTensors(g, torch.device("cuda", torch.cuda.current_device()))
+        _share_stream(g, self.t)
         self.MEM_TABLE, self.MEM_ROWS, self.HANDLE = _gpu.MEM_TABLE, _gpu.MEM_ROWS, _gpu.IPC_HANDLE_BYTES
         self.DiscoError = _gpu.DiscoError
         if symmetric is None:

@@ -69,6 +69,7 @@ typedef struct {
     uint64_t edge_capacity;                       /* adjacency entries allocated */
     uint64_t queries_contained, queries_edges;    /* reads searched by this context's launches */
     uint64_t kernel_launches;                     /* kernels this library launched since disco_gpu_begin (all contexts of the process) */
+    uint64_t mark_rows_fetched, mark_entries_fetched; /* the marking kernel's share of reduce_rows/entries_fetched */
     /* device time of the last disco_gpu_build_graph(), CUDA events on the context's stream, milliseconds */
     float ms_table_all, ms_contained, ms_finish_contained, ms_table_nc, ms_edges, ms_mark, ms_emit, ms_total;
     float ms_edges_kernel, ms_contained_kernel; /* the search kernels alone (edge pass = probe + verify + exact) */

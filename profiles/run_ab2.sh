@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 i=0
 for kv in "$@"; do
   i=$((i+1))
-  env $kv timeout 200 python bench.py --steps 4 --warmup 3 --no-cpu $BENCH_ARGS 2>&1 | tail -1 > gpurun_out/ab2_$i.json
+  env $kv timeout 200 python bench.py --steps 4 --warmup 3 --no-cpu --no-config3 $BENCH_ARGS 2>&1 | tail -1 > gpurun_out/ab2_$i.json
   KV="$kv" python - <<PY
 import json, os
 try:

@@ -35,9 +35,11 @@ def _contained(prefix, shards):
 
 
 @pytest.mark.skipif(not os.access(REF, os.X_OK), reason="oracle/_ref/buildG not built")
-@pytest.mark.parametrize("min_overlap", [30, 50])
-def test_paired_genome_against_reference_binary(tmp_path, min_overlap):
-    rs = synth.paired_genome(60_000, 250, insert=500, insert_sd=50, coverage=30.0, seed=1)
+@pytest.mark.parametrize("n_pairs,min_overlap", [(60_000, 30), (60_000, 50), (276_000, 30)],
+                         ids=["1Mb_m30", "1Mb_m50", "ecoli_size_4.6Mb_552k_reads_m30"])
+def test_paired_genome_against_reference_binary(tmp_path, n_pairs, min_overlap):
+    # 4.6 Mb genome, 2 x 250 bp pairs, 30x = 552 k reads, minOverlap 30 (disco.cfg:9), runEcoli.sh's -n 4 -m 5
+    rs = synth.paired_genome(n_pairs, 250, insert=500, insert_sd=50, coverage=30.0, seed=1)
     fa = str(tmp_path / "ecoli_like.fna")
     rs.write_fasta(fa)
     cfg = tmp_path / "disco.cfg"

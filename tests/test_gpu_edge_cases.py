@@ -149,3 +149,34 @@ def test_other_cap_values(cap):
                 assert np.bincount(pos.astype(np.int64)).max() <= cap
     finally:
         bg.close()
+
+
+def test_buffer_overflow_retry_gives_the_same_graph(monkeypatch):
+    """Adjacency and candidate buffers start from a guess (48 entries per read); a pass that overflows either is repeated
+    with the size its cursors asked for.  Forced here with a guess of one entry per read, in one pass and in parts."""
+    from disco_b200 import gpu, host, synth
+    rs = synth.single_genome(40_000, 150, 40.0, seed=9)
+    packed, lens = host.pack_codes(rs.codes, rs.off)
+
+    def run(parts):
+        g = gpu.GpuBuildGraph(0)
+        g.load_reads(packed, lens)
+        n = rs.n
+        g.begin(50, 4)
+        g.phase_table(False)
+        g.phase_contained(0, n)
+        g.phase_finish_contained()
+        g.phase_table(True)
+        b = [n * i // parts for i in range(parts + 1)]
+        for i in range(parts):
+            g.phase_edges_part(0, n, b[i], b[i + 1])
+        g.phase_reduce(0, n)
+        out = (gpu.sort_edges(g.edges()), g.stats())
+        g.close()
+        return out
+    e0, s0 = run(1)
+    monkeypatch.setenv("DISCO_ENTRIES_PER_READ", "1")
+    e1, s1 = run(1)
+    e3, s3 = run(3)
+    assert s0["raw_directed_edges"] == s1["raw_directed_edges"] == s3["raw_directed_edges"] > 40_000 * 30
+    assert np.array_equal(e0, e1) and np.array_equal(e0, e3)
