@@ -301,7 +301,10 @@ def measure(args, workload, reads_per_gpu, world, rank, local, primary):
     key_sharded = args.partition == "key-sharded"
     runner = None
     if world > 1:
-        runner = multigpu.KeyShardedBuildGraph(g, rank, world) if key_sharded else multigpu.ShardedBuildGraph(g, rank, world)
+        if args.partition == "replicated-gather":
+            runner = multigpu.ShardedBuildGraph(g, rank, world)
+        else:   # adjacency partitioned by query range, read through peer pointers; table sharded by key or replicated
+            runner = multigpu.KeyShardedBuildGraph(g, rank, world, shard_table=key_sharded)
 
     def device_step():
         g.load_reads_device(d_packed.data_ptr(), d_lens.data_ptr(), n, wpr, READ_LEN, READ_LEN)
@@ -471,7 +474,7 @@ def measure(args, workload, reads_per_gpu, world, rank, local, primary):
         "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": f"synthetic {n} x {READ_LEN}bp {wl_text} reads ({COVERAGE:.0f}x mean, both strands, error-free), "
-                               f"minOverlap={MIN_OVERLAP}" + (f", {world} GPUs: queries sharded by read id, " + ("reads replicated, table sharded by key and adjacency by query range (remote shards read over NVLink)" if key_sharded else "table+reads replicated") if world > 1 else (" (BASELINE config 2)" if workload == "single" and n == 10_000_000 else "")),
+                               f"minOverlap={MIN_OVERLAP}" + (f", {world} GPUs: queries sharded by read id, " + ("reads replicated, table sharded by key and adjacency by query range (remote shards read over NVLink)" if key_sharded else ("table+reads replicated, adjacency all-gathered" if args.partition == "replicated-gather" else "table+reads replicated, adjacency partitioned by query range (neighbours' rows read over NVLink)")) if world > 1 else (" (BASELINE config 2)" if workload == "single" and n == 10_000_000 else "")),
                    "partition": (args.partition if world > 1 else "single"),
                    "reads": n, "reads_per_gpu": reads_per_gpu, "read_len": READ_LEN, "min_overlap": MIN_OVERLAP,
                    "max_edge_per_kmer": 4, "l2": "inputs larger than L2 (packed reads + table > 126 MB), no flush needed"},
@@ -547,8 +550,10 @@ def main():
                     help="single = BASELINE config 2's shape (headline); metagenome = config 3's shape (200 genomes, log-normal abundance)")
     ap.add_argument("--no-config3", dest="config3", action="store_false", help="skip the second measurement on config 3's shape")
     ap.add_argument("--config3-reads", type=int, default=12_500_000, help="reads per GPU of the config-3-shape measurement (8 GPUs: 100M)")
-    ap.add_argument("--partition", default=os.environ.get("DISCO_PARTITION", "replicated"), choices=["replicated", "key-sharded"],
-                    help="N > 1 only: replicated = Mode A (config 3), key-sharded = Mode B (config 5's partitioning)")
+    ap.add_argument("--partition", default=os.environ.get("DISCO_PARTITION", "replicated"), choices=["replicated", "replicated-gather", "key-sharded"],
+                    help="N > 1 only: replicated = table + reads replicated, queries sharded by read id (config 3; the adjacency stays "
+                         "with its owner), replicated-gather = the same with the adjacency all-gathered, key-sharded = table sharded by "
+                         "key (config 5's partitioning)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

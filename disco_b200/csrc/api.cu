@@ -80,6 +80,8 @@ struct disco_ctx {
     // rows of its own query range; the other shards are reached through peer-mapped pointers (CUDA IPC)
     bool own_slots = true, own_rows = true; // false: caller-owned memory (disco_gpu_adopt_buffer), never freed or grown here
     uint32_t shard_world = 1, shard_rank = 0;
+    bool table_sharded = true; // false: the table is replicated (built from all reads on this GPU); only the adjacency is partitioned
+    uint32_t tw() const { return table_sharded ? shard_world : 1u; } // shards of the table
     struct PeerSet {
         const uint64_t **d_ptrs = nullptr;         // device array [DISCO_MAX_SHARDS]
         void *opened[DISCO_MAX_SHARDS] = {};       // mappings this context opened (to close them again)
@@ -174,7 +176,7 @@ TableView table_view(const disco_ctx *c)
     TableView tv{};
     tv.slots = c->d_slots; tv.nbuckets = c->nbuckets; tv.filter = c->d_filter;
     tv.filter_mask = (uint32_t)(c->filter_bits ? c->filter_bits - 1 : 0);
-    tv.peers = c->peer_table.d_ptrs; tv.world = c->shard_world; tv.rank = c->shard_rank;
+    tv.peers = c->peer_table.d_ptrs; tv.world = c->tw(); tv.rank = c->table_sharded ? c->shard_rank : 0u;
     tv.full = reinterpret_cast<unsigned int *>(c->d_cursors + CUR_TABLE_FULL);
     return tv;
 }
@@ -373,8 +375,8 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
             uint64_t nb = 3 * n;
-            if (nb * 32 > free_b / 10 * ctx->shard_world) nb = n + n / 2;
-            nb = (nb + ctx->shard_world - 1) / ctx->shard_world; // key-sharded: buckets of this GPU's shard
+            if (nb * 32 > free_b / 10 * ctx->tw()) nb = n + n / 2;
+            nb = (nb + ctx->tw() - 1) / ctx->tw(); // key-sharded: buckets of this GPU's shard
             ctx->nbuckets = std::max<uint64_t>(1024, nb);
         }
         CK(cudaMalloc(&ctx->d_slots, ctx->nbuckets * 4 * sizeof(uint64_t)));
@@ -382,8 +384,10 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
         // look-ups run at full L2 speed up to 16 MB, -5% at 32 MB, -17% at 64 MB while 1.2 GB of buckets stream by; at
         // 10 M reads 32 MB is the best trade between look-up speed and false-positive bucket reads.  Pointless once it
         // has fewer bits than records.
+        // (a replicated table over many GPUs' reads: one more doubling per 4x records keeps the false positives in check)
+        const uint64_t filter_cap = n > 160000000ULL ? (1ULL << 30) : n > 40000000ULL ? (1ULL << 29) : (1ULL << 28);
         ctx->filter_bits = 1ULL << 16;
-        while (ctx->filter_bits < 32 * n && ctx->filter_bits < (1ULL << 28)) ctx->filter_bits <<= 1;
+        while (ctx->filter_bits < 32 * n && ctx->filter_bits < filter_cap) ctx->filter_bits <<= 1;
         if (const char *e = getenv("DISCO_FILTER_LOG2")) { // tuning knob: 0 disables the filter
             const int lg = atoi(e);
             ctx->filter_bits = lg >= 10 && lg <= 33 ? (1ULL << lg) : 0;
@@ -404,7 +408,7 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
     ctx->stats = disco_stats{};
     ctx->launches_at_begin = launches_total();
     ctx->stats.n_reads = n;
-    ctx->stats.table_buckets = ctx->nbuckets * ctx->shard_world;
+    ctx->stats.table_buckets = ctx->nbuckets * ctx->tw();
     for (auto &d : ctx->ev_done) d = false;
     ctx->n_contained = ctx->n_edges = 0;
     ctx->begun = true;
@@ -436,7 +440,7 @@ int disco_gpu_phase_contained(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
 {
     if (!ctx || !ctx->begun) return fail(ctx, DISCO_E_ARG, "call disco_gpu_begin first");
     if (q_lo > q_hi || q_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad query range");
-    if (ctx->shard_world > 1 && !ctx->peer_table.ready) return fail(ctx, DISCO_E_ARG, "sharded table: import the peers' shards first (disco_gpu_import_peers)");
+    if (ctx->tw() > 1 && !ctx->peer_table.ready) return fail(ctx, DISCO_E_ARG, "sharded table: import the peers' shards first (disco_gpu_import_peers)");
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
     SearchParams p{};
@@ -460,7 +464,7 @@ int disco_gpu_phase_finish_contained(disco_ctx *ctx)
     CK(cudaMemcpyAsync(&nc, ctx->d_cursors + CUR_NCONTAINED, sizeof nc, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&full, ctx->d_cursors + CUR_TABLE_FULL, sizeof full, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (full) return fail(ctx, DISCO_E_LIMIT, "hash table%s full: %llu buckets cannot hold this rank's keys (skewed k-mers)", ctx->shard_world > 1 ? " shard" : "", (unsigned long long)ctx->nbuckets);
+    if (full) return fail(ctx, DISCO_E_LIMIT, "hash table%s full: %llu buckets cannot hold this rank's keys (skewed k-mers)", ctx->tw() > 1 ? " shard" : "", (unsigned long long)ctx->nbuckets);
     ctx->n_contained = nc;
     if (nc > ctx->crows_cap) {
         dfree(ctx->d_crows);
@@ -483,7 +487,7 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
 {
     if (!ctx || !ctx->begun || !ctx->have_contained) return fail(ctx, DISCO_E_ARG, "containment pass not finished");
     if (q_lo > q_hi || q_hi > ctx->reads.n || part_lo < q_lo || part_hi > q_hi || part_lo > part_hi) return fail(ctx, DISCO_E_ARG, "bad query range");
-    if (ctx->shard_world > 1 && !ctx->peer_table.ready) return fail(ctx, DISCO_E_ARG, "sharded table: import the peers' shards first (disco_gpu_import_peers)");
+    if (ctx->tw() > 1 && !ctx->peer_table.ready) return fail(ctx, DISCO_E_ARG, "sharded table: import the peers' shards first (disco_gpu_import_peers)");
     CK(cudaSetDevice(ctx->device));
     const bool first = part_lo == q_lo;
     if (!first && !ctx->have_edges) return fail(ctx, DISCO_E_ARG, "edge pass parts must start at q_lo");
@@ -558,7 +562,7 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
         CK(cudaMemcpyAsync(cur, ctx->d_cursors, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(st, ctx->d_stats_e, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        if (cur[CUR_TABLE_FULL]) return fail(ctx, DISCO_E_LIMIT, "hash table%s full: %llu buckets cannot hold this rank's keys (skewed k-mers)", ctx->shard_world > 1 ? " shard" : "", (unsigned long long)ctx->nbuckets);
+        if (cur[CUR_TABLE_FULL]) return fail(ctx, DISCO_E_LIMIT, "hash table%s full: %llu buckets cannot hold this rank's keys (skewed k-mers)", ctx->tw() > 1 ? " shard" : "", (unsigned long long)ctx->nbuckets);
         ctx->stats.raw_directed_edges = st[ST_ENTRIES];
         ctx->stats.max_degree = st[ST_MAXDEG];
         if (!st[ST_OVERFLOW]) {
@@ -588,6 +592,7 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
             uint64_t need = cur[CUR_ROWS] + (uint64_t)ctx->num_sms * 64 * 1024;
             if (np && np < nq) need += (cur[CUR_ROWS] - cursor_before) * ((q_hi - part_hi) / np + 1);
             uint64_t *nr = nullptr;
+            if (!cursor_before) dfree(ctx->d_rows); // nothing to keep: do not hold both buffers at once
             CK(cudaMalloc(&nr, need * sizeof(uint64_t)));
             if (cursor_before) CK(cudaMemcpyAsync(nr, ctx->d_rows, cursor_before * sizeof(uint64_t), cudaMemcpyDeviceToDevice, ctx->stream));
             CK(cudaStreamSynchronize(ctx->stream));
@@ -678,17 +683,19 @@ int disco_gpu_phase_reduce(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
 }
 
 // ---- key-sharded mode (Mode B) --------------------------------------------------------------------------------------
-int disco_gpu_set_shard(disco_ctx *ctx, uint32_t world, uint32_t rank)
+int disco_gpu_set_shard(disco_ctx *ctx, uint32_t world, uint32_t rank) { return disco_gpu_set_partition(ctx, world, rank, 1); }
+
+int disco_gpu_set_partition(disco_ctx *ctx, uint32_t world, uint32_t rank, int shard_table)
 {
     if (!ctx) return DISCO_E_ARG;
     if (world < 1 || world > DISCO_MAX_SHARDS || rank >= world) return fail(ctx, DISCO_E_ARG, "bad shard %u of %u (at most %d)", rank, world, DISCO_MAX_SHARDS);
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (world != ctx->shard_world || rank != ctx->shard_rank) {
+    if (world != ctx->shard_world || rank != ctx->shard_rank || (shard_table != 0) != ctx->table_sharded) {
         close_peers(ctx->peer_table); close_peers(ctx->peer_rows);
         free_run_buffers(ctx); // the table is sized per shard
     }
-    ctx->shard_world = world; ctx->shard_rank = rank;
+    ctx->shard_world = world; ctx->shard_rank = rank; ctx->table_sharded = shard_table != 0;
     if (world > 1) {
         if (!ctx->peer_table.d_ptrs) CK(cudaMalloc(&ctx->peer_table.d_ptrs, DISCO_MAX_SHARDS * sizeof(uint64_t *)));
         if (!ctx->peer_rows.d_ptrs) CK(cudaMalloc(&ctx->peer_rows.d_ptrs, DISCO_MAX_SHARDS * sizeof(uint64_t *)));
@@ -715,7 +722,7 @@ namespace {
 int check_import(disco_ctx *ctx, int which, const void *src, const uint64_t *bounds)
 {
     if (!ctx || !src) return DISCO_E_ARG;
-    if (ctx->shard_world < 2) return fail(ctx, DISCO_E_ARG, "not in sharded mode (disco_gpu_set_shard)");
+    if ((which == DISCO_MEM_TABLE ? ctx->tw() : ctx->shard_world) < 2) return fail(ctx, DISCO_E_ARG, "not in sharded mode (disco_gpu_set_shard / disco_gpu_set_partition)");
     if (which != DISCO_MEM_TABLE && which != DISCO_MEM_ROWS) return fail(ctx, DISCO_E_ARG, "bad buffer selector %d", which);
     if (which == DISCO_MEM_ROWS && !bounds) return fail(ctx, DISCO_E_ARG, "the adjacency needs the ranks' read-id bounds");
     if (!(which == DISCO_MEM_TABLE ? (void *)ctx->d_slots : (void *)ctx->d_rows)) return fail(ctx, DISCO_E_ARG, "own buffer not allocated yet");
@@ -1042,6 +1049,30 @@ void *disco_gpu_dev_rows(disco_ctx *ctx, uint64_t *n_entries)
     if (!ctx) return nullptr;
     if (n_entries) *n_entries = ctx->rows_used;
     return ctx->d_rows;
+}
+
+// Sparse form of the containment-key exchange (multi-GPU): this rank's keys that are set, as u64 pairs (read, key), into
+// the caller's device buffer (capacity in pairs); returns how many there are -- more than the capacity: nothing usable was
+// written, fall back to the dense all-reduce.  apply takes pairs gathered from all ranks (read >= n: padding).
+int disco_gpu_compact_keys(disco_ctx *ctx, void *d_pairs, uint64_t capacity, uint64_t *n_pairs)
+{
+    if (!ctx || !ctx->begun || !d_pairs || !n_pairs) return fail(ctx, DISCO_E_ARG, "compact_keys: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemsetAsync(ctx->d_cursors + CUR_CROWS, 0, sizeof(unsigned long long), ctx->stream)); // (free until finish_contained)
+    CK(launch_compact_keys(ctx->d_best, ctx->reads.n, static_cast<unsigned long long *>(d_pairs), capacity, ctx->d_cursors + CUR_CROWS, ctx->stream));
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(&c, ctx->d_cursors + CUR_CROWS, sizeof c, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *n_pairs = c;
+    return DISCO_OK;
+}
+
+int disco_gpu_apply_keys(disco_ctx *ctx, const void *d_pairs, uint64_t n_pairs)
+{
+    if (!ctx || !ctx->begun || (!d_pairs && n_pairs)) return fail(ctx, DISCO_E_ARG, "apply_keys: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    CK(launch_apply_keys(ctx->d_best, ctx->reads.n, static_cast<const unsigned long long *>(d_pairs), n_pairs, ctx->stream));
+    return DISCO_OK;
 }
 
 int disco_gpu_rebase_rows(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi, uint64_t base)

@@ -2004,6 +2004,50 @@ __global__ void k_min_keys(unsigned long long *mine, const uint64_t *const *peer
     mine[i] = v;
 }
 
+// Containment keys that are set, as (read, key) pairs -- what a rank contributes to the exchange of the keys: a few
+// percent of n instead of the whole array.  Warp-aggregated append; order is irrelevant (the consumer takes minima).
+__global__ void k_compact_keys(const unsigned long long *best, uint64_t n, unsigned long long *pairs, uint64_t cap, unsigned long long *count)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned long long k = i < n ? best[i] : ~0ULL;
+    const bool set = k != ~0ULL;
+    const unsigned m = __ballot_sync(FULL, set);
+    if (!m) return;
+    const int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL, base, 0);
+    if (set) {
+        const unsigned long long at = base + __popc(m & ((1u << lane) - 1));
+        if (at < cap) { pairs[2 * at] = i; pairs[2 * at + 1] = k; }
+    }
+}
+
+// best[read] = min(best[read], key) for every pair (pairs with read >= n are padding)
+__global__ void k_apply_keys(unsigned long long *best, uint64_t n, const unsigned long long *pairs, uint64_t npairs)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npairs) return;
+    const unsigned long long r = pairs[2 * i], k = pairs[2 * i + 1];
+    if (r < n && k != ~0ULL) atomicMin(best + r, k);
+}
+
+cudaError_t launch_compact_keys(const unsigned long long *best, uint64_t n, unsigned long long *pairs, uint64_t cap, unsigned long long *count, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    k_compact_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(best, n, pairs, cap, count);
+    DISCO_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_apply_keys(unsigned long long *best, uint64_t n, const unsigned long long *pairs, uint64_t npairs, cudaStream_t s)
+{
+    if (npairs == 0) return cudaSuccess;
+    k_apply_keys<<<(unsigned)((npairs + 255) / 256), 256, 0, s>>>(best, n, pairs, npairs);
+    DISCO_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_min_keys(unsigned long long *mine, const uint64_t *const *peers, uint32_t world, uint32_t rank, uint64_t n, cudaStream_t s)
 {
     if (n == 0) return cudaSuccess;

@@ -116,6 +116,9 @@ cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t 
 cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s);
 // mine[i] = min over ranks of peers[r][i] (peers = device array of the ranks' key arrays, [rank] == mine)
 cudaError_t launch_min_keys(unsigned long long *mine, const uint64_t *const *peers, uint32_t world, uint32_t rank, uint64_t n, cudaStream_t s);
+// sparse exchange of the containment keys: the keys that are set as (read, key) pairs / minima taken from such pairs
+cudaError_t launch_compact_keys(const unsigned long long *best, uint64_t n, unsigned long long *pairs, uint64_t cap, unsigned long long *count, cudaStream_t s);
+cudaError_t launch_apply_keys(unsigned long long *best, uint64_t n, const unsigned long long *pairs, uint64_t npairs, cudaStream_t s);
 // out[r][0..3] = the 128 bases that end read r (bases before the read: zero)
 cudaError_t launch_make_tails(const ReadsView &r, uint64_t *out, cudaStream_t s);
 // out[r] = reverse complement of read r, same row layout as r.words

@@ -22,7 +22,7 @@ EXPORTS = [
     "disco_gpu_set_rows_used", "disco_gpu_use_rows", "disco_gpu_phase_edges_part", "disco_gpu_phase_reduce_mark",
     "disco_gpu_phase_reduce_emit", "disco_gpu_set_shard", "disco_gpu_export_mem", "disco_gpu_import_peers",
     "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table", "disco_gpu_table_words", "disco_gpu_adopt_buffer",
-    "disco_gpu_build_graph_multi", "disco_gpu_device_count",
+    "disco_gpu_build_graph_multi", "disco_gpu_device_count", "disco_gpu_set_partition", "disco_gpu_compact_keys", "disco_gpu_apply_keys",
 ]
 MAX_SHARDS, IPC_HANDLE_BYTES, MEM_TABLE, MEM_ROWS = 8, 64, 0, 1
 
@@ -78,6 +78,9 @@ def lib():
         L.disco_gpu_phase_reduce_mark.argtypes = [vp, u64, u64]
         L.disco_gpu_phase_reduce_emit.argtypes = [vp, u64, u64]
         L.disco_gpu_set_shard.argtypes = [vp, u32, u32]
+        L.disco_gpu_set_partition.argtypes = [vp, u32, u32, i32]
+        L.disco_gpu_compact_keys.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.disco_gpu_apply_keys.argtypes = [vp, vp, u64]
         L.disco_gpu_export_mem.argtypes = [vp, i32, vp]
         L.disco_gpu_import_peers.argtypes = [vp, i32, vp, vp]
         L.disco_gpu_import_peer_ptrs.argtypes = [vp, i32, vp, vp]
@@ -195,6 +198,9 @@ class GpuBuildGraph:
     def set_shard(self, world: int, rank: int):
         self._ck(self._L.disco_gpu_set_shard(self._h, world, rank), "set_shard")
 
+    def set_partition(self, world: int, rank: int, shard_table: bool):
+        self._ck(self._L.disco_gpu_set_partition(self._h, world, rank, int(shard_table)), "set_partition")
+
     def export_mem(self, which: int) -> bytes:
         buf = C.create_string_buffer(IPC_HANDLE_BYTES)
         self._ck(self._L.disco_gpu_export_mem(self._h, which, buf), "export_mem")
@@ -220,6 +226,14 @@ class GpuBuildGraph:
 
     def adopt_buffer(self, which: int, d_ptr: int, n_u64: int):
         self._ck(self._L.disco_gpu_adopt_buffer(self._h, which, C.c_void_p(d_ptr), n_u64), "adopt_buffer")
+
+    def compact_keys(self, d_pairs_ptr: int, capacity: int) -> int:
+        n = C.c_uint64()
+        self._ck(self._L.disco_gpu_compact_keys(self._h, C.c_void_p(d_pairs_ptr), capacity, C.byref(n)), "compact_keys")
+        return n.value
+
+    def apply_keys(self, d_pairs_ptr: int, n_pairs: int):
+        self._ck(self._L.disco_gpu_apply_keys(self._h, C.c_void_p(d_pairs_ptr), n_pairs), "apply_keys")
 
     def dev_contained_keys(self) -> int:
         return self._L.disco_gpu_dev_contained_keys(self._h)

@@ -79,6 +79,58 @@ def allreduce_unsigned_min(keys: torch.Tensor, group=None):
     return keys
 
 
+def allreduce_keys(keys: torch.Tensor, world: int, group=None, g=None):
+    """MIN over ranks of the containment keys.  Only a few percent of the reads are contained, so the ranks exchange the
+    (read, key) pairs that are set -- an all-gather of a few MB -- instead of all-reducing u64[n]; dense when many are.
+    g: the context, whose kernels compact the keys and take the minima (without it: the same in torch ops)."""
+    n = keys.numel()
+    compact = getattr(g, "compact_keys", None) if keys.is_cuda else None
+    cap = max(n // 8, 1024)
+    if compact is not None:
+        mine = torch.empty((cap, 2), dtype=torch.int64, device=keys.device)
+        cnt_here = compact(mine.data_ptr(), cap)
+    else:
+        sel = (keys != -1).nonzero(as_tuple=True)[0]
+        cnt_here = sel.numel()
+    cnt = torch.tensor([cnt_here], dtype=torch.int64, device=keys.device)
+    every = [torch.empty_like(cnt) for _ in range(world)]
+    dist.all_gather(every, cnt, group=group)
+    most = max(int(c[0]) for c in every)
+    if most > cap:
+        return allreduce_unsigned_min(keys, group)
+    if most == 0:
+        return keys
+    if compact is not None:
+        if cnt_here < most:
+            mine[cnt_here:most, 0] = n          # padding: a read id outside the set
+        allp = torch.empty((world, most, 2), dtype=torch.int64, device=keys.device)
+        dist.all_gather_into_tensor(allp.view(-1), mine[:most].reshape(-1), group=group)
+        g.apply_keys(allp.data_ptr(), world * most)
+        return keys
+    sign = torch.iinfo(torch.int64).min
+    pair = torch.empty((2, most), dtype=torch.int64, device=keys.device)
+    pair[0].zero_()
+    pair[1].fill_(-1)                       # padding: the all-ones sentinel, loses against everything
+    pair[0, :cnt_here] = sel
+    pair[1, :cnt_here] = keys[sel]
+    allp = torch.empty((world, 2, most), dtype=torch.int64, device=keys.device)
+    dist.all_gather_into_tensor(allp.view(-1), pair.view(-1), group=group)
+    keys.bitwise_xor_(sign)                 # signed order == unsigned order
+    keys.scatter_reduce_(0, allp[:, 0, :].reshape(-1), allp[:, 1, :].reshape(-1).bitwise_xor(sign), reduce="amin")
+    keys.bitwise_xor_(sign)
+    return keys
+
+
+def exchange_rowinfo(rowinfo: torch.Tensor, n: int, rank: int, world: int, group=None):
+    """Every rank ends up with the row infos of all reads.  A rank's own entries are final and the others' are still zero,
+    so an all-reduce(SUM) does it; with equal ranges an in-place all-gather moves half the bytes."""
+    if n % world == 0:
+        per = n // world
+        dist.all_gather_into_tensor(rowinfo, rowinfo[rank * per:(rank + 1) * per], group=group)
+    else:
+        dist.all_reduce(rowinfo, op=dist.ReduceOp.SUM, group=group)
+
+
 def exchange_adjacency(t, max_degree: int, lo: int, hi: int, rank: int, world: int, group=None):
     """All ranks end up with every rank's rows in one common layout -- rank r's rows at [r * slot, r * slot + count_r),
     slot = the largest count -- and a row-info array that points into it.  One in-place all-gather (each rank
@@ -108,8 +160,8 @@ def exchange_adjacency(t, max_degree: int, lo: int, hi: int, rank: int, world: i
     t.move_rows(rank * slot)                   # this rank's rows from the front of the buffer into its slot
     t.rebase_rows(lo, hi, rank * slot)
     mark("move+rebase")
-    dist.all_reduce(t.rowinfo(), op=dist.ReduceOp.SUM, group=group)  # entries of rows owned by other ranks are zero here
-    mark("rowinfo all-reduce")
+    exchange_rowinfo(t.rowinfo(), t.rowinfo().numel(), rank, world, group)  # entries of rows owned by other ranks are zero here
+    mark("rowinfo exchange")
     buf = t.rows_buffer(world * slot)
     dist.all_gather_into_tensor(buf, buf[rank * slot:(rank + 1) * slot], group=group)
     mark("rows all-gather")
@@ -125,10 +177,13 @@ class ShardedBuildGraph:
     """Mode A driver.  `parts` > 1 pipelines the adjacency exchange with the edge pass: the local query range is searched
     in `parts` pieces and the all-gather of piece c runs on the NCCL stream while piece c+1 is being searched."""
 
-    def __init__(self, g, rank: int, world: int, group=None, tensors=None, parts: int = 4):
+    def __init__(self, g, rank: int, world: int, group=None, tensors=None, parts: int = None):
         self.g, self.rank, self.world, self.group = g, rank, world, group
         self.t = tensors or GpuTensors(g, torch.device("cuda", torch.cuda.current_device()))
         _share_stream(g, self.t)
+        if parts is None:   # more, smaller parts as the gathered volume grows: only the last part's gather is exposed
+            import os
+            parts = int(os.environ.get("DISCO_PARTS", "4" if world <= 2 else "8"))
         self.parts = max(1, parts)
         self.big = None           # gathered adjacency, kept across calls
         self.comm = None
@@ -139,7 +194,7 @@ class ShardedBuildGraph:
         g.begin(min_overlap, max_edge_per_kmer)
         g.phase_table(False)
         g.phase_contained(lo, hi)
-        allreduce_unsigned_min(self.t.keys(), self.group)
+        allreduce_keys(self.t.keys(), self.world, self.group, self.g)
         g.phase_finish_contained()
         # Every rank holds the whole table, so a rebuild without the contained reads costs world x the single-GPU time;
         # beyond two ranks it is cheaper to keep the one table and let the edge pass skip contained candidates via the
@@ -195,7 +250,7 @@ class ShardedBuildGraph:
         st = g.stats()
         meta = torch.tensor([int(st["max_degree"])], device=dev, dtype=torch.int64)
         dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=self.group)
-        dist.all_reduce(t.rowinfo(), op=dist.ReduceOp.SUM, group=self.group)  # entries of rows owned by other ranks are zero here
+        exchange_rowinfo(t.rowinfo(), g.n, rank, world, self.group)  # entries of rows owned by other ranks are zero here
         for w in works:
             w.wait()
         main.wait_stream(self.comm)
@@ -216,7 +271,7 @@ class KeyShardedBuildGraph:
     What the host exchanges: the IPC handles (64 bytes per rank, once per allocation), the two all-reduces, and the
     barriers that order the phases across ranks."""
 
-    def __init__(self, g, rank: int, world: int, group=None, tensors=None, symmetric=None, alloc=None):
+    def __init__(self, g, rank: int, world: int, group=None, tensors=None, symmetric=None, alloc=None, shard_table: bool = True):
         """symmetric: allocate the table shards and the adjacency as torch symmetric memory (CUDA VMM allocations with
         2 MB pages, mapped into every peer at rendezvous) instead of exporting the library's cudaMalloc buffers through
         legacy CUDA IPC handles.  Measured on B200: through legacy IPC mappings, random remote reads collapse (8x
@@ -234,7 +289,13 @@ class KeyShardedBuildGraph:
         self.symmetric = symmetric
         self.alloc = alloc                   # (n_u64) -> (int64 tensor, [peer pointers]); default: torch symmetric memory
         self._symm = {}                      # which -> (tensor, peer pointers, handle)
-        g.set_shard(world, rank)
+        # shard_table=False: the hybrid of the two modes -- table (and reads) replicated and probed locally as in Mode A,
+        # adjacency partitioned by query range and read through peer pointers as in Mode B: nothing is all-gathered
+        self.shard_table = shard_table
+        if shard_table:
+            g.set_shard(world, rank)
+        else:
+            g.set_partition(world, rank, False)
 
     def _symm_buffer(self, which, n_u64):
         """Symmetric int64 buffer of n_u64 words for `which`, (re)allocated collectively when the size changes."""
@@ -276,29 +337,35 @@ class KeyShardedBuildGraph:
         lo, hi = partition(n, self.rank, self.world)
         bounds = [partition(n, r, self.world)[0] for r in range(self.world)] + [n]
         g.begin(min_overlap, max_edge_per_kmer)
-        if self.symmetric:
-            words = g.table_words()
-            t, ptrs, _ = self._symm_buffer(self.MEM_TABLE, words)
-            if g.dev_table() != t.data_ptr():
-                g.adopt_buffer(self.MEM_TABLE, t.data_ptr(), words)
-            g.import_peer_ptrs(self.MEM_TABLE, ptrs)
-        g.phase_table(False)
-        if not self.symmetric:
-            self._attach(self.MEM_TABLE)
-        self._barrier()                         # every shard complete before anybody probes it
+        if self.shard_table:
+            if self.symmetric:
+                words = g.table_words()
+                t, ptrs, _ = self._symm_buffer(self.MEM_TABLE, words)
+                if g.dev_table() != t.data_ptr():
+                    g.adopt_buffer(self.MEM_TABLE, t.data_ptr(), words)
+                g.import_peer_ptrs(self.MEM_TABLE, ptrs)
+            g.phase_table(False)
+            if not self.symmetric:
+                self._attach(self.MEM_TABLE)
+            self._barrier()                         # every shard complete before anybody probes it
+        else:
+            g.phase_table(False)                    # the whole table, on every GPU
         g.phase_contained(lo, hi)
-        allreduce_unsigned_min(self.t.keys(), self.group)
+        allreduce_keys(self.t.keys(), self.world, self.group, self.g)
         g.phase_finish_contained()
-        self._barrier()                         # everybody done probing before the shards are rebuilt
-        g.phase_table(True)                     # own shard only: 1/world of the single-GPU cost
-        self._barrier()
+        if self.shard_table:
+            self._barrier()                         # everybody done probing before the shards are rebuilt
+            g.phase_table(True)                     # own shard only: 1/world of the single-GPU cost
+            self._barrier()
+        elif self.world <= 2:
+            g.phase_table(True)                     # (beyond two ranks the rebuild costs more than the bitmap checks it saves)
         if self.symmetric:
             self._edges_symmetric(lo, hi, n)
         else:
             g.phase_edges(lo, hi)               # rows of the own query range stay here
         meta = torch.tensor([int(g.stats()["max_degree"])], device=self.t.device, dtype=torch.int64)
         dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=self.group)
-        dist.all_reduce(self.t.rowinfo(), op=dist.ReduceOp.SUM, group=self.group)  # starts are offsets in the owner's buffer
+        exchange_rowinfo(self.t.rowinfo(), n, self.rank, self.world, self.group)  # starts are offsets in the owner's buffer
         g.set_max_degree(int(meta[0]))
         if self.symmetric:
             g.import_peer_ptrs(self.MEM_ROWS, self._symm[self.MEM_ROWS][1], bounds)

@@ -133,6 +133,12 @@ int disco_gpu_phase_reduce_emit(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi);
 void *disco_gpu_dev_contained_keys(disco_ctx *ctx);
 void *disco_gpu_dev_rowinfo(disco_ctx *ctx);
 void *disco_gpu_dev_rows(disco_ctx *ctx, uint64_t *n_entries);
+/* Sparse exchange of the containment keys (only a few percent of the reads are contained): compact_keys writes this
+ * rank's keys that are set as u64 pairs (read, key) into the caller's device buffer (capacity in pairs) and returns their
+ * number (larger than the capacity: nothing usable was written -- all-reduce the dense array instead); apply_keys takes
+ * the minimum over pairs gathered from every rank (a pair whose read is >= n is padding). */
+int disco_gpu_compact_keys(disco_ctx *ctx, void *d_pairs, uint64_t capacity, uint64_t *n_pairs);
+int disco_gpu_apply_keys(disco_ctx *ctx, const void *d_pairs, uint64_t n_pairs);
 /* Adjacency exchange helpers.  Common layout on every rank: rank r's rows live at [r * slot, r * slot + count_r).
  *   reserve_rows : make the adjacency buffer hold at least n_entries (contents kept)
  *   move_rows    : move this rank's rows from the front of the buffer to dst_offset (regions may not overlap)
@@ -165,6 +171,11 @@ int disco_gpu_adopt_rows(disco_ctx *ctx, const uint64_t *d_rows, uint64_t n_entr
 #define DISCO_MEM_TABLE 0
 #define DISCO_MEM_ROWS 1
 int disco_gpu_set_shard(disco_ctx *ctx, uint32_t world, uint32_t rank);
+/* The same with the choice of what is partitioned: shard_table != 0 is disco_gpu_set_shard; shard_table == 0 keeps the
+ * hash table replicated (every GPU builds it from all reads and probes it locally, as BuildGraphMPI does) and partitions
+ * only the adjacency by query range -- neighbours' rows are then read from their owner through peer pointers instead of
+ * being all-gathered (import DISCO_MEM_ROWS only). */
+int disco_gpu_set_partition(disco_ctx *ctx, uint32_t world, uint32_t rank, int shard_table);
 int disco_gpu_export_mem(disco_ctx *ctx, int which, void *handle_out);
 int disco_gpu_import_peers(disco_ctx *ctx, int which, const void *handles, const uint64_t *bounds);
 /* shards held by contexts of the same process: device pointers [world] instead of IPC handles (the table shard from

@@ -259,3 +259,42 @@ def test_key_sharded_symmetric_retry_gloo():
         assert imported[0][0] == [1000 + r for r in range(world)]          # table: first allocation
         assert imported[1][0] == [3000 + r for r in range(world)]          # adjacency: the buffer that was large enough
         assert [x for x in log if x in ("mark", "emit")] == ["mark", "emit"]
+
+
+def _sparse_keys(rank, n, frac):
+    rng = np.random.default_rng(300 + rank)
+    k = np.full(n, SENT, dtype=np.int64)
+    sel = rng.random(n) < frac
+    # containers anywhere in the id space, incl. keys with the top bit set (unsigned order != signed order)
+    k[sel] = (rng.integers(0, 1 << 43, size=int(sel.sum())).astype(np.int64) << 20) | rng.integers(0, 1 << 19, size=int(sel.sum()))
+    return k
+
+
+def _keys_worker(rank, world, port, q, n, frac):
+    sys.path.insert(0, ROOT)
+    from disco_b200 import multigpu
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    k = torch.from_numpy(_sparse_keys(rank, n, frac))
+    multigpu.allreduce_keys(k, world)
+    q.put((rank, k.numpy().copy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,frac", [(2, 0.03), (3, 0.05), (2, 0.0), (2, 0.5)], ids=["sparse2", "sparse3", "none", "dense"])
+def test_allreduce_keys_gloo(world, frac):
+    """the sparse (pairs all-gathered) and the dense (all-reduce) exchange of containment keys give the unsigned minimum"""
+    n = 5000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + world + int(frac * 100)
+    procs = [ctx.Process(target=_keys_worker, args=(r, world, port, q, n, frac)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.stack([_sparse_keys(r, n, frac) for r in range(world)]).view(np.uint64).min(axis=0).view(np.int64)
+    for _, k in res:
+        assert np.array_equal(k, want)
