@@ -374,60 +374,36 @@ uint64_t oracle_raw_edges(octx *c, oracle_edge **out, oracle_stats *st)
 }
 
 /* ------------------------------------------------------------------ union over endpoints + transitive reduction */
-/* in: raw directed finds.  out: kept undirected edges (src<dst, from src's perspective) sorted by (src,dst). */
+/* in: raw directed finds (every non-contained read's own capped search, sorted by (src, offset, dst, orient)).
+ * out: kept undirected edges (src<dst, from src's perspective) sorted by (src,dst).
+ *
+ * Canonical, order-free semantics:
+ *   - the row of a read is what its OWN search found (OverlapGraph.cpp:631-678 without the explored-skip);
+ *   - markTransitiveEdges (:687-723) runs for every node on those rows: neighbours in (offset, id, orientation) order,
+ *     a still-INPLAY neighbour v eliminates every neighbour w of u that v's row reaches with a chaining orientation;
+ *   - the undirected edge {a<b} exists when either endpoint found it, is removed when it was eliminated in any row that
+ *     holds it (edge and twin are flagged together, :717-718), and is written with a's overlap when a found it, else with
+ *     the twin of b's (:808, :617).
+ * Whenever cap_fired == multi_overlap_pairs == one_sided_edges == 0 every pair is found from both ends with the same
+ * overlap, the rows are symmetric and this is exactly the reference's graph (pinned by the goldens).  Where the cap fires
+ * (or a k-mer is a reverse palindrome) the reference's own result depends on its thread schedule; there this definition is
+ * the deterministic stand-in, and the GPU path is tested against it edge for edge. */
+static int find_in_row(const oracle_edge *raw, const uint64_t *row, uint64_t u, uint64_t w, uint64_t *at)
+{
+    for (uint64_t q = row[u]; q < row[u + 1]; q++)
+        if (raw[q].dst == w) { *at = q; return 1; }
+    return 0;
+}
+
 uint64_t oracle_reduce(octx *c, const oracle_edge *raw, uint64_t nraw, oracle_edge **out, oracle_stats *st)
 {
-    /* 1. canonical undirected set: src<dst; the lower-id endpoint's find wins, else the twin of the other's */
-    oracle_edge *u = (oracle_edge *)malloc((nraw ? nraw : 1) * sizeof(oracle_edge));
-    uint8_t *from_low = (uint8_t *)malloc(nraw ? nraw : 1);
-    for (uint64_t i = 0; i < nraw; i++) {
-        oracle_edge x = raw[i];
-        if (x.src < x.dst) { u[i] = x; }
-        else {
-            uint64_t Ls = rlen(c, x.src - 1), Ld = rlen(c, x.dst - 1);
-            u[i].src = x.dst; u[i].dst = x.src; u[i].orient = (uint32_t)twin_orient((int)x.orient);
-            u[i].offset = (uint32_t)(Ld + x.offset - Ls);   /* OverlapGraph.cpp:617 */
-        }
-    }
-    /* stable tag: sort by (src,dst) keeping which endpoint found it */
-    uint64_t *idx = (uint64_t *)malloc((nraw ? nraw : 1) * sizeof(uint64_t));
-    for (uint64_t i = 0; i < nraw; i++) from_low[i] = raw[i].src < raw[i].dst;
-    /* simple: build array of structs with flag in high bit of orient */
-    for (uint64_t i = 0; i < nraw; i++) u[i].orient |= from_low[i] ? 0x100u : 0u;
-    qsort(u, nraw, sizeof(oracle_edge), cmp_edge_pair);
-    uint64_t ne = 0;
-    oracle_edge *und = (oracle_edge *)malloc((nraw ? nraw : 1) * sizeof(oracle_edge));
-    for (uint64_t i = 0; i < nraw;) {
-        uint64_t k = i;
-        while (k < nraw && u[k].src == u[i].src && u[k].dst == u[i].dst) k++;
-        const oracle_edge *lowv = NULL, *highv = NULL;
-        for (uint64_t q = i; q < k; q++) { if (u[q].orient & 0x100u) lowv = &u[q]; else highv = &u[q]; }
-        if (lowv && highv) {
-            if ((lowv->orient & 3u) != (highv->orient & 3u) || lowv->offset != highv->offset) st->multi_overlap_pairs++;
-        } else st->one_sided_edges++;
-        const oracle_edge *pick = lowv ? lowv : highv;
-        und[ne] = *pick; und[ne].orient &= 3u; ne++;
-        i = k;
-    }
-    free(u); free(from_low); free(idx);
-
-    /* 2. adjacency rows (both directions), each sorted by (offset, neighbour id, orient) */
-    uint64_t nd = 2 * ne;
-    oracle_edge *dir = (oracle_edge *)malloc((nd ? nd : 1) * sizeof(oracle_edge));
-    for (uint64_t i = 0; i < ne; i++) {
-        dir[2 * i] = und[i];
-        uint64_t Ls = rlen(c, und[i].src - 1), Ld = rlen(c, und[i].dst - 1);
-        dir[2 * i + 1].src = und[i].dst; dir[2 * i + 1].dst = und[i].src;
-        dir[2 * i + 1].orient = (uint32_t)twin_orient((int)und[i].orient);
-        dir[2 * i + 1].offset = (uint32_t)(Ld + und[i].offset - Ls);
-    }
-    qsort(dir, nd, sizeof(oracle_edge), cmp_edge_key);
+    /* 1. rows: raw is sorted by src, then (offset, dst, orient) = the visiting order */
     uint64_t *row = (uint64_t *)calloc(c->n + 2, sizeof(uint64_t));
-    for (uint64_t i = 0; i < nd; i++) row[dir[i].src + 1]++;
+    for (uint64_t i = 0; i < nraw; i++) row[raw[i].src + 1]++;
     for (uint64_t r = 1; r <= c->n + 1; r++) row[r] += row[r - 1]; /* row[id] .. row[id+1] */
-    uint8_t *elim = (uint8_t *)calloc(nd ? nd : 1, 1);
+    uint8_t *elim = (uint8_t *)calloc(nraw ? nraw : 1, 1);
 
-    /* 3. markTransitiveEdges for every node on the full graph */
+    /* 2. markTransitiveEdges for every node */
     uint64_t maxdeg = 0;
     for (uint64_t r = 1; r <= c->n; r++) if (row[r + 1] - row[r] > maxdeg) maxdeg = row[r + 1] - row[r];
     uint8_t *state = (uint8_t *)malloc(maxdeg ? maxdeg : 1); /* 0 INPLAY, 1 ELIMINATED */
@@ -437,30 +413,46 @@ uint64_t oracle_reduce(octx *c, const oracle_edge *raw, uint64_t nraw, oracle_ed
         memset(state, 0, d);
         for (uint64_t i = 0; i < d; i++) {
             if (state[i]) continue;
-            uint64_t v = dir[b + i].dst;
-            uint32_t t1 = dir[b + i].orient;
+            uint64_t v = raw[b + i].dst;
+            uint32_t t1 = raw[b + i].orient;
             for (uint64_t q = row[v]; q < row[v + 1]; q++) {
-                uint64_t w = dir[q].dst; uint32_t t2 = dir[q].orient;
+                uint64_t w = raw[q].dst; uint32_t t2 = raw[q].orient;
                 int ok = ((t1 == 0 || t1 == 2) && (t2 == 0 || t2 == 1)) || ((t1 == 1 || t1 == 3) && (t2 == 2 || t2 == 3));
                 if (!ok) continue;
                 for (uint64_t k = 0; k < d; k++)
-                    if (dir[b + k].dst == w && state[k] == 0) state[k] = 1; /* all parallel edges to w */
+                    if (raw[b + k].dst == w) state[k] = 1; /* a visited neighbour can still be eliminated (:712) */
             }
         }
         for (uint64_t k = 0; k < d; k++) if (state[k]) elim[b + k] = 1;
     }
-    /* 4. an edge is removed when flagged from either endpoint (edge + twin flagged, OverlapGraph.cpp:717-718) */
-    oracle_edge *kept = (oracle_edge *)malloc((ne ? ne : 1) * sizeof(oracle_edge));
+    /* 3. union over both endpoints; removed when flagged in any row that holds the edge */
+    oracle_edge *kept = (oracle_edge *)malloc((nraw ? nraw : 1) * sizeof(oracle_edge));
     uint64_t nk = 0;
-    for (uint64_t i = 0; i < nd; i++) {
-        if (dir[i].src >= dir[i].dst) continue;
-        int dead = elim[i];
-        for (uint64_t q = row[dir[i].dst]; q < row[dir[i].dst + 1] && !dead; q++)
-            if (dir[q].dst == dir[i].src && elim[q]) dead = 1;
-        if (!dead) kept[nk++] = dir[i];
+    for (uint64_t i = 0; i < nraw; i++) {
+        const oracle_edge x = raw[i];
+        uint64_t at = 0;
+        const int twin_found = find_in_row(raw, row, x.dst, x.src, &at);
+        /* (the two counters look at entries that survive the marking of the row that holds them: that is where the
+         * emission step meets them) */
+        if (x.src < x.dst) {
+            if (twin_found && !elim[i]) {
+                uint64_t Ls = rlen(c, x.src - 1), Ld = rlen(c, x.dst - 1);
+                if ((uint32_t)twin_orient((int)x.orient) != raw[at].orient || (uint32_t)(Ld + x.offset - Ls) != raw[at].offset) st->multi_overlap_pairs++;
+            } else if (!twin_found && !elim[i]) st->one_sided_edges++;
+            if (!elim[i] && !(twin_found && elim[at])) kept[nk++] = x;
+        } else if (!twin_found) { /* only the higher id found it: written from the lower id's side as the twin */
+            if (!elim[i]) st->one_sided_edges++;
+            if (!elim[i]) {
+                uint64_t Ls = rlen(c, x.src - 1), Ld = rlen(c, x.dst - 1);
+                oracle_edge t;
+                t.src = x.dst; t.dst = x.src; t.orient = (uint32_t)twin_orient((int)x.orient);
+                t.offset = (uint32_t)(Ld + x.offset - Ls);   /* OverlapGraph.cpp:617 */
+                kept[nk++] = t;
+            }
+        }
     }
     qsort(kept, nk, sizeof(oracle_edge), cmp_edge_pair);
-    free(und); free(dir); free(row); free(elim); free(state);
+    free(row); free(elim); free(state);
     *out = kept;
     return nk;
 }

@@ -125,6 +125,11 @@ def test_reverse_palindromic_kmers_even_k():
         rows = sorted((int(e["src"]) + 1, int(e["offset"]), int(e["dst"]) + 1, int(e["orient"])) for r in range(res.n) for e in bg._g.row(r))
         assert rows == sorted((int(e["src"]), int(e["offset"]), int(e["dst"]), int(e["orient"])) for e in o["res"].raw)
         assert res.stats["cap_fired"] == o["res"].stats["cap_fired"]
+        # overlaps only one endpoint can see (the reference's `if / else if` typing of a palindromic record): one-sided rows,
+        # and still the oracle's reduced graph edge for edge
+        assert res.stats["one_sided_edges"] == o["res"].stats["one_sided_edges"]
+        assert res.stats["multi_overlap_pairs"] == o["res"].stats["multi_overlap_pairs"]
+        assert sorted(bg.edge_lines()) == o["edges"]
     finally:
         bg.close()
 

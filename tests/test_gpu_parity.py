@@ -39,9 +39,10 @@ def test_golden_reference_outputs(path):
         assert st["raw_directed_edges"] == o["res"].stats["raw_directed"]
         if st["cap_fired"] == 0 and st["multi_overlap_pairs"] == 0 and st["one_sided_edges"] == 0:
             assert sorted(bg.edge_lines()) == g["ref_edges"]
-            assert sorted(bg.edge_lines()) == o["edges"]
-        else:
-            assert st["one_sided_edges"] == o["res"].stats["one_sided_edges"]
+        # cap or not: the reduced graph equals the oracle's canonical one (own-row marking, union over both endpoints)
+        assert sorted(bg.edge_lines()) == o["edges"]
+        assert st["one_sided_edges"] == o["res"].stats["one_sided_edges"]
+        assert st["multi_overlap_pairs"] == o["res"].stats["multi_overlap_pairs"]
     finally:
         bg.close()
 
@@ -97,6 +98,11 @@ def test_cap_fires_rows_match_oracle(single_table, monkeypatch):
         assert res.stats["cap_fired"] == o["res"].stats["cap_fired"]
         assert res.stats["slow_path_reads"] > 0
         assert _raw_rows(bg._g, res.n) == _oracle_raw(o["res"])
+        # the rows are not symmetric here (a capped read misses partners that still see it): marking on each read's own row,
+        # an edge dying when either endpoint's row flags it, the lower id's overlap winning -- edge for edge the oracle's
+        assert res.stats["one_sided_edges"] == o["res"].stats["one_sided_edges"] > 0
+        assert res.stats["multi_overlap_pairs"] == o["res"].stats["multi_overlap_pairs"]
+        assert sorted(bg.edge_lines()) == o["edges"]
     finally:
         bg.close()
 
