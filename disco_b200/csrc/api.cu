@@ -171,6 +171,34 @@ void close_peers(disco_ctx::PeerSet &ps)
     ps.ready = false;
 }
 
+// candidate lists of the flat kernels for a launch over np reads: four segment words per 32-read batch + the lists
+int ensure_flat_buffers(disco_ctx *ctx, uint64_t np)
+{
+    const uint64_t nb = (np + 31) / 32;
+    if (nb > ctx->batch_cap) {
+        dfree(ctx->d_batchinfo);
+        ctx->batch_cap = 0;
+        CK(cudaMalloc(&ctx->d_batchinfo, std::max<uint64_t>(nb, 1) * 4 * sizeof(uint64_t)));
+        ctx->batch_cap = nb;
+    }
+    const bool tiny = getenv("DISCO_ENTRIES_PER_READ") != nullptr;
+    const uint64_t slack = tiny ? 8192 : std::min<uint64_t>(edges_flat_slack(ctx->num_sms), nb * 8192) + 8192;
+    const uint64_t want = std::max<uint64_t>((np + 1024) * entries_per_read_guess(), tiny ? 1 << 10 : 1 << 16) + slack;
+    if (ctx->cands_cap < want) { // (a buffer a retry has grown is kept; parts of one pass differ by a read at most)
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        const uint64_t lim = (uint64_t)((free_b + ctx->cands_cap * sizeof(uint64_t)) * 0.5) / sizeof(uint64_t);
+        const uint64_t take = std::min(want, std::max<uint64_t>(lim, 1 << 16));
+        if (take > ctx->cands_cap) {
+            dfree(ctx->d_cands);
+            ctx->cands_cap = 0;
+            CK(cudaMalloc(&ctx->d_cands, take * sizeof(uint64_t)));
+            ctx->cands_cap = take;
+        }
+    }
+    return DISCO_OK;
+}
+
 TableView table_view(const disco_ctx *c)
 {
     TableView tv{};
@@ -442,14 +470,45 @@ int disco_gpu_phase_contained(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi)
     if (q_lo > q_hi || q_hi > ctx->reads.n) return fail(ctx, DISCO_E_ARG, "bad query range");
     if (ctx->tw() > 1 && !ctx->peer_table.ready) return fail(ctx, DISCO_E_ARG, "sharded table: import the peers' shards first (disco_gpu_import_peers)");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
     SearchParams p{};
     p.reads = ctx->reads; p.table = table_view(ctx);
     p.K = ctx->K; p.cap = ctx->cap; p.q_lo = q_lo; p.q_hi = q_hi;
     p.work_counter = ctx->d_cursors + CUR_WORK; p.stats = ctx->d_stats_c; p.best = ctx->d_best;
+    p.rowinfo = ctx->d_rowinfo;
+    // reads of several lengths: the flat kernels (candidate lists in global memory; a list that does not fit is measured by
+    // the cursor and the pass repeated).  One length: k_contain_uniform, no lists.
+    const bool flat = !ctx->reads.uniform_len && q_hi > q_lo && edges_flat_supported(ctx->reads.max_len, ctx->reads.stride, ctx->K);
+    if (flat) { int rc = ensure_flat_buffers(ctx, q_hi - q_lo); if (rc) return rc; }
+    unsigned long long st_before[ST_COUNT] = {};
+    if (flat) { // (several ranges may be searched one after the other: keep their counters)
+        CK(cudaMemcpyAsync(st_before, ctx->d_stats_c, sizeof st_before, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     int rc = record(ctx, EV_CONT_K0);
     if (rc) return rc;
-    if (q_hi > q_lo) CK(launch_search_contained(p, ctx->num_sms, ctx->stream));
+    for (int attempt = 0;; attempt++) {
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, 3 * sizeof(unsigned long long), ctx->stream));
+        if (flat) {
+            CK(cudaMemsetAsync(ctx->d_cursors + CUR_CANDS, 0, sizeof(unsigned long long), ctx->stream));
+            if (attempt) CK(cudaMemcpyAsync(ctx->d_stats_c, st_before, sizeof st_before, cudaMemcpyHostToDevice, ctx->stream));
+            p.cands = ctx->d_cands; p.cands_cap = ctx->cands_cap; p.cands_cursor = ctx->d_cursors + CUR_CANDS; p.batchinfo = ctx->d_batchinfo;
+        }
+        if (q_hi > q_lo) CK(launch_search_contained(p, ctx->num_sms, ctx->stream));
+        if (!flat) break;
+        unsigned long long cur[CUR_COUNT] = {}, st[ST_COUNT];
+        CK(cudaMemcpyAsync(cur, ctx->d_cursors, sizeof cur, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(st, ctx->d_stats_c, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (!st[ST_OVERFLOW]) break;
+        if (attempt >= 2) return fail(ctx, DISCO_E_NOMEM, "containment pass: candidate buffer overflow after retries (%llu entries needed)", cur[CUR_CANDS]);
+        const uint64_t need = cur[CUR_CANDS] + edges_flat_slack(ctx->num_sms);
+        dfree(ctx->d_cands);
+        ctx->cands_cap = 0;
+        CK(cudaMalloc(&ctx->d_cands, need * sizeof(uint64_t)));
+        ctx->cands_cap = need;
+        // (keys written by the incomplete attempt are valid minima: they can only be confirmed by the repeat)
+    }
+    if (flat) CK(cudaMemsetAsync(ctx->d_rowinfo + q_lo, 0, (q_hi - q_lo) * sizeof(uint64_t), ctx->stream)); // fall-back flags
     if ((rc = record(ctx, EV_CONT_K1))) return rc;
     return record(ctx, EV_CONTAINED);
 }
@@ -512,29 +571,7 @@ int disco_gpu_phase_edges_part(disco_ctx *ctx, uint64_t q_lo, uint64_t q_hi, uin
     ctx->d_rows_active = ctx->d_rows;
     // flat kernels (short reads): candidate lists of this launch + four segment words per 32-read batch
     const bool flat = edges_flat_supported(ctx->reads.max_len, ctx->reads.stride, ctx->K);
-    if (flat) {
-        const uint64_t nb = (np + 31) / 32;
-        if (nb > ctx->batch_cap) {
-            dfree(ctx->d_batchinfo);
-            ctx->batch_cap = 0;
-            CK(cudaMalloc(&ctx->d_batchinfo, std::max<uint64_t>(nb, 1) * 4 * sizeof(uint64_t)));
-            ctx->batch_cap = nb;
-        }
-        const uint64_t slack = getenv("DISCO_ENTRIES_PER_READ") ? 8192 : std::min<uint64_t>(edges_flat_slack(ctx->num_sms), nb * 8192) + 8192;
-        const uint64_t want = std::max<uint64_t>((np + 1024) * entries_per_read_guess(), getenv("DISCO_ENTRIES_PER_READ") ? 1 << 10 : 1 << 16) + slack;
-        if (ctx->cands_cap < want) { // (a buffer a retry has grown is kept; parts of one pass differ by a read at most)
-            size_t free_b = 0, total_b = 0;
-            CK(cudaMemGetInfo(&free_b, &total_b));
-            const uint64_t lim = (uint64_t)((free_b + ctx->cands_cap * sizeof(uint64_t)) * 0.5) / sizeof(uint64_t);
-            const uint64_t take = std::min(want, std::max<uint64_t>(lim, 1 << 16));
-            if (take > ctx->cands_cap) {
-                dfree(ctx->d_cands);
-                ctx->cands_cap = 0;
-                CK(cudaMalloc(&ctx->d_cands, take * sizeof(uint64_t)));
-                ctx->cands_cap = take;
-            }
-        }
-    }
+    if (flat) { int rc = ensure_flat_buffers(ctx, np); if (rc) return rc; }
     const uint64_t cursor_before = first ? 0 : ctx->rows_used;
     unsigned long long st_before[ST_COUNT] = {};
     if (!first) {

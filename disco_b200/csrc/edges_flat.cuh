@@ -79,6 +79,10 @@ __host__ __device__ inline size_t probe_flat_words_per_warp(int stride)
     return (size_t)32 * flat_row_u64(stride) + kFlatQueue + kFlatQueue / 2 + 16 + kFlatSegs + 2;
 }
 __host__ __device__ inline int flat_query_u32(int max_len) { return 4 * (((max_len + 31) >> 5) + 2) + 1; } // A + R of one read, odd pitch
+__host__ __device__ inline size_t contain_flat_words_per_warp(int max_len)
+{   // staged queries + their lengths
+    return ((size_t)32 * flat_query_u32(max_len) + 1) / 2 + 16;
+}
 __host__ __device__ inline size_t verify_flat_words_per_warp(int max_len)
 {   // staged queries, neighbour set, row starts, lengths + counters, control
     return ((size_t)32 * flat_query_u32(max_len) + 1) / 2 + kFlatSet / 2 + 32 + 32 + 4 + 96;
@@ -128,7 +132,10 @@ __device__ __forceinline__ void load_sector(const uint64_t *p, uint64_t &a, uint
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-template <int KW, bool SHARDED>
+// CONTAIN: the containment pass (markContainedReads, OverlapGraph.cpp:333-505) through the same machinery: every read is a
+// query, positions [0, L-K) pruned to those where a read of the shortest length could fit, no exact path (a batch whose
+// candidate list outgrows its segments is left to the warp-per-read kernel, flagged through its row infos).
+template <int KW, bool SHARDED, bool CONTAIN>
 __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
 {
     extern __shared__ uint64_t smem[];
@@ -138,7 +145,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
     uint64_t *w0 = smem + wib * probe_flat_words_per_warp(p.reads.stride);
     uint64_t *rw = w0 + lane * RS;                                   // this lane's read
     uint64_t *qh = w0 + 32 * RS;                                     // queue: fingerprints
-    uint32_t *qm = reinterpret_cast<uint32_t *>(qh + kFlatQueue);    // queue: [31..17 j][16 canonical-is-forward][15..11 lane][10..8 buckets walked][7..4 matches so far]
+    uint32_t *qm = reinterpret_cast<uint32_t *>(qh + kFlatQueue);    // queue: [31..17 j][16 canonical-is-forward][15..11 lane][10..4 buckets walked][3..0 matches so far]
     uint32_t *cnt = qm + kFlatQueue;                                 // tag matches per read of the batch
     uint64_t *segs = reinterpret_cast<uint64_t *>(cnt + 32);
     uint32_t *ctrl = reinterpret_cast<uint32_t *>(segs + kFlatSegs); // [0] reads flagged for the exact path (bit per lane)
@@ -158,7 +165,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
         if (bi >= nbatches) break;
         const uint64_t r0 = p.q_lo + (bi << 5), r1 = r0 + lane;
         const bool inrange = r1 < p.q_hi;
-        const bool valid = inrange && !((__ldg(p.contained_bits + (r1 >> 5)) >> (r1 & 31)) & 1); // OverlapGraph.cpp:657
+        const bool valid = inrange && (CONTAIN || !((__ldg(p.contained_bits + (r1 >> 5)) >> (r1 & 31)) & 1)); // OverlapGraph.cpp:657
         const int L1 = valid ? read_len(p.reads, r1) : 0;
         if (inrange) {
             const uint64_t *src = p.reads.words + r1 * (uint64_t)p.reads.stride;
@@ -169,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
         } else {
             for (int w = 0; w < p.reads.stride; w++) rw[w] = 0;
         }
-        cnt[lane] = 0;
+        cnt[lane] = CONTAIN ? (uint32_t)L1 : 0u; // (containment: the batch's read lengths, for the geometry test in flush())
         if (lane == 0) ctrl[0] = 0;
         n_queries += valid;
         __syncwarp();
@@ -209,8 +216,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
             const uint32_t meta = has ? qm[qi] : 0;
             const int j = (int)(meta >> 17), fq = (int)((meta >> 16) & 1);
             const uint32_t src = (meta >> 11) & 31;
-            const int walked = (int)((meta >> 8) & 7);
-            int pushed = (int)((meta >> 4) & 15);
+            const int walked = (int)((meta >> 4) & 127);
+            int pushed = (int)(meta & 15);
             const uint32_t self = (uint32_t)(r0 + src);
             const uint32_t tag = slot_tag(h);
             const uint64_t *slots = p.table.slots;
@@ -233,12 +240,27 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
                     const bool match = !empty && (uint32_t)(v[q] >> 33) == tag && ((uint32_t)v[q] >> 1) != self; // :655
                     mbits |= (unsigned)match << q;
                 }
-                if (mbits && p.skip_contained) { // "ignore contained reads" (HashTable.cpp:533); the bitmap sits in L2
+                if (!CONTAIN && mbits && p.skip_contained) { // "ignore contained reads" (HashTable.cpp:533); the bitmap sits in L2
 #pragma unroll
                     for (int q = 0; q < 4; q++)
                         if (((mbits >> q) & 1) && is_contained(p.contained_bits, (uint32_t)v[q] >> 1)) mbits &= ~(1u << q);
                 }
-                if (mbits && cnt[src] > (uint32_t)kFlatParkMax) mbits = 0; // this read goes to the exact path anyway
+                if (!CONTAIN && mbits && cnt[src] > (uint32_t)kFlatParkMax) mbits = 0; // this read goes to the exact path anyway
+                if (CONTAIN && mbits) {
+                    // only candidates that can be contained at this position are worth listing: read 1 longer, or equal
+                    // and earlier in the file (OverlapGraph.cpp:424, :449), and the window inside read 1 (:517-554)
+                    const int Lq = (int)cnt[src];
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        if (!((mbits >> q) & 1)) continue;
+                        const uint32_t rec = (uint32_t)v[q], r2 = rec >> 1;
+                        const int L2 = read_len(p.reads, r2);
+                        int use_rc, a, bb, nn;
+                        const bool ok = (Lq > L2 || (Lq == L2 && self < r2)) &&
+                                        contained_window(cand_type(rec & 1, (int)((v[q] >> 32) & 1) == fq), Lq, j, K, L2, &use_rc, &a, &bb, &nn);
+                        if (!ok) mbits &= ~(1u << q);
+                    }
+                }
             }
             const int c = __popc(mbits);
             int incl = c;
@@ -270,37 +292,47 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
                     } else if (lane == 0) {
                         atomicOr(p.stats + ST_OVERFLOW, 2ULL);
                     }
-                    if (c) atomicAdd(&cnt[src], (uint32_t)c);
+                    if (!CONTAIN && c) atomicAdd(&cnt[src], (uint32_t)c);
                     blk_cur += tot; seg_cnt += tot;
                 }
             }
             pushed = min(pushed + c, 15);
             bool cont = has && !hole;
-            if (cont && walked + 1 == kScanLimit) { atomicOr(&ctrl[0], 1u << src); cont = false; } // long chain: exact path
-            if (has && !cont && pushed > cap) atomicOr(&ctrl[0], 1u << src); // MAX_EDGE_PER_KMER may fire here: exact path
+            if (!CONTAIN) {
+                if (cont && walked + 1 == kScanLimit) { atomicOr(&ctrl[0], 1u << src); cont = false; } // long chain: exact path
+                if (has && !cont && pushed > cap) atomicOr(&ctrl[0], 1u << src); // MAX_EDGE_PER_KMER may fire here: exact path
+            } else if (cont && walked + 1 == 127) { // a chain longer than the queue entry can count (many copies of one read)
+                atomicOr(&ctrl[0], 1u << src);      // -> this batch is redone by the warp-per-read kernel
+                cont = false;
+            }
             const unsigned cm = __ballot_sync(FULL, cont); // (also orders this round's queue reads before the writes below)
             if (cont) {
                 const int pos = qn - n + __popc(cm & lt_mask);
                 qh[pos] = h;
-                qm[pos] = (meta & 0xFFFFF800u) | ((uint32_t)(walked + 1) << 8) | ((uint32_t)pushed << 4);
+                qm[pos] = (meta & 0xFFFFF800u) | ((uint32_t)(walked + 1) << 4) | (uint32_t)pushed;
             }
             qn = qn - n + __popc(cm);
             __syncwarp();
         };
 
         // (one loop for the position steps and the final drain of the queue, so that flush() is inlined once)
-        for (int j = 1; j < jtop || qn > 0; j++) {
+        // containment: positions [0, L1-K) (OverlapGraph.cpp:401) where some read can fit -- types 0/2 need j + L2 <= L1,
+        // types 1/3 need j >= L2 - K, and L2 >= min_len; edges: positions [1, L1-K) (:638)
+        const int fit_lo = L1 - p.reads.min_len, fit_hi = p.reads.min_len - K;
+        for (int j = CONTAIN ? 0 : 1; j < jtop || qn > 0; j++) {
             if (j < jtop) {
-                const int t = j + K - 1; // incoming base
-                if ((t & 31) == 0) wi = rw[t >> 5];
-                const uint64_t in = wi >> 62;
-                wi <<= 2;
-                slide_fwd<KW>(x, in, last_sh);
-                slide_rc<KW>(y, 3 - in, tmask);
+                if (j > 0) {
+                    const int t = j + K - 1; // incoming base
+                    if ((t & 31) == 0) wi = rw[t >> 5];
+                    const uint64_t in = wi >> 62;
+                    wi <<= 2;
+                    slide_fwd<KW>(x, in, last_sh);
+                    slide_rc<KW>(y, 3 - in, tmask);
+                }
                 bool pass = false;
                 uint64_t h = 0;
                 int fq = 0;
-                if (j < jmax) {
+                if (j < jmax && (!CONTAIN || j <= fit_lo || j >= fit_hi)) {
                     h = window_hash<KW>(x, y, seed, &fq);
                     n_probes++;
                     pass = filter_test(p.table, h);
@@ -325,6 +357,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
         __syncwarp();
         const uint32_t flagged = ctrl[0];
         uint32_t c = cnt[lane];
+        if (CONTAIN) {
+            // nothing to reserve: the verify kernel only takes minima.  A batch that could not be listed completely is
+            // flagged read by read for the warp-per-read kernel (the row infos are free until the edge pass).
+            const bool redo = dead || flagged != 0;
+            if (inrange && redo) p.rowinfo[r1] = kInfoExact;
+            if (lane < kFlatSegs) p.batchinfo[bi * kFlatSegs + lane] = (!redo && lane < nseg) ? segs[lane] : 0ULL;
+            __syncwarp();
+            continue;
+        }
         const bool exact = valid && (dead || ((flagged >> lane) & 1) || c > (uint32_t)kFlatParkMax);
         if (exact || !valid) c = 0;
         uint32_t incl = c;
@@ -528,6 +569,95 @@ __global__ void __launch_bounds__(kThreads, 2) k_verify_flat(SearchParams p)
     warp_stat_add(p.stats, ST_ENTRIES, n_entries);
     for (int o = 16; o; o >>= 1) { unsigned t = __shfl_xor_sync(FULL, maxdeg, o); if (t > maxdeg) maxdeg = t; }
     if (lane == 0 && maxdeg) atomicMax(p.stats + ST_MAXDEG, (unsigned long long)maxdeg);
+}
+
+// checkOverlapForContainedRead (OverlapGraph.cpp:517-554) for the candidates k_probe_flat<CONTAIN> listed: one lane per
+// candidate, two in flight; a verified containment elects the container with one atomicMin (dna.cuh: make_ckey).
+template <int NW>
+__global__ void __launch_bounds__(kThreads, 3) k_contain_verify_flat(SearchParams p)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int K = p.K;
+    const int WP = ((p.reads.max_len + 31) >> 5) + 2, PU = 2 * WP, QS = flat_query_u32(p.reads.max_len);
+    uint64_t *w0 = smem + wib * contain_flat_words_per_warp(p.reads.max_len);
+    uint32_t *qbase = reinterpret_cast<uint32_t *>(w0);
+    uint32_t *rlen = reinterpret_cast<uint32_t *>(w0 + ((size_t)32 * QS + 1) / 2);
+    const uint64_t nbatches = (p.q_hi - p.q_lo + 31) >> 5;
+    const uint64_t pol_stream = policy_evict_first();
+    unsigned n_verified = 0, n_hits = 0;
+    if (*reinterpret_cast<volatile unsigned long long *>(p.stats + ST_OVERFLOW)) return; // candidate lists incomplete: the pass is repeated
+    for (;;) {
+        unsigned long long bi = 0;
+        if (lane == 0) bi = atomicAdd(p.work_counter + 1, 1ULL);
+        bi = __shfl_sync(FULL, bi, 0);
+        if (bi >= nbatches) break;
+        const uint64_t mysegs = lane < kFlatSegs ? p.batchinfo[bi * kFlatSegs + lane] : 0ULL;
+        if (!__any_sync(FULL, mysegs != 0)) continue;
+        const uint64_t r0 = p.q_lo + (bi << 5), r1 = r0 + lane;
+        const bool inrange = r1 < p.q_hi;
+        uint32_t *A = qbase + lane * QS, *R = A + PU;
+        const int L1 = inrange ? read_len(p.reads, r1) : 0;
+        if (inrange) {
+            const int W = (L1 + 31) >> 5;
+            const uint64_t *src = p.reads.words + r1 * (uint64_t)p.reads.stride;
+            pstore(A, 0, 0ULL); pstore(R, 0, 0ULL);
+            for (int w = 1; w <= W; w++) pstore(A, w, __ldg(src + (w - 1)));
+            for (int w = W + 1; w < WP; w++) { pstore(A, w, 0ULL); pstore(R, w, 0ULL); }
+            for (int w = 1; w <= W; w++) pstore(R, w, rc_word(A, L1, W, w - 1));
+        }
+        rlen[lane] = (uint32_t)L1;
+        __syncwarp();
+        for (int sg = 0; sg < kFlatSegs; sg++) {
+            const uint64_t seg = __shfl_sync(FULL, mysegs, sg);
+            const uint32_t sn = (uint32_t)(seg & 0xFFFFF);
+            if (!sn) break;
+            const uint64_t *cl = p.cands + (seg >> 20);
+            for (uint32_t i0 = 0; i0 < sn; i0 += 64) {
+                uint64_t cd[2], v[2][NW];
+                int l2[2];
+                bool act[2];
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    const uint32_t i = i0 + 32 * u + lane;
+                    act[u] = i < sn;
+                    cd[u] = act[u] ? __ldg(cl + i) : 0ULL;
+                    l2[u] = 0;
+#pragma unroll
+                    for (int w = 0; w < NW; w++) v[u][w] = 0;
+                    if (act[u]) {
+                        const uint32_t r2 = cand_read(cd[u]);
+                        l2[u] = read_len(p.reads, r2);
+                        const uint64_t *row = p.reads.words + (uint64_t)r2 * (uint64_t)p.reads.stride;
+#pragma unroll
+                        for (int w = 0; w < NW / 2; w++)
+                            asm volatile("ld.global.nc.L2::cache_hint.L2::64B.v2.u64 {%0,%1}, [%2], %3;" : "=l"(v[u][2 * w]), "=l"(v[u][2 * w + 1]) : "l"(row + 2 * w), "l"(pol_stream));
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    if (!act[u]) continue;
+                    const uint32_t local = cand_local(cd[u]), r2 = cand_read(cd[u]);
+                    const uint64_t rq = r0 + local;
+                    const int j = cand_j(cd[u]), type = cand_type(cd[u]);
+                    const int Lq = (int)rlen[local], L2 = l2[u];
+                    // read1 must be longer, or equal and earlier in the file (OverlapGraph.cpp:424, :449)
+                    if (!(Lq > L2 || (Lq == L2 && rq < r2))) continue;
+                    n_verified++;
+                    int use_rc, a, b, n;
+                    if (!contained_window(type, Lq, j, K, L2, &use_rc, &a, &b, &n)) continue;
+                    const uint32_t *P = qbase + local * QS + (use_rc ? PU : 0);
+                    if (!match_regs<NW>(v[u], P, a, b, n, PU)) continue;
+                    n_hits++;
+                    const uint32_t rec = (uint32_t)(cd[u] >> 2);
+                    atomicMin(p.best + r2, (unsigned long long)make_ckey(rq, j, (int)(rec & 1), type));
+                }
+            }
+        }
+        __syncwarp();
+    }
+    warp_stat_add(p.stats, ST_VERIFIED, n_verified);
+    warp_stat_add(p.stats, ST_HITS, n_hits);
 }
 
 } // namespace disco

@@ -662,6 +662,7 @@ __global__ void __launch_bounds__(kThreads, (NW > 0 && NW <= 8) ? 4 : 1) k_searc
     while (grab_chunk(p.work_counter, p.q_lo, p.q_hi, lane, &rb, &re)) {
         for (uint64_t r1 = rb; r1 < re; r1++) {
             if (MODE == MODE_EDGES && ((__ldg(p.contained_bits + (r1 >> 5)) >> (r1 & 31)) & 1)) continue; // OverlapGraph.cpp:657
+            if (MODE == MODE_CONTAIN && p.only_flagged && !(p.rowinfo[r1] & kInfoExact)) continue;       // fall-back of the flat pass
             const int L1 = read_len(p.reads, r1);
             if (use_pre) {
                 // the words of this read were requested while the previous one was processed
@@ -1834,6 +1835,25 @@ static cudaError_t launch_search(const SearchParams &p_in, int num_sms, cudaStre
     return cudaGetLastError();
 }
 
+template <typename Kern>
+static cudaError_t launch_warps(Kern kern, const SearchParams &p, size_t per_warp_bytes, int num_sms, cudaStream_t s)
+{
+    const int warps = warps_that_fit(per_warp_bytes);
+    if (!warps) return cudaErrorInvalidConfiguration;
+    int grid = 0;
+    cudaError_t e = persistent_grid(kern, per_warp_bytes * warps, num_sms, &grid, warps * 32);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, warps * 32, per_warp_bytes * warps, s>>>(p);
+    DISCO_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+bool edges_flat_supported(int max_len, int stride, int K)
+{
+    if (getenv("DISCO_LEGACY_EDGES") || getenv("DISCO_FUSED")) return false; // the warp-per-read kernels, for A/B timing
+    return stride <= 8 && max_len <= 32 * stride && (K + 31) / 32 <= 4;
+}
+
 cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStream_t s)
 {
     const size_t per_warp = (size_t)64 * lane_array_u32(p.reads.max_len) * sizeof(uint32_t);
@@ -1861,26 +1881,39 @@ cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStre
 #undef DISCO_LAUNCH_CU
         return cudaGetLastError();
     }
+    if (p.cands && edges_flat_supported(p.reads.max_len, p.reads.stride, p.K)) {
+        // flat pass (edges_flat.cuh): probe<CONTAIN> lists the candidates of every 32-read batch, the verify kernel tests
+        // them one per lane; batches it could not list go through the warp-per-read kernel
+        const size_t pb = probe_flat_words_per_warp(p.reads.stride) * sizeof(uint64_t);
+        const size_t vb = contain_flat_words_per_warp(p.reads.max_len) * sizeof(uint64_t);
+        const bool sharded = p.table.world > 1;
+        cudaError_t e;
+#define DISCO_LAUNCH_PC(KWV)                                                                                      \
+    e = sharded ? launch_warps(k_probe_flat<KWV, true, true>, p, pb, num_sms, s) : launch_warps(k_probe_flat<KWV, false, true>, p, pb, num_sms, s); \
+    break;
+        switch ((p.K + 31) / 32) {
+        case 1: DISCO_LAUNCH_PC(1)
+        case 2: DISCO_LAUNCH_PC(2)
+        case 3: DISCO_LAUNCH_PC(3)
+        default: DISCO_LAUNCH_PC(4)
+        }
+#undef DISCO_LAUNCH_PC
+        if (e != cudaSuccess) return e;
+        switch ((words + 1) / 2) {
+        case 1: e = launch_warps(k_contain_verify_flat<2>, p, vb, num_sms, s); break;
+        case 2: e = launch_warps(k_contain_verify_flat<4>, p, vb, num_sms, s); break;
+        case 3: e = launch_warps(k_contain_verify_flat<6>, p, vb, num_sms, s); break;
+        default: e = launch_warps(k_contain_verify_flat<8>, p, vb, num_sms, s); break;
+        }
+        if (e != cudaSuccess) return e;
+        SearchParams q = p;
+        q.only_flagged = 1;
+        q.work_counter = p.work_counter + 2;
+        return launch_search<MODE_CONTAIN>(q, num_sms, s);
+    }
     return launch_search<MODE_CONTAIN>(p, num_sms, s);
 }
-template <typename Kern>
-static cudaError_t launch_warps(Kern kern, const SearchParams &p, size_t per_warp_bytes, int num_sms, cudaStream_t s)
-{
-    const int warps = warps_that_fit(per_warp_bytes);
-    if (!warps) return cudaErrorInvalidConfiguration;
-    int grid = 0;
-    cudaError_t e = persistent_grid(kern, per_warp_bytes * warps, num_sms, &grid, warps * 32);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, warps * 32, per_warp_bytes * warps, s>>>(p);
-    DISCO_COUNT_LAUNCH();
-    return cudaGetLastError();
-}
 
-bool edges_flat_supported(int max_len, int stride, int K)
-{
-    if (getenv("DISCO_LEGACY_EDGES") || getenv("DISCO_FUSED")) return false; // the warp-per-read kernels, for A/B timing
-    return stride <= 8 && max_len <= 32 * stride && (K + 31) / 32 <= 4;
-}
 
 uint64_t edges_flat_slack(int num_sms) { return (uint64_t)num_sms * 5 * kWarps * kFlatSlice; }
 
@@ -1895,7 +1928,7 @@ static cudaError_t launch_edges_flat(SearchParams &p, int num_sms, cudaStream_t 
     const bool sect = p.reads.tails != nullptr && p.reads.uniform_len > 128 && p.reads.stride == 8; // two sectors per row
     cudaError_t e;
 #define DISCO_LAUNCH_P(KWV)                                                                                       \
-    e = sharded ? launch_warps(k_probe_flat<KWV, true>, p, pb, num_sms, s) : launch_warps(k_probe_flat<KWV, false>, p, pb, num_sms, s); \
+    e = sharded ? launch_warps(k_probe_flat<KWV, true, false>, p, pb, num_sms, s) : launch_warps(k_probe_flat<KWV, false, false>, p, pb, num_sms, s); \
     break;
     switch ((p.K + 31) / 32) {
     case 1: DISCO_LAUNCH_P(1)

@@ -62,6 +62,7 @@ struct SearchParams {
     unsigned long long *best; // n keys, ~0 = not contained
     // edge pass
     const uint32_t *contained_bits;
+    int only_flagged;   // containment, warp-per-read kernel as the fall-back of the flat one: only reads whose row info says so
     int skip_contained; // the table still holds contained reads (built once): drop them as candidates (HashTable.cpp:533)
     uint64_t *rows;
     uint64_t rows_cap;

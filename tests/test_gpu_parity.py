@@ -132,3 +132,21 @@ def test_all_identical_reads():
         assert len(res.edges) == 0
     finally:
         bg.close()
+
+
+def test_many_copies_with_a_shorter_read():
+    """700 copies of one read plus a truncated one: reads of two lengths take the flat containment kernels, and the 175-bucket
+    chain of the copies' k-mer is longer than a queued probe can count -- those batches fall back to the warp-per-read
+    kernel.  Everything but the first copy is contained in it (OverlapGraph.cpp:424, :449)."""
+    s = synth.single_genome(1, 150, 1.0, seed=43).strings()[0]
+    recs = [s] * 700 + [s[10:130]]
+    o = oracle_forms(recs, 50)
+    bg = BuildGraph(min_overlap=50)
+    bg.add_records(recs)
+    res = bg.run()
+    try:
+        assert len(res.crows) == 700 and set(res.crows["container"]) == {0}
+        assert bg.crow_lines() == o["crows"]
+        assert len(res.edges) == 0
+    finally:
+        bg.close()
