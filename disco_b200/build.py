@@ -29,7 +29,7 @@ def _run(cmd, verbose):
 
 
 def build_gpu(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "api.cu")]
+    srcs = [os.path.join(CSRC, f) for f in ("kernels.cu", "api.cu", "simplify.cu")]
     deps = srcs + [os.path.join(CSRC, f) for f in ("dna.cuh", "kernels.cuh", "edges_flat.cuh")] + [os.path.join(ROOT, "include", "disco_gpu.h")]
     if force or _newer(GPU_LIB, deps):
         nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

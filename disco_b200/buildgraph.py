@@ -74,6 +74,25 @@ class BuildGraph:
             out.append(f"{int(res.file_index[c])}\t{int(res.file_index[k])}\t{int(r['orient'])},{l2},0,0,{l2},0,{l2},{l1},{st},{st + l2}")
         return out
 
+    def simplified_lines(self, min_overlap: int = 0, min_reads: int = 5, min_len: int = 500):
+        """parsimplify's output lines (OverlapGraphSimple.cpp:658-690) computed on the GPU from the edges still in HBM:
+        `src \t dst \t orient,offset,length,0,0 \t (read,strand,offset)...`, ids as file indices."""
+        res = self.result
+        e, inner, st = self._g.simplify(min_overlap, min_reads, min_len)
+        fi, lens = res.file_index, res.lens
+        rid = (inner & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        off = ((inner >> np.uint64(32)) & np.uint64(0x7FFFFFFF)).astype(np.int64)
+        strand = (inner >> np.uint64(63)).astype(np.int64)
+        out = []
+        for r in e:
+            s, d = int(r["src"]), int(r["dst"])
+            a, k = int(r["inner_start"]), int(r["n_inner"])
+            tail = "".join(f"({int(fi[rid[i]])},{int(strand[i])},{int(off[i])})" for i in range(a, a + k))
+            total = int(r["offset_total"])
+            out.append(f"{int(fi[s])}\t{int(fi[d])}\t{int(r['orient'])},{total},{total + int(lens[d])},0,0\t{tail}")
+        self.simplify_stats = st
+        return out
+
     def write(self, prefix: str, shards: int = 1):
         """Writes the files runDisco.sh expects for -n <shards>: all edges go to shard 0 with mark
         flag 2, the other shards are created empty."""

@@ -71,6 +71,11 @@ struct disco_ctx {
     // output
     disco_edge *d_edges = nullptr;
     uint64_t edges_cap = 0, n_edges = 0;
+    // simplified graph (disco_gpu_simplify)
+    disco_cedge *d_cedges = nullptr;
+    uint64_t *d_inner = nullptr;
+    uint64_t n_cedges = 0, n_inner = 0, simp_rounds = 0, simp_removed = 0, simp_cycle = 0;
+    float simp_ms = 0.f;
     // counters / stats
     unsigned long long *d_cursors = nullptr;  // CUR_COUNT
     unsigned long long *d_stats_c = nullptr;  // containment pass
@@ -149,7 +154,8 @@ void free_run_buffers(disco_ctx *c)
     c->own_slots = c->own_rows = true;
     c->peer_table.ready = c->peer_rows.ready = false; // whatever the peers mapped is gone
     dfree(c->d_filter); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
-    dfree(c->d_rowinfo); dfree(c->d_edges); dfree(c->d_cands); dfree(c->d_batchinfo);
+    dfree(c->d_rowinfo); dfree(c->d_edges); dfree(c->d_cands); dfree(c->d_batchinfo); dfree(c->d_cedges); dfree(c->d_inner);
+    c->n_cedges = c->n_inner = 0;
     c->d_rows_active = nullptr;
     c->rows_cap = c->edges_cap = c->crows_cap = c->run_n = c->cands_cap = c->batch_cap = 0;
     c->begun = c->have_contained = c->have_edges = c->have_reduced = false;
@@ -1017,6 +1023,53 @@ int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, ui
         CK(cudaStreamSynchronize(ctx->stream));
     }
     if (n_written) *n_written = ctx->n_edges;
+    return DISCO_OK;
+}
+
+// ---- first consumer step on the device-resident edges (simplify.cu) ----------------------------------------------------
+int disco_gpu_simplify(disco_ctx *ctx, uint32_t min_overlap, uint32_t min_reads, uint32_t min_len, uint64_t *n_edges, uint64_t *n_inner)
+{
+    if (!ctx || !ctx->have_reduced) return fail(ctx, DISCO_E_ARG, "reduction not finished");
+    if (ctx->shard_world > 1) return fail(ctx, DISCO_E_ARG, "simplify works on one context's complete edge set (single-GPU runs)");
+    CK(cudaSetDevice(ctx->device));
+    dfree(ctx->d_cedges); dfree(ctx->d_inner);
+    ctx->n_cedges = ctx->n_inner = 0;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+    unsigned long long launches = 0;
+    const cudaError_t e = run_simplify(ctx->d_edges, ctx->n_edges, ctx->reads.n, ctx->d_len, ctx->reads.uniform_len, min_overlap, min_reads, min_len,
+                                       ctx->stream, &ctx->d_cedges, &ctx->n_cedges, &ctx->d_inner, &ctx->n_inner, &ctx->simp_rounds,
+                                       &ctx->simp_removed, &ctx->simp_cycle, &launches);
+    count_launches(launches);
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ctx->simp_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? DISCO_E_NOMEM : DISCO_E_CUDA, "simplify failed: %s", cudaGetErrorString(e));
+    if (n_edges) *n_edges = ctx->n_cedges;
+    if (n_inner) *n_inner = ctx->n_inner;
+    return DISCO_OK;
+}
+
+int disco_gpu_get_simplified(disco_ctx *ctx, disco_cedge *edges, uint64_t edge_capacity, uint64_t *inner, uint64_t inner_capacity)
+{
+    if (!ctx || !ctx->d_cedges) return fail(ctx, DISCO_E_ARG, "call disco_gpu_simplify first");
+    if (edge_capacity < ctx->n_cedges || inner_capacity < ctx->n_inner) return fail(ctx, DISCO_E_ARG, "capacity too small");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->n_cedges) CK(cudaMemcpyAsync(edges, ctx->d_cedges, ctx->n_cedges * sizeof(disco_cedge), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->n_inner) CK(cudaMemcpyAsync(inner, ctx->d_inner, ctx->n_inner * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DISCO_OK;
+}
+
+int disco_gpu_simplify_stats(disco_ctx *ctx, uint64_t *rounds, uint64_t *removed_edges, uint64_t *cycle_edges, float *ms)
+{
+    if (!ctx) return DISCO_E_ARG;
+    if (rounds) *rounds = ctx->simp_rounds;
+    if (removed_edges) *removed_edges = ctx->simp_removed;
+    if (cycle_edges) *cycle_edges = ctx->simp_cycle;
+    if (ms) *ms = ctx->simp_ms;
     return DISCO_OK;
 }
 

@@ -14,7 +14,7 @@
 //                  flight): 64-byte row fetch, windowed 2-bit compare, survivors scattered into their read's row.
 //
 // Everything that needs the reference's sequential semantics -- a position with more than `cap` partners, a neighbour
-// reached through two positions (OverlapGraph.cpp:656), a chain longer than kScanLimit, more than kFlatParkMax
+// reached through two positions (OverlapGraph.cpp:656), a chain of more than kFlatWalkMax buckets, more than kFlatParkMax
 // candidates -- only FLAGS the read here; k_edges_exact then redoes it exactly as the reference inserts.
 #pragma once
 
@@ -26,6 +26,7 @@ constexpr int kFlatParkMax = 1024;  // candidates one read may have before it is
 constexpr int kFlatSet = 2048;      // slots of the verify kernel's (read, neighbour) set
 constexpr int kFlatGroupMax = 1400; // candidates verified against one filling of that set
 constexpr int kFlatSegs = 4;        // segments a batch's candidate list may consist of
+constexpr int kFlatWalkMax = 127;   // buckets of one chain a queued probe may walk (7 bits of its queue entry)
 
 // candidate: [63..59 read within the batch][58..44 position j][33..2 record][1..0 type]
 __device__ __forceinline__ uint64_t make_cand(uint32_t local, int j, uint32_t rec, int type)
@@ -298,13 +299,12 @@ __global__ void __launch_bounds__(kThreads, 4) k_probe_flat(SearchParams p)
             }
             pushed = min(pushed + c, 15);
             bool cont = has && !hole;
-            if (!CONTAIN) {
-                if (cont && walked + 1 == kScanLimit) { atomicOr(&ctrl[0], 1u << src); cont = false; } // long chain: exact path
-                if (has && !cont && pushed > cap) atomicOr(&ctrl[0], 1u << src); // MAX_EDGE_PER_KMER may fire here: exact path
-            } else if (cont && walked + 1 == 127) { // a chain longer than the queue entry can count (many copies of one read)
-                atomicOr(&ctrl[0], 1u << src);      // -> this batch is redone by the warp-per-read kernel
-                cont = false;
-            }
+            // A chain longer than the queue entry can count (very many copies of one k-mer): containment redoes the batch
+            // with the warp-per-read kernel, the edge pass leaves the read to the exact path.  (Long chains as such are no
+            // reason for the exact path here -- a re-queued probe costs one more lane slot; with the contained reads still
+            // in the table, duplicate-rich data has many chains of a dozen buckets.)
+            if (cont && walked + 1 == kFlatWalkMax) { atomicOr(&ctrl[0], 1u << src); cont = false; }
+            if (!CONTAIN && has && !cont && pushed > cap) atomicOr(&ctrl[0], 1u << src); // MAX_EDGE_PER_KMER may fire here: exact path
             const unsigned cm = __ballot_sync(FULL, cont); // (also orders this round's queue reads before the writes below)
             if (cont) {
                 const int pos = qn - n + __popc(cm & lt_mask);

@@ -1707,6 +1707,7 @@ static int wp_of(int max_len) { return ((max_len + 31) >> 5) + 2; }
 
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long launches_total() { return g_launches.load(); }
+void count_launches(unsigned long long k) { g_launches.fetch_add(k, std::memory_order_relaxed); }
 #define DISCO_COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 constexpr size_t kSmemBudget = 200 * 1024; // per block; leaves room for the driver's reservation out of 227 KB

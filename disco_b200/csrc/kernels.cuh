@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "../../include/disco_gpu.h"
 
 namespace disco {
 
@@ -132,6 +133,12 @@ bool search_edges_fits(int max_len, int K, int cap);
 bool edges_flat_supported(int max_len, int stride, int K);
 // candidate-buffer entries the flat probe kernel may leave unused (one partly filled slice per resident warp)
 uint64_t edges_flat_slack(int num_sms);
+// simplify.cu: composite-edge contraction + dead-end removal on a reduced edge list; allocates *d_out / *d_inner (cudaFree)
+cudaError_t run_simplify(const disco_edge *d_edges, uint64_t ne, uint64_t n_reads, const uint16_t *d_len, int uniform_len,
+                         uint32_t min_ovl, uint32_t min_reads, uint32_t min_len, cudaStream_t s,
+                         disco_cedge **d_out, uint64_t *n_out, uint64_t **d_inner, uint64_t *n_inner, uint64_t *rounds, uint64_t *removed_edges,
+                         uint64_t *cycle_atoms, unsigned long long *launches);
+void count_launches(unsigned long long k);
 // kernels launched by this library since it was loaded (every launcher counts its own)
 unsigned long long launches_total();
 

@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(PKG, "libdisco_gpu.so")
 
 EDGE_DTYPE = np.dtype([("src", "<u4"), ("dst", "<u4"), ("offset", "<u4"), ("orient", "<u4")])
 CROW_DTYPE = np.dtype([("contained", "<u4"), ("container", "<u4"), ("orient", "<u4"), ("start", "<u4")])
+CEDGE_DTYPE = np.dtype([("src", "<u4"), ("dst", "<u4"), ("orient", "<u4"), ("n_inner", "<u4"), ("offset_total", "<u8"), ("inner_start", "<u8")])
 
 EXPORTS = [
     "disco_gpu_create", "disco_gpu_destroy", "disco_gpu_last_error", "disco_gpu_set_stream", "disco_gpu_load_reads",
@@ -22,7 +23,7 @@ EXPORTS = [
     "disco_gpu_set_rows_used", "disco_gpu_use_rows", "disco_gpu_phase_edges_part", "disco_gpu_phase_reduce_mark",
     "disco_gpu_phase_reduce_emit", "disco_gpu_set_shard", "disco_gpu_export_mem", "disco_gpu_import_peers",
     "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table", "disco_gpu_table_words", "disco_gpu_adopt_buffer",
-    "disco_gpu_build_graph_multi", "disco_gpu_device_count", "disco_gpu_set_partition", "disco_gpu_compact_keys", "disco_gpu_apply_keys",
+    "disco_gpu_build_graph_multi", "disco_gpu_device_count", "disco_gpu_set_partition", "disco_gpu_compact_keys", "disco_gpu_apply_keys", "disco_gpu_simplify", "disco_gpu_get_simplified", "disco_gpu_simplify_stats",
 ]
 MAX_SHARDS, IPC_HANDLE_BYTES, MEM_TABLE, MEM_ROWS = 8, 64, 0, 1
 
@@ -80,6 +81,9 @@ def lib():
         L.disco_gpu_set_shard.argtypes = [vp, u32, u32]
         L.disco_gpu_set_partition.argtypes = [vp, u32, u32, i32]
         L.disco_gpu_compact_keys.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.disco_gpu_simplify.argtypes = [vp, u32, u32, u32, C.POINTER(u64), C.POINTER(u64)]
+        L.disco_gpu_get_simplified.argtypes = [vp, vp, u64, vp, u64]
+        L.disco_gpu_simplify_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float)]
         L.disco_gpu_apply_keys.argtypes = [vp, vp, u64]
         L.disco_gpu_export_mem.argtypes = [vp, i32, vp]
         L.disco_gpu_import_peers.argtypes = [vp, i32, vp, vp]
@@ -289,6 +293,18 @@ class GpuBuildGraph:
         w = C.c_uint64()
         self._ck(self._L.disco_gpu_get_edges(self._h, out.ctypes.data, len(out), C.byref(w)), "get_edges")
         return out[:w.value]
+
+    def simplify(self, min_overlap: int = 0, min_reads: int = 5, min_len: int = 500):
+        """parsimplify's composite-edge contraction + dead-end removal on the device-resident reduced edges (defaults:
+        Config.cpp:43-44).  Returns (edges CEDGE_DTYPE, inner u64 [read | offset << 32 | strand << 63], stats dict)."""
+        ne, ni = C.c_uint64(), C.c_uint64()
+        self._ck(self._L.disco_gpu_simplify(self._h, min_overlap, min_reads, min_len, C.byref(ne), C.byref(ni)), "simplify")
+        e = np.zeros(ne.value, dtype=CEDGE_DTYPE)
+        inner = np.zeros(ni.value, dtype=np.uint64)
+        self._ck(self._L.disco_gpu_get_simplified(self._h, e.ctypes.data, len(e), inner.ctypes.data, len(inner)), "get_simplified")
+        r, rm, cy, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_float()
+        self._ck(self._L.disco_gpu_simplify_stats(self._h, C.byref(r), C.byref(rm), C.byref(cy), C.byref(ms)), "simplify_stats")
+        return e, inner, {"rounds": r.value, "removed_edges": rm.value, "cycle_edges": cy.value, "ms": ms.value}
 
     def row(self, read: int, capacity: int = 1 << 16) -> np.ndarray:
         out = np.zeros(capacity, dtype=EDGE_DTYPE)

@@ -78,6 +78,16 @@ typedef struct {
                                                              * whatever the caller did between the phases) */
 } disco_stats;
 
+/* One edge of the simplified graph (parsimplify's output, src/SimplifyGraph/src/OverlapGraphSimple.cpp:658-690): a maximal
+ * chain of reduced edges through nodes with exactly one way in and one way out, written from its smaller end.  The
+ * n_inner reads it swallowed are inner[inner_start ..], each (read | overlap offset << 32 | strand << 63) as in the
+ * reference's packed list (EdgeSimple.cpp:226-230); edge length = offset_total + len(dst). */
+typedef struct {
+    uint32_t src, dst, orient, n_inner;
+    uint64_t offset_total;
+    uint64_t inner_start;
+} disco_cedge;
+
 /* number of CUDA devices this process can use (0 when there is none or the driver is missing); `buildG -g all` */
 int disco_gpu_device_count(void);
 /* ---- life cycle ---------------------------------------------------------------------------------------------- */
@@ -108,6 +118,19 @@ int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, ui
 /* unreduced adjacency of one read (its own capped search, sorted by offset): for tests of the cap semantics */
 int disco_gpu_get_row(disco_ctx *ctx, uint64_t read, disco_edge *out, uint64_t capacity, uint64_t *n_written);
 int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out);
+
+/* ---- the first consumer step, on the edges still in HBM: parsimplify's composite-edge contraction and
+ * dead-end removal (OverlapGraphSimple.cpp:236-244: contract, then { contract; remove dead ends } until nothing changes).
+ * min_overlap: edges with a shorter overlap are dropped first (:572); min_reads / min_len: a (composite) edge with at least
+ * that many inner reads / that long keeps its end nodes from being dead ends (Config.cpp:43-44: 5 and 500).  Needs
+ * disco_gpu_build_graph (or phase_reduce) to have run; single-GPU result sets (every edge in this context). */
+int disco_gpu_simplify(disco_ctx *ctx, uint32_t min_overlap, uint32_t min_reads, uint32_t min_len,
+                       uint64_t *n_edges, uint64_t *n_inner);
+int disco_gpu_get_simplified(disco_ctx *ctx, disco_cedge *edges, uint64_t edge_capacity, uint64_t *inner, uint64_t inner_capacity);
+/* rounds of contraction + dead-end removal, reduced edges removed with dead-end nodes, edges of closed chains (isolated
+ * cycles: written unmerged -- the reference breaks them wherever its node order starts) and device milliseconds of the
+ * last disco_gpu_simplify */
+int disco_gpu_simplify_stats(disco_ctx *ctx, uint64_t *rounds, uint64_t *removed_edges, uint64_t *cycle_edges, float *ms);
 
 /* ---- phase-level entry points (multi-GPU: query reads sharded by id, table and reads replicated; mirrors
  * BuildGraphMPI/src/OverlapGraph.cpp:524-529 and :293-295).  disco_gpu_build_graph() == the sequence
