@@ -338,6 +338,7 @@ def measure(args, workload, reads_per_gpu, world, rank, local, primary):
         nc, ne = g.counts()
         if h_edges is None or h_edges.shape[0] < ne:
             h_edges = torch.empty((int(ne * 1.1) + 16, 4), dtype=torch.int32).pin_memory()
+            g.set_edge_sink(h_edges.data_ptr(), h_edges.shape[0])   # from the next call on the emission kernel fills it itself
         if h_crows is None or h_crows.shape[0] < nc:
             h_crows = torch.empty((int(nc * 1.1) + 16, 4), dtype=torch.int32).pin_memory()
         e = g.edges(out=h_edges.numpy().view(gpu.EDGE_DTYPE).reshape(-1))
@@ -435,6 +436,16 @@ def measure(args, workload, reads_per_gpu, world, rank, local, primary):
         dist.broadcast(ok, 0)
         good_everywhere = bool(int(ok[0]))
     else:
+        # next row of the scope table, outside the timed region: parsimplify's contraction + dead-end removal on
+        # the edges still in HBM (parity: tests/test_simplify_gpu.py against the reference parsimplify)
+        simplify = None
+        try:
+            ce, inner, sst = g.simplify(MIN_OVERLAP)
+            simplify = {"ms": float(sst["ms"]), "rounds": int(sst["rounds"]), "composite_edges": int(len(ce)), "inner_reads": int(len(inner)),
+                        "reduced_edges_in": int(st["n_edges"]), "removed_with_dead_ends": int(sst["removed_edges"]),
+                        "longest_edge_bases": int((ce["offset_total"]).max()) + READ_LEN if len(ce) else 0}
+        except Exception as e:
+            simplify = {"error": str(e)}
         g.close()
         good_everywhere = True
 
@@ -505,6 +516,8 @@ def measure(args, workload, reads_per_gpu, world, rank, local, primary):
     }
     if parity is not None:
         line["parity_check"] = parity
+    if world == 1 and simplify is not None:
+        line["simplify_next_row"] = simplify
     del d_packed, d_lens
     torch.cuda.empty_cache()
     return line, good_everywhere

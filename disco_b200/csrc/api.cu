@@ -71,6 +71,10 @@ struct disco_ctx {
     // output
     disco_edge *d_edges = nullptr;
     uint64_t edges_cap = 0, n_edges = 0;
+    // optional result sink: the caller's pinned host buffer, filled by the emission kernel itself (no D2H copy afterwards)
+    disco_edge *sink_host = nullptr, *sink_dev = nullptr;
+    uint64_t sink_cap = 0;
+    bool sink_filled = false;
     // simplified graph (disco_gpu_simplify)
     disco_cedge *d_cedges = nullptr;
     uint64_t *d_inner = nullptr;
@@ -701,6 +705,8 @@ int disco_gpu_phase_reduce_emit(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
         // the emission kernel's own counters: zeroed per attempt, so that a retry after an edge-buffer overflow counts once
         CK(cudaMemsetAsync(ctx->d_stats_e + ST_MULTI_OVERLAP, 0, (ST_COUNT - ST_MULTI_OVERLAP) * sizeof(unsigned long long), ctx->stream));
         p.edges_out = ctx->d_edges; p.edges_cap = ctx->edges_cap; p.edges_cursor = ctx->d_cursors + CUR_EDGES;
+        p.edges_out2 = ctx->sink_dev; p.edges_cap2 = ctx->sink_cap;
+        ctx->sink_filled = false;
         if ((rc = record(ctx, EV_EMIT_K0))) return rc;
         if (u_hi > u_lo && ctx->stats.raw_directed_edges) CK(launch_reduce_emit(p, ctx->num_sms, ctx->stream));
         if ((rc = record(ctx, EV_EMIT))) return rc;
@@ -714,6 +720,7 @@ int disco_gpu_phase_reduce_emit(disco_ctx *ctx, uint64_t u_lo, uint64_t u_hi)
         CK(cudaMalloc(&ctx->d_edges, ne * sizeof(disco_edge)));
         ctx->edges_cap = ne;
     }
+    ctx->sink_filled = ctx->sink_dev != nullptr && ctx->n_edges <= ctx->sink_cap;
     ctx->stats.n_edges = ctx->n_edges;
     ctx->have_reduced = true;
     return DISCO_OK;
@@ -1018,7 +1025,7 @@ int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, ui
     if (!ctx || !ctx->have_reduced) return fail(ctx, DISCO_E_ARG, "reduction not finished");
     if (capacity < ctx->n_edges) return fail(ctx, DISCO_E_ARG, "capacity too small");
     CK(cudaSetDevice(ctx->device));
-    if (ctx->n_edges) {
+    if (ctx->n_edges && !(edges == ctx->sink_host && ctx->sink_filled)) { // (the sink already holds them: the kernel wrote it)
         CK(cudaMemcpyAsync(edges, ctx->d_edges, ctx->n_edges * sizeof(disco_edge), cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -1070,6 +1077,21 @@ int disco_gpu_simplify_stats(disco_ctx *ctx, uint64_t *rounds, uint64_t *removed
     if (removed_edges) *removed_edges = ctx->simp_removed;
     if (cycle_edges) *cycle_edges = ctx->simp_cycle;
     if (ms) *ms = ctx->simp_ms;
+    return DISCO_OK;
+}
+
+// The emission kernel writes every kept edge to this pinned host buffer as well (over PCIe, while it runs), so that the
+// device-to-host copy of the result is off the critical path: disco_gpu_get_edges(ctx, host_pinned, ...) then returns at
+// once.  NULL clears it.  A result larger than the capacity is simply not mirrored (get_edges copies as usual).
+int disco_gpu_set_edge_sink(disco_ctx *ctx, disco_edge *host_pinned, uint64_t capacity)
+{
+    if (!ctx) return DISCO_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    ctx->sink_host = ctx->sink_dev = nullptr; ctx->sink_cap = 0; ctx->sink_filled = false;
+    if (!host_pinned || !capacity) return DISCO_OK;
+    void *dp = nullptr;
+    if (cudaHostGetDevicePointer(&dp, host_pinned, 0) != cudaSuccess) { cudaGetLastError(); return fail(ctx, DISCO_E_ARG, "edge sink must be page-locked host memory (cudaHostAlloc / cudaHostRegister)"); }
+    ctx->sink_host = host_pinned; ctx->sink_dev = static_cast<disco_edge *>(dp); ctx->sink_cap = capacity;
     return DISCO_OK;
 }
 

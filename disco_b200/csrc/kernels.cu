@@ -1606,6 +1606,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_reduce_emit(ReduceParams p) // 
 {
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     disco_edge *out = reinterpret_cast<disco_edge *>(p.edges_out);
+    disco_edge *out2 = reinterpret_cast<disco_edge *>(p.edges_out2);
     __shared__ disco_edge ebuf_all[kWarps][32]; // kept edges are staged per warp: one global atomic per 32 edges
     disco_edge *ebuf = ebuf_all[wib];
     int nbuf = 0;                               // warp-uniform
@@ -1678,6 +1679,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_reduce_emit(ReduceParams p) // 
                             if (lane == 0) pos = atomicAdd(p.edges_cursor, 32ULL);
                             pos = __shfl_sync(FULL, pos, 0);
                             if (pos + lane < p.edges_cap) out[pos + lane] = ebuf[lane];
+                            if (out2 && pos + lane < p.edges_cap2) out2[pos + lane] = ebuf[lane];
                             __syncwarp();
                             nbuf = 0;
                         }
@@ -1692,6 +1694,7 @@ __global__ void __launch_bounds__(kThreads, 8) k_reduce_emit(ReduceParams p) // 
         if (lane == 0) pos = atomicAdd(p.edges_cursor, (unsigned long long)nbuf);
         pos = __shfl_sync(FULL, pos, 0);
         if (lane < nbuf && pos + lane < p.edges_cap) out[pos + lane] = ebuf[lane];
+        if (out2 && lane < nbuf && pos + lane < p.edges_cap2) out2[pos + lane] = ebuf[lane];
     }
     warp_stat_add(p.stats, ST_EMIT_ROWS, n_rows);
     warp_stat_add(p.stats, ST_EMIT_ENTRIES, n_ent);

@@ -99,6 +99,8 @@ struct ReduceParams {
     // emit
     void *edges_out;       // disco_edge[edges_cap]
     uint64_t edges_cap;
+    void *edges_out2;      // optional second destination (the caller's pinned host buffer, written over PCIe while the kernel runs)
+    uint64_t edges_cap2;
     unsigned long long *edges_cursor;
 };
 

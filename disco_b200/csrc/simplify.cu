@@ -18,12 +18,23 @@
 #include "../../include/disco_gpu.h"
 #include "dna.cuh"
 #include "kernels.cuh"
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cub/device/device_scan.cuh>
 
 namespace disco {
 
 namespace {
+
+// one half-edge's view of its chain: successor, last atom, atoms and offset sum up to the end -- one 32-byte sector, so
+// that a pointer-jumping step costs one random access per half-edge
+struct __align__(32) SLink {
+    int32_t nxt, last;
+    uint32_t cnt, pad;
+    uint64_t sum, pad2;
+};
 
 __device__ __forceinline__ int twin_o(int o) { return ((o >> 1) ^ 1) | (((o & 1) ^ 1) << 1); } // EdgeSimple.cpp:261-267
 __device__ __forceinline__ int rlen_of(const uint16_t *len, int uniform, uint32_t r) { return uniform ? uniform : (int)len[r]; }
@@ -79,7 +90,7 @@ __global__ void k_s_nodes(uint64_t n, const uint64_t *row, const uint32_t *adj, 
 
 // chain links: the half-edge that continues h through a contractible destination
 __global__ void k_s_links(uint64_t nh, const uint32_t *a_dst, const uint32_t *a_off, const uint8_t *alive, const uint8_t *contractible,
-                          const int32_t *slot, int32_t *nxt, uint32_t *cnt, uint64_t *sum, int32_t *last)
+                          const int32_t *slot, SLink *L)
 {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= nh) return;
@@ -88,23 +99,24 @@ __global__ void k_s_links(uint64_t nh, const uint32_t *a_dst, const uint32_t *a_
         const uint32_t y = a_dst[h];
         if (contractible[y]) nx = slot[2 * y] == (int32_t)(h ^ 1) ? slot[2 * y + 1] : slot[2 * y];
     }
-    nxt[h] = nx; cnt[h] = 1; sum[h] = a_off[h]; last[h] = (int32_t)h;
+    SLink l;
+    l.nxt = nx; l.last = (int32_t)h; l.cnt = 1; l.pad = 0; l.sum = a_off[h]; l.pad2 = 0;
+    L[h] = l;
 }
 
-// one pointer-jumping step (ping-pong buffers); *active counts the half-edges that still have a successor
-__global__ void k_s_jump(uint64_t nh, const int32_t *nxt, const uint32_t *cnt, const uint64_t *sum, const int32_t *last,
-                         int32_t *nxt2, uint32_t *cnt2, uint64_t *sum2, int32_t *last2, unsigned long long *active)
+// one pointer-jumping step (ping-pong buffers); *active counts the warps that still hold a half-edge with a successor
+__global__ void k_s_jump(uint64_t nh, const SLink *L, SLink *L2, unsigned long long *active)
 {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool more = false;
     if (h < nh) {
-        const int32_t n1 = nxt[h];
-        if (n1 < 0) { nxt2[h] = -1; cnt2[h] = cnt[h]; sum2[h] = sum[h]; last2[h] = last[h]; }
-        else {
-            const int32_t n2 = nxt[n1];
-            nxt2[h] = n2; cnt2[h] = cnt[h] + cnt[n1]; sum2[h] = sum[h] + sum[n1]; last2[h] = last[n1];
-            more = n2 >= 0;
+        SLink a = L[h];
+        if (a.nxt >= 0) {
+            const SLink b = L[a.nxt];
+            a.nxt = b.nxt; a.last = b.last; a.cnt += b.cnt; a.sum += b.sum;
+            more = b.nxt >= 0;
         }
+        L2[h] = a;
     }
     const unsigned m = __ballot_sync(0xffffffffu, more);
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(active, 1ULL);
@@ -113,8 +125,8 @@ __global__ void k_s_jump(uint64_t nh, const int32_t *nxt, const uint32_t *cnt, c
 // removeParDeadEndNodes (:135-218) on the chain aggregates: a node all of whose (composite) edges are short, are no loops
 // and point the same way
 __global__ void k_s_deadends(uint64_t n, const uint64_t *row, const uint32_t *adj, const uint8_t *alive, const uint8_t *contractible,
-                             const uint32_t *a_dst, const uint8_t *a_or, const int32_t *nxt, const uint32_t *cnt, const uint64_t *sum,
-                             const int32_t *last, const uint16_t *len, int uniform, uint32_t min_reads, uint32_t min_len, uint8_t *dead)
+                             const uint32_t *a_dst, const uint8_t *a_or, const SLink *L, const uint16_t *len, int uniform,
+                             uint32_t min_reads, uint32_t min_len, uint8_t *dead)
 {
     const uint64_t v = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n) return;
@@ -125,10 +137,11 @@ __global__ void k_s_deadends(uint64_t n, const uint64_t *row, const uint32_t *ad
         for (uint64_t k = row[v]; k < row[v + 1] && !good; k++) {
             const uint32_t h = adj[k];
             if (!alive[h]) continue;
-            const uint32_t far = a_dst[last[h]];
-            if (nxt[h] >= 0) { good = true; break; }                          // (runs into a closed chain: leave it alone)
-            if (cnt[h] - 1 >= min_reads) good = true;                         // composite edge with enough reads (:176)
-            else if (sum[h] + (uint64_t)rlen_of(len, uniform, far) >= min_len) good = true; // long enough (:181)
+            const SLink l = L[h];
+            const uint32_t far = a_dst[l.last];
+            if (l.nxt >= 0) { good = true; break; }                           // (runs into a closed chain: leave it alone)
+            if (l.cnt - 1 >= min_reads) good = true;                          // composite edge with enough reads (:176)
+            else if (l.sum + (uint64_t)rlen_of(len, uniform, far) >= min_len) good = true; // long enough (:181)
             else if (far == (uint32_t)v) good = true;                         // loop (:186)
             else if ((a_or[h] >> 1) & 1) out++; else in++;                    // (:193-196)
         }
@@ -138,11 +151,11 @@ __global__ void k_s_deadends(uint64_t n, const uint64_t *row, const uint32_t *ad
 }
 
 // the edges of a dead-end node go, i.e. every atom of every chain that starts or ends there
-__global__ void k_s_remove(uint64_t nh, const uint32_t *a_dst, const int32_t *last, const uint8_t *dead, uint8_t *alive, unsigned long long *removed)
+__global__ void k_s_remove(uint64_t nh, const uint32_t *a_dst, const SLink *L, const uint8_t *dead, uint8_t *alive, unsigned long long *removed)
 {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= nh || !alive[h]) return;
-    const uint32_t w = a_dst[last[h]], u = a_dst[last[h ^ 1]]; // far ends of the chain in both directions
+    const uint32_t w = a_dst[L[h].last], u = a_dst[L[h ^ 1].last]; // far ends of the chain in both directions
     if (dead[u] || dead[w]) {
         alive[h] = 0;
         if (!(h & 1)) atomicAdd(removed, 1ULL);
@@ -152,7 +165,7 @@ __global__ void k_s_remove(uint64_t nh, const uint32_t *a_dst, const int32_t *la
 // output, pass 1: chain heads (source not contractible) on the side printEdge writes (:663): reserve the record and the
 // inner-read slots.  Atoms of closed chains are written one by one.
 __global__ void k_s_heads(uint64_t nh, const uint32_t *a_src, const uint32_t *a_dst, const uint32_t *a_off, const uint8_t *a_or, const uint8_t *alive,
-                          const uint8_t *contractible, const int32_t *nxt, const uint32_t *cnt, const uint64_t *sum, const int32_t *last,
+                          const uint8_t *contractible, const SLink *L,
                           disco_cedge *out, uint64_t cap, uint64_t *base_of, unsigned long long *cursors /* [0] edges [1] inner [2] cycle atoms */)
 {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,14 +176,15 @@ __global__ void k_s_heads(uint64_t nh, const uint32_t *a_src, const uint32_t *a_
     uint32_t w, natoms;
     uint64_t total;
     int o;
-    if (nxt[h] >= 0) { // atom of a closed chain: written unmerged, once, from its smaller end
+    const SLink l = L[h];
+    if (l.nxt >= 0) { // atom of a closed chain: written unmerged, once, from its smaller end
         w = a_dst[h]; natoms = 1; total = a_off[h]; o = a_or[h];
         if (!(u < w)) return;
         atomicAdd(cursors + 2, 1ULL);
     } else {
         if (contractible[u]) return;
-        const int32_t t = last[h];
-        w = a_dst[t]; natoms = cnt[h]; total = sum[h];
+        const int32_t t = l.last;
+        w = a_dst[t]; natoms = l.cnt; total = l.sum;
         o = (a_or[h] & 2) | (a_or[t] & 1); // mergedEdgeOrientation (EdgeSimple.cpp:256-259) along the chain
         if (!(u < w || (u == w && h < (uint64_t)(t ^ 1)))) return;
     }
@@ -188,15 +202,16 @@ __global__ void k_s_heads(uint64_t nh, const uint32_t *a_src, const uint32_t *a_
 // output, pass 2: every atom of an emitted chain writes the read it leads to at its rank: (read | offset << 32 | strand << 63)
 // = mergeList's entry (EdgeSimple.cpp:226-230)
 __global__ void k_s_inner(uint64_t nh, const uint32_t *a_dst, const uint32_t *a_off, const uint8_t *a_or, const uint8_t *alive,
-                          const int32_t *nxt, const uint32_t *cnt, const int32_t *last, const uint64_t *base_of, uint64_t *inner, uint64_t cap)
+                          const SLink *L, const uint64_t *base_of, uint64_t *inner, uint64_t cap)
 {
     const uint64_t h = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (h >= nh || !alive[h] || nxt[h] >= 0) return;
-    const int32_t head = last[h ^ 1] ^ 1;          // the reverse chain ends at the reverse of this chain's first atom
+    if (h >= nh || !alive[h] || L[h].nxt >= 0) return;
+    const int32_t head = L[h ^ 1].last ^ 1;        // the reverse chain ends at the reverse of this chain's first atom
     const uint64_t b = base_of[head];
     if (b == ~0ULL) return;                        // not the side that is written
-    const uint32_t rank = cnt[head] - cnt[h];      // atoms in front of this one
-    if (rank + 1 >= cnt[head]) return;             // the last atom leads to the end node, not to an inner read
+    const uint32_t nhead = L[head].cnt;
+    const uint32_t rank = nhead - L[h].cnt;        // atoms in front of this one
+    if (rank + 1 >= nhead) return;                 // the last atom leads to the end node, not to an inner read
     const uint64_t at = b + rank;
     if (at < cap) inner[at] = (uint64_t)a_dst[h] | ((uint64_t)a_off[h] << 32) | ((uint64_t)(a_or[h] & 1) << 63);
 }
@@ -209,9 +224,9 @@ struct SimplifyBuffers {
     unsigned long long *deg_all = nullptr;
     void *scan_tmp = nullptr;
     uint8_t *a_or = nullptr, *alive = nullptr, *contractible = nullptr, *dead = nullptr;
-    uint64_t *row = nullptr, *sum[2] = {nullptr, nullptr}, *base_of = nullptr;
-    int32_t *slot = nullptr, *nxt[2] = {nullptr, nullptr}, *last[2] = {nullptr, nullptr};
-    uint32_t *cnt[2] = {nullptr, nullptr};
+    uint64_t *row = nullptr, *base_of = nullptr;
+    int32_t *slot = nullptr;
+    SLink *L[2] = {nullptr, nullptr};
     unsigned long long *counters = nullptr; // [0] active / removed, [1..3] output cursors
 };
 
@@ -229,6 +244,15 @@ cudaError_t run_simplify(const disco_edge *d_edges, uint64_t ne, uint64_t n_read
     auto blocks = [&](uint64_t k) { return (unsigned)((k + T - 1) / T); };
     int cur = 0;
     uint64_t tot_removed = 0, nrounds = 0;
+    const bool trace = getenv("DISCO_SIMPLIFY_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (!trace) return;
+        cudaStreamSynchronize(s);
+        const auto t = std::chrono::steady_clock::now();
+        fprintf(stderr, "simplify: %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - t_last).count());
+        t_last = t;
+    };
     unsigned long long hc[4] = {0, 0, 0, 0};
     *d_out = nullptr; *d_inner = nullptr; *n_out = *n_inner = 0;
     if (ne == 0) { *rounds = 0; *removed_edges = 0; *cycle_atoms = 0; return cudaSuccess; }
@@ -236,10 +260,9 @@ cudaError_t run_simplify(const disco_edge *d_edges, uint64_t ne, uint64_t n_read
     SCK(cudaMalloc(&b.a_or, nh)); SCK(cudaMalloc(&b.alive, nh)); SCK(cudaMalloc(&b.adj, nh * 4)); SCK(cudaMalloc(&b.base_of, nh * 8));
     SCK(cudaMalloc(&b.deg_all, (n + 1) * 8)); SCK(cudaMalloc(&b.deg, n * 4)); SCK(cudaMalloc(&b.fillc, n * 4)); SCK(cudaMalloc(&b.row, (n + 1) * 8));
     SCK(cudaMalloc(&b.slot, n * 8)); SCK(cudaMalloc(&b.contractible, n)); SCK(cudaMalloc(&b.dead, n));
-    for (int k = 0; k < 2; k++) {
-        SCK(cudaMalloc(&b.nxt[k], nh * 4)); SCK(cudaMalloc(&b.last[k], nh * 4)); SCK(cudaMalloc(&b.cnt[k], nh * 4)); SCK(cudaMalloc(&b.sum[k], nh * 8));
-    }
+    for (int k = 0; k < 2; k++) SCK(cudaMalloc(&b.L[k], nh * sizeof(SLink)));
     SCK(cudaMalloc(&b.counters, 4 * sizeof(unsigned long long)));
+    lap("allocations");
     SCK(cudaMemsetAsync(b.deg_all, 0, (n + 1) * 8, s)); SCK(cudaMemsetAsync(b.fillc, 0, n * 4, s));
     k_s_atoms<<<blocks(ne), T, 0, s>>>(d_edges, ne, d_len, uniform_len, min_ovl, b.a_src, b.a_dst, b.a_off, b.a_or, b.alive, b.deg_all);
     {   // CSR offsets: exclusive prefix sum of the n + 1 counters (the last one is zero) -- library scan, runs once per call
@@ -250,15 +273,16 @@ cudaError_t run_simplify(const disco_edge *d_edges, uint64_t ne, uint64_t n_read
     }
     k_s_fill<<<blocks(nh), T, 0, s>>>(b.a_src, nh, b.row, b.fillc, b.adj);
     *launches += 3;
+    lap("atoms + CSR");
     for (;;) {
         nrounds++;
         k_s_nodes<<<blocks(n), T, 0, s>>>(n, b.row, b.adj, b.alive, b.a_or, b.deg, b.slot, b.contractible);
         cur = 0;
-        k_s_links<<<blocks(nh), T, 0, s>>>(nh, b.a_dst, b.a_off, b.alive, b.contractible, b.slot, b.nxt[0], b.cnt[0], b.sum[0], b.last[0]);
+        k_s_links<<<blocks(nh), T, 0, s>>>(nh, b.a_dst, b.a_off, b.alive, b.contractible, b.slot, b.L[0]);
         *launches += 2;
         for (int it = 0; it < 40; it++) { // chains double per step; closed chains never finish and are left after 2^40
             SCK(cudaMemsetAsync(b.counters, 0, sizeof(unsigned long long), s));
-            k_s_jump<<<blocks(nh), T, 0, s>>>(nh, b.nxt[cur], b.cnt[cur], b.sum[cur], b.last[cur], b.nxt[cur ^ 1], b.cnt[cur ^ 1], b.sum[cur ^ 1], b.last[cur ^ 1], b.counters);
+            k_s_jump<<<blocks(nh), T, 0, s>>>(nh, b.L[cur], b.L[cur ^ 1], b.counters);
             *launches += 1;
             cur ^= 1;
             SCK(cudaMemcpyAsync(hc, b.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -266,21 +290,22 @@ cudaError_t run_simplify(const disco_edge *d_edges, uint64_t ne, uint64_t n_read
             if (!hc[0]) break;
             if (it >= 34) break; // only closed chains are left
         }
-        k_s_deadends<<<blocks(n), T, 0, s>>>(n, b.row, b.adj, b.alive, b.contractible, b.a_dst, b.a_or, b.nxt[cur], b.cnt[cur], b.sum[cur], b.last[cur],
-                                            d_len, uniform_len, min_reads, min_len, b.dead);
+        lap("nodes + links + jumping");
+        k_s_deadends<<<blocks(n), T, 0, s>>>(n, b.row, b.adj, b.alive, b.contractible, b.a_dst, b.a_or, b.L[cur], d_len, uniform_len, min_reads, min_len, b.dead);
         SCK(cudaMemsetAsync(b.counters, 0, sizeof(unsigned long long), s));
-        k_s_remove<<<blocks(nh), T, 0, s>>>(nh, b.a_dst, b.last[cur], b.dead, b.alive, b.counters);
+        k_s_remove<<<blocks(nh), T, 0, s>>>(nh, b.a_dst, b.L[cur], b.dead, b.alive, b.counters);
         *launches += 2;
         SCK(cudaMemcpyAsync(hc, b.counters, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
         SCK(cudaStreamSynchronize(s));
         tot_removed += hc[0];
+        lap("dead ends + removal");
         if (!hc[0]) break; // nothing removed: the chains of this round are the result
         if (nrounds > 10000) break;
     }
     // ---- output: count, allocate, fill
     for (int pass = 0; pass < 2; pass++) {
         SCK(cudaMemsetAsync(b.counters, 0, 4 * sizeof(unsigned long long), s));
-        k_s_heads<<<blocks(nh), T, 0, s>>>(nh, b.a_src, b.a_dst, b.a_off, b.a_or, b.alive, b.contractible, b.nxt[cur], b.cnt[cur], b.sum[cur], b.last[cur],
+        k_s_heads<<<blocks(nh), T, 0, s>>>(nh, b.a_src, b.a_dst, b.a_off, b.a_or, b.alive, b.contractible, b.L[cur],
                                          *d_out, pass ? *n_out : 0, b.base_of, b.counters + 1);
         *launches += 1;
         SCK(cudaMemcpyAsync(hc, b.counters, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
@@ -291,14 +316,15 @@ cudaError_t run_simplify(const disco_edge *d_edges, uint64_t ne, uint64_t n_read
             SCK(cudaMalloc(d_inner, (hc[2] ? hc[2] : 1) * sizeof(uint64_t)));
         }
     }
-    k_s_inner<<<blocks(nh), T, 0, s>>>(nh, b.a_dst, b.a_off, b.a_or, b.alive, b.nxt[cur], b.cnt[cur], b.last[cur], b.base_of, *d_inner, *n_inner);
+    k_s_inner<<<blocks(nh), T, 0, s>>>(nh, b.a_dst, b.a_off, b.a_or, b.alive, b.L[cur], b.base_of, *d_inner, *n_inner);
     *launches += 1;
     SCK(cudaStreamSynchronize(s));
+    lap("output");
     *rounds = nrounds; *removed_edges = tot_removed;
 done:
     cudaFree(b.a_src); cudaFree(b.a_dst); cudaFree(b.a_off); cudaFree(b.a_or); cudaFree(b.alive); cudaFree(b.adj); cudaFree(b.base_of);
     cudaFree(b.deg_all); cudaFree(b.deg); cudaFree(b.fillc); cudaFree(b.row); cudaFree(b.slot); cudaFree(b.contractible); cudaFree(b.dead);
-    for (int k = 0; k < 2; k++) { cudaFree(b.nxt[k]); cudaFree(b.last[k]); cudaFree(b.cnt[k]); cudaFree(b.sum[k]); }
+    for (int k = 0; k < 2; k++) cudaFree(b.L[k]);
     cudaFree(b.counters); cudaFree(b.scan_tmp);
     if (err != cudaSuccess) { cudaFree(*d_out); cudaFree(*d_inner); *d_out = nullptr; *d_inner = nullptr; }
     return err;

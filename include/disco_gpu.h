@@ -115,6 +115,9 @@ int disco_gpu_counts(disco_ctx *ctx, uint64_t *n_contained, uint64_t *n_edges);
 int disco_gpu_get_contained(disco_ctx *ctx, disco_crow *rows, uint64_t capacity, uint64_t *n_written);
 /* edges in device emission order (callers sort if they need a canonical order) */
 int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, uint64_t *n_written);
+/* Optional: a page-locked host buffer the emission kernel fills itself (over PCIe while it runs); disco_gpu_get_edges into
+ * that same buffer then needs no copy.  NULL clears it; results larger than the capacity are not mirrored. */
+int disco_gpu_set_edge_sink(disco_ctx *ctx, disco_edge *host_pinned, uint64_t capacity);
 /* unreduced adjacency of one read (its own capped search, sorted by offset): for tests of the cap semantics */
 int disco_gpu_get_row(disco_ctx *ctx, uint64_t read, disco_edge *out, uint64_t capacity, uint64_t *n_written);
 int disco_gpu_get_stats(disco_ctx *ctx, disco_stats *out);

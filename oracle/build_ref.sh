@@ -37,8 +37,9 @@ g++ $GZ -Wno-sign-compare -fopenmp -std=c++11 -O3 -w -o "$OUT/buildG" "$TMP"/*.c
 echo "build_ref: built $OUT/buildG"
 
 # The first consumer of the hot path's files: parsimplify (src/SimplifyGraph), used only to check that our
-# files are accepted and lead to the same contracted graph.  Same treatment: scratch copy, compile fixes only
-# (SSTR in Config.h:47 and OverlapGraphSimple.h:17, missing <cstdint> in Utils.cpp).
+# files are accepted and lead to the same contracted graph, and as the oracle of the GPU contraction (simplify.cu).  Same
+# treatment: scratch copy, compile fixes (SSTR in Config.h:47 and OverlapGraphSimple.h:17, missing <cstdint> in Utils.cpp)
+# plus one determinism fix (3. below).
 SG="${DISCO_REFERENCE:-/root/reference}/src/SimplifyGraph/src"
 TMP2="$(mktemp -d /tmp/disco_ref_build2.XXXXXX)"
 trap 'rm -rf "$TMP" "$TMP2"' EXIT
@@ -48,5 +49,18 @@ for f in Config.h OverlapGraphSimple.h; do
   sed -i 's|^#define SSTR( x ).*|#define SSTR( x ) (static_cast< std::ostringstream \&\& >( std::ostringstream() << std::dec << x ).str())|' "$TMP2/$f"
 done
 sed -i '1i #include <cstdint>' "$TMP2/Utils.cpp"
+# 3. determinism fix: EdgeSimple::copyEdge (EdgeSimple.cpp:46-61) copies an edge WITHOUT its two read lengths, and the copy
+#    constructor initialises nothing else -- every composite edge grown from such a copy (OverlapGraphSimple.cpp:365, :408)
+#    carries an uninitialised m_destinationLen, which is printed as part of the edge length (:672) and decides
+#    removeParDeadEndNodes' "edge long enough" test (:181).  The unpatched binary's output depends on heap garbage (observed:
+#    length = offset + 0 / + 2954, short tips kept at random); with the two members copied it is a function of its input.
+python3 - "$TMP2/EdgeSimple.cpp" <<'PY'
+import sys
+p = sys.argv[1]
+src = open(p).read()
+needle = "\tm_source = edge.m_source;\n"
+assert src.count(needle) == 1, "EdgeSimple::copyEdge not found"
+open(p, "w").write(src.replace(needle, needle + "\tm_sourceLen = edge.m_sourceLen;\n\tm_destinationLen = edge.m_destinationLen;\n"))
+PY
 ( cd "$TMP2" && g++ $GZ -Wno-sign-compare -fopenmp -std=c++11 -O3 -w -o "$OUT/parsimplify" Config.cpp DataSet.cpp EdgeSimple.cpp OverlapGraphSimple.cpp Read.cpp Utils.cpp dna.cpp mainParSimplify.cpp $GZL ) \
   && echo "build_ref: built $OUT/parsimplify" || echo "build_ref: parsimplify did not build (acceptance test will be skipped)"

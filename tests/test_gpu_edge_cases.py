@@ -185,3 +185,29 @@ def test_buffer_overflow_retry_gives_the_same_graph(monkeypatch):
     e3, s3 = run(3)
     assert s0["raw_directed_edges"] == s1["raw_directed_edges"] == s3["raw_directed_edges"] > 40_000 * 30
     assert np.array_equal(e0, e1) and np.array_equal(e0, e3)
+
+
+def test_edge_sink_is_filled_by_the_emission_kernel():
+    """disco_gpu_set_edge_sink: the kept edges land in the caller's pinned buffer while the kernel runs; get_edges into that
+    buffer copies nothing, and the content equals the device-side list."""
+    import torch
+    rs = synth.single_genome(30_000, 150, 30.0, seed=12)
+    packed, lens = host.pack_codes(rs.codes, rs.off)
+    g = gpu.GpuBuildGraph(0)
+    g.load_reads(packed, lens)
+    g.build_graph(50, 4)
+    want = gpu.sort_edges(g.edges())
+    sink = torch.zeros((len(want) + 100, 4), dtype=torch.int32).pin_memory()
+    g.set_edge_sink(sink.data_ptr(), sink.shape[0])
+    g.load_reads(packed, lens)
+    g.build_graph(50, 4)
+    view = sink.numpy().view(gpu.EDGE_DTYPE).reshape(-1)
+    got = g.edges(out=view)            # no copy: the kernel already wrote the sink
+    assert np.array_equal(gpu.sort_edges(got.copy()), want)
+    g.set_edge_sink(0, 0)
+    small = torch.zeros((10, 4), dtype=torch.int32).pin_memory()
+    g.set_edge_sink(small.data_ptr(), 10)                     # too small: not mirrored, the normal copy path still works
+    g.load_reads(packed, lens)
+    g.build_graph(50, 4)
+    assert np.array_equal(gpu.sort_edges(g.edges()), want)
+    g.close()

@@ -23,13 +23,6 @@ def _reference_lines(tmp_path, res, m):
     return [l.rstrip("\n") for l in open(out)]
 
 
-def _split(line):
-    """(line without the edge-length field, edge length)"""
-    f = line.split("\t")
-    p = f[2].split(",")
-    return "\t".join([f[0], f[1], ",".join(p[:2] + p[3:])] + f[3:]), int(p[2])
-
-
 def _check(records, m, tmp_path, expect_composite=True):
     bg = BuildGraph(min_overlap=m)
     bg.add_records(records)
@@ -39,14 +32,9 @@ def _check(records, m, tmp_path, expect_composite=True):
         st = bg.simplify_stats
         ref = _reference_lines(tmp_path, res, m)
         if st["cycle_edges"] == 0:
-            a, b = sorted(_split(l) for l in mine), sorted(_split(l) for l in ref)
-            assert [x[0] for x in a] == [x[0] for x in b]          # ends, orientation, offset sum, every inner read in order
-            # edge length = offset sum + len(dst).  The reference copies edges without their read lengths
-            # (EdgeSimple::copyEdge, EdgeSimple.cpp:46-61, used at OverlapGraphSimple.cpp:365/:408), so a chain whose
-            # forward part was not extended prints offset sum + an uninitialised length (0 in practice): accept exactly that
-            for (key, la), (_, lb) in zip(a, b):
-                assert la == lb or lb == int(key.split("\t")[2].split(",")[1]), (key, la, lb)
-            assert sum(la == lb for (_, la), (_, lb) in zip(a, b)) >= 0.5 * len(a)
+            # line for line: ends, orientation, offset sum, edge length, every inner read in order (the reference binary is
+            # built with its copyEdge determinism fix, oracle/build_ref.sh patch 3)
+            assert sorted(mine) == sorted(ref)
         else:   # an isolated cycle: the reference breaks it where its node order starts (simplify.cu header)
             assert len(mine) >= len(ref)
         if expect_composite:
