@@ -40,6 +40,14 @@ struct disco_ctx {
     uint64_t *d_tails = nullptr;    // last 128 bases of every read as one 32-byte sector (flat verify kernel); 64-byte rows only
     uint64_t *d_stage = nullptr; // host rows arrive here when their pitch differs from the device row
     uint64_t stage_words = 0;
+    bool own_reads = true;       // false: d_words / d_len are the caller's device buffers (disco_gpu_use_reads_device)
+    // deferred upload (disco_gpu_load_reads_async): host buffers waiting to be copied, chunk by chunk, under the table build
+    const uint64_t *pend_packed = nullptr;
+    const uint16_t *pend_len = nullptr;
+    uint32_t pend_wpr = 0;
+    bool pending = false;
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copy[17] = {};
     ReadsView reads{};
     // run parameters
     int K = 0, cap = 0;
@@ -167,8 +175,11 @@ void free_run_buffers(disco_ctx *c)
 
 void free_reads(disco_ctx *c)
 {
-    dfree(c->d_words); dfree(c->d_words_rc); dfree(c->d_tails); dfree(c->d_len); dfree(c->d_stage);
+    if (c->own_reads) { dfree(c->d_words); dfree(c->d_len); }
+    c->d_words = nullptr; c->d_len = nullptr; c->own_reads = true;
+    dfree(c->d_words_rc); dfree(c->d_tails); dfree(c->d_stage);
     c->stage_words = 0;
+    c->pending = false; c->pend_packed = nullptr; c->pend_len = nullptr;
     c->reads = ReadsView{};
 }
 
@@ -229,7 +240,8 @@ int record(disco_ctx *ctx, int which)
 int alloc_reads(disco_ctx *ctx, uint64_t n, int min_len, int max_len)
 {
     // same shape as the resident set (the steady state of a service that processes batch after batch): keep every buffer
-    if (ctx->d_words && n == ctx->reads.n && n > 0 && pick_stride(max_len) == ctx->reads.stride) {
+    ctx->pending = false;
+    if (ctx->d_words && ctx->own_reads && n == ctx->reads.n && n > 0 && pick_stride(max_len) == ctx->reads.stride) {
         ctx->reads.min_len = min_len; ctx->reads.max_len = max_len;
         ctx->reads.uniform_len = (min_len == max_len) ? max_len : 0;
         ctx->begun = ctx->have_contained = ctx->have_edges = ctx->have_reduced = false;
@@ -341,6 +353,8 @@ void disco_gpu_destroy(disco_ctx *ctx)
     free_reads(ctx);
     dfree(ctx->d_cursors); dfree(ctx->d_stats_c); dfree(ctx->d_stats_e);
     for (auto &ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto &ev : ctx->ev_copy) if (ev) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -386,6 +400,83 @@ int disco_gpu_load_reads_device(disco_ctx *ctx, const uint64_t *d_packed, const 
     int rc = alloc_reads(ctx, n_reads, (int)min_len, (int)max_len);
     if (rc) return rc;
     return copy_reads(ctx, d_packed, d_len, words_per_read, cudaMemcpyDeviceToDevice);
+}
+
+// The caller's device buffers used in place (no copy): rows must already have this library's pitch -- the power of two
+// {2,4,8,16} that holds the longest read, else an even word count -- and 16-byte alignment; any other pitch is copied as
+// disco_gpu_load_reads_device does.  The buffers must stay valid and unchanged until the results have been read.
+int disco_gpu_use_reads_device(disco_ctx *ctx, const uint64_t *d_packed, const uint16_t *d_len, uint64_t n_reads,
+                               uint32_t words_per_read, uint32_t min_len, uint32_t max_len)
+{
+    if (!ctx) return DISCO_E_ARG;
+    if (!d_packed || !d_len) return fail(ctx, DISCO_E_ARG, "NULL input");
+    if (min_len > max_len || min_len < 1) return fail(ctx, DISCO_E_ARG, "bad length bounds");
+    if (max_len > 32767) return fail(ctx, DISCO_E_LIMIT, "read length %u exceeds the 15-bit limit of the reference record header (HashTable.cpp:437)", max_len);
+    const int stride = pick_stride((int)max_len);
+    if ((int)words_per_read != stride || (reinterpret_cast<uintptr_t>(d_packed) & 15))
+        return disco_gpu_load_reads_device(ctx, d_packed, d_len, n_reads, words_per_read, min_len, max_len);
+    if (n_reads == 0) return fail(ctx, DISCO_E_ARG, "no reads");
+    if (n_reads > 0x7FFFFFF0ULL) return fail(ctx, DISCO_E_LIMIT, "at most 2^31-16 reads per context (record ids are 32 bit)");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const bool same = ctx->d_words && n_reads == ctx->reads.n && stride == ctx->reads.stride;
+    if (same) { // keep the run buffers (and the tail copy's allocation); only the read buffers change hands
+        if (ctx->own_reads) { dfree(ctx->d_words); dfree(ctx->d_len); }
+        dfree(ctx->d_words_rc);
+        dfree(ctx->d_stage); ctx->stage_words = 0;
+    } else {
+        free_run_buffers(ctx);
+        free_reads(ctx);
+        if (stride == 8 && !(getenv("DISCO_TAILS") && atoi(getenv("DISCO_TAILS")) == 0)) {
+            if (cudaMalloc(&ctx->d_tails, n_reads * 4 * sizeof(uint64_t)) != cudaSuccess) { ctx->d_tails = nullptr; cudaGetLastError(); }
+        }
+    }
+    ctx->own_reads = false; ctx->pending = false;
+    ctx->d_words = const_cast<uint64_t *>(d_packed); ctx->d_len = const_cast<uint16_t *>(d_len);
+    ctx->reads.tails = nullptr;
+    ctx->reads.words = ctx->d_words; ctx->reads.words_rc = nullptr; ctx->reads.len = ctx->d_len; ctx->reads.n = n_reads; ctx->reads.stride = stride;
+    ctx->reads.min_len = (int)min_len; ctx->reads.max_len = (int)max_len;
+    ctx->reads.uniform_len = (min_len == max_len) ? (int)max_len : 0;
+    ctx->begun = ctx->have_contained = ctx->have_edges = ctx->have_reduced = false;
+    return DISCO_OK;
+}
+
+// disco_gpu_load_reads with the copy deferred into disco_gpu_build_graph / disco_gpu_phase_table(ctx, 0): there the rows
+// cross PCIe in chunks on a copy stream while the table is built from the chunks that have arrived, so the table build
+// (and the re-striding) hide under the transfer.  The host buffers must stay valid and unchanged until that call has
+// returned; only page-locked memory makes the copies asynchronous.  min_len / max_len: the shortest and longest read --
+// every loader knows them (Dataset.cpp prints them) -- or 0, 0 to have them found here (one pass over `len`).
+int disco_gpu_load_reads_async(disco_ctx *ctx, const uint64_t *packed, const uint16_t *len, uint64_t n_reads, uint32_t words_per_read,
+                               uint32_t min_len, uint32_t max_len)
+{
+    if (!ctx) return DISCO_E_ARG;
+    if (!packed || !len) return fail(ctx, DISCO_E_ARG, "NULL input");
+    CK(cudaSetDevice(ctx->device));
+    int mn = (int)min_len, mx = (int)max_len;
+    if (!mn || !mx) {
+        mn = 1 << 30; mx = 0;
+        for (uint64_t i = 0; i < n_reads; i++) { int l = len[i]; mn = std::min(mn, l); mx = std::max(mx, l); }
+    }
+    if (mn > mx) return fail(ctx, DISCO_E_ARG, "min_len > max_len");
+    int rc = alloc_reads(ctx, n_reads, mn, mx);
+    if (rc) return rc;
+    if ((int)words_per_read < (mx + 31) / 32) return fail(ctx, DISCO_E_ARG, "words_per_read %u too small for max length %d", words_per_read, mx);
+    if ((int)words_per_read != ctx->reads.stride) {
+        const uint64_t need = n_reads * (uint64_t)words_per_read;
+        if (ctx->stage_words < need) {
+            dfree(ctx->d_stage);
+            ctx->stage_words = 0;
+            CK(cudaMalloc(&ctx->d_stage, need * sizeof(uint64_t)));
+            ctx->stage_words = need;
+        }
+    }
+    if (!ctx->copy_stream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        for (auto &e : ctx->ev_copy) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    ctx->pend_packed = packed; ctx->pend_len = len; ctx->pend_wpr = words_per_read;
+    ctx->pending = true;
+    return DISCO_OK;
 }
 
 // ---- phases -------------------------------------------------------------------------------------------------------
@@ -437,6 +528,7 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
         CK(cudaMalloc(&ctx->d_rowinfo, n * sizeof(uint64_t)));
         ctx->run_n = n;
     }
+    if (ctx->pending) CK(cudaEventRecord(ctx->ev_copy[16], ctx->stream));
     CK(cudaMemsetAsync(ctx->d_best, 0xFF, n * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_rowinfo, 0, n * sizeof(uint64_t), ctx->stream));
@@ -452,14 +544,51 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
     ctx->begun = true;
     int rc0 = record(ctx, EV_T0);
     if (rc0) return rc0;
-    if (ctx->d_words_rc) CK(launch_revcomp_rows(ctx->reads, ctx->d_words_rc, ctx->stream)); // part of the timed run
+    // (a deferred upload prepares these copies chunk by chunk in disco_gpu_phase_table)
+    if (ctx->d_words_rc && !ctx->pending) CK(launch_revcomp_rows(ctx->reads, ctx->d_words_rc, ctx->stream)); // part of the timed run
     ctx->reads.tails = nullptr;
     if (ctx->d_tails && ctx->reads.uniform_len > 128) { // (every read one length: the kernel knows the overlap before it fetches)
-        CK(launch_make_tails(ctx->reads, ctx->d_tails, ctx->stream));                         // part of the timed run
+        if (!ctx->pending) CK(launch_make_tails(ctx->reads, ctx->d_tails, ctx->stream));      // part of the timed run
         ctx->reads.tails = ctx->d_tails;
     }
     return DISCO_OK;
 }
+
+namespace {
+// The deferred upload (disco_gpu_load_reads_async) and the first table build as one pipeline: chunk c crosses PCIe on the
+// copy stream while the main stream re-strides chunk c-1, derives its tail sectors and inserts its records.
+int upload_and_insert(disco_ctx *ctx, const TableView &tv)
+{
+    const uint64_t n = ctx->reads.n;
+    const int stride = ctx->reads.stride;
+    const uint32_t wpr = ctx->pend_wpr;
+    const bool flat = (int)wpr == stride;
+    int chunks = 8;
+    if (const char *e = getenv("DISCO_UPLOAD_CHUNKS")) chunks = std::max(1, std::min(16, atoi(e)));
+    if (n < 65536) chunks = 1;
+    // whatever still reads the previous batch's rows was queued before disco_gpu_begin: the copies start after that point
+    // (ev_copy[16], recorded there) and do not wait for this run's memsets
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy[16], 0));
+    if (!ctx->reads.uniform_len) // (one length: the kernels never look at the array)
+        CK(cudaMemcpyAsync(ctx->d_len, ctx->pend_len, n * sizeof(uint16_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+    for (int c = 0; c < chunks; c++) {
+        const uint64_t lo = n * (uint64_t)c / chunks, hi = n * (uint64_t)(c + 1) / chunks, m = hi - lo;
+        if (!m) continue;
+        uint64_t *dst = flat ? ctx->d_words + lo * stride : ctx->d_stage + lo * wpr;
+        CK(cudaMemcpyAsync(dst, ctx->pend_packed + lo * wpr, m * wpr * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->copy_stream));
+        CK(cudaEventRecord(ctx->ev_copy[c], ctx->copy_stream));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[c], 0));
+        if (!flat) CK(launch_restride(ctx->d_stage + lo * wpr, (int)wpr, std::min<int>((int)wpr, stride), ctx->d_words + lo * stride, stride, m, ctx->stream));
+        ReadsView part = ctx->reads;
+        part.words += lo * stride; part.len += lo; part.n = m; part.tails = nullptr;
+        if (ctx->reads.tails) CK(launch_make_tails(part, ctx->d_tails + lo * 4, ctx->stream));
+        if (ctx->d_words_rc) CK(launch_revcomp_rows(part, ctx->d_words_rc + lo * stride, ctx->stream));
+        CK(launch_table_insert(ctx->reads, tv, ctx->K, nullptr, ctx->num_sms, ctx->stream, lo, hi));
+    }
+    ctx->pending = false;
+    return DISCO_OK;
+}
+} // namespace
 
 int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained)
 {
@@ -470,7 +599,13 @@ int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained)
     if (ctx->d_filter) CK(cudaMemsetAsync(ctx->d_filter, 0, ctx->filter_bits / 8, ctx->stream));
     ctx->table_has_contained = !exclude_contained;
     const TableView tv = table_view(ctx);
-    CK(launch_table_insert(ctx->reads, tv, ctx->K, exclude_contained ? ctx->d_bits : nullptr, ctx->num_sms, ctx->stream));
+    if (ctx->pending) { // the reads are still on the host: upload and insert chunk by chunk
+        if (exclude_contained) return fail(ctx, DISCO_E_ARG, "reads not uploaded yet");
+        const int rc = upload_and_insert(ctx, tv);
+        if (rc) return rc;
+    } else {
+        CK(launch_table_insert(ctx->reads, tv, ctx->K, exclude_contained ? ctx->d_bits : nullptr, ctx->num_sms, ctx->stream));
+    }
     return record(ctx, exclude_contained ? EV_TABLE_NC : EV_TABLE_ALL);
 }
 

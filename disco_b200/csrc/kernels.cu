@@ -274,7 +274,7 @@ __device__ __forceinline__ void warp_stat_add(unsigned long long *stats, int slo
 // Warp per read; quad 0 inserts the prefix record and quad 1 the suffix record cooperatively: each lane of the quad
 // reads one slot of the bucket (one coalesced sector), the quad votes, the first empty lane does the CAS.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits)
+__global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits, uint64_t r_lo, uint64_t r_hi)
 {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableVi
     uint32_t *A = reinterpret_cast<uint32_t *>(smem + (size_t)wib * 2 * WP), *R = A + 2 * WP;
     const int wpb = blockDim.x >> 5;
     const uint64_t nwarps = (uint64_t)gridDim.x * wpb;
-    for (uint64_t r = (uint64_t)blockIdx.x * wpb + wib; r < rv.n; r += nwarps) {
+    for (uint64_t r = r_lo + (uint64_t)blockIdx.x * wpb + wib; r < r_hi; r += nwarps) {
         if (skip_bits && ((__ldg(skip_bits + (r >> 5)) >> (r & 31)) & 1)) continue; // warp-uniform
         const int L = read_len(rv, r);
         stage_read(rv, r, L, A, R, WP, lane);
@@ -341,7 +341,7 @@ __device__ __forceinline__ void stage_lane(const ReadsView &rv, uint64_t r, bool
 // Table build, 32 reads per warp step.  Each lane hashes the prefix and suffix k-mer of its read; the 64 records are
 // then inserted eight at a time, one record per quad, cooperatively (four lanes read the four slots of the bucket --
 // one sector --, vote, the first empty lane does the CAS).
-__global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits)
+__global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits, uint64_t r_lo, uint64_t r_hi)
 {
     extern __shared__ uint64_t smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -353,9 +353,9 @@ __global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, T
     const uint64_t nwarps = (uint64_t)gridDim.x * wpb;
     const int quad = lane >> 2, sub = lane & 3;
     const unsigned qmask = 0xFu << (quad * 4);
-    for (uint64_t r0 = ((uint64_t)blockIdx.x * wpb + wib) * 32; r0 < rv.n; r0 += nwarps * 32) {
+    for (uint64_t r0 = r_lo + ((uint64_t)blockIdx.x * wpb + wib) * 32; r0 < r_hi; r0 += nwarps * 32) {
         const uint64_t r = r0 + lane;
-        bool valid = r < rv.n;
+        bool valid = r < r_hi;
         if (valid && skip_bits) valid = !((__ldg(skip_bits + (r >> 5)) >> (r & 31)) & 1);
         const int L = valid ? read_len(rv, r) : 0;
         stage_lane(rv, r, valid, L, A, R, WP);
@@ -1742,8 +1742,11 @@ static cudaError_t persistent_grid(Kern kern, size_t smem, int num_sms, int *gri
 constexpr size_t kLaneSmemPerWarp = 12 * 1024; // lane-per-read kernels are used while 32 private array pairs fit in this
 
 cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, const uint32_t *skip_bits,
-                                int num_sms, cudaStream_t s)
+                                int num_sms, cudaStream_t s, uint64_t r_lo, uint64_t r_hi)
 {
+    if (r_hi > r.n) r_hi = r.n; // (default: all reads)
+    if (r_lo >= r_hi) return cudaSuccess;
+    const uint64_t nr = r_hi - r_lo;
     {
         const size_t per_warp = (size_t)64 * lane_array_u32(r.max_len) * sizeof(uint32_t);
         if (per_warp <= kLaneSmemPerWarp) {
@@ -1751,9 +1754,9 @@ cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, c
             int grid = 0;
             cudaError_t e = persistent_grid(k_table_insert_lanes, smem, num_sms, &grid);
             if (e != cudaSuccess) return e;
-            const uint64_t need = (r.n + kWarps * 32 - 1) / (kWarps * 32);
+            const uint64_t need = (nr + kWarps * 32 - 1) / (kWarps * 32);
             if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
-            k_table_insert_lanes<<<grid, kThreads, smem, s>>>(r, t, K, skip_bits);
+            k_table_insert_lanes<<<grid, kThreads, smem, s>>>(r, t, K, skip_bits, r_lo, r_hi);
             DISCO_COUNT_LAUNCH();
             return cudaGetLastError();
         }
@@ -1765,9 +1768,9 @@ cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, c
     int grid = 0;
     cudaError_t e = persistent_grid(k_table_insert, smem, num_sms, &grid, warps * 32);
     if (e != cudaSuccess) return e;
-    const uint64_t need = (r.n + warps - 1) / warps;
+    const uint64_t need = (nr + warps - 1) / warps;
     if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
-    k_table_insert<<<grid, warps * 32, smem, s>>>(r, t, K, skip_bits);
+    k_table_insert<<<grid, warps * 32, smem, s>>>(r, t, K, skip_bits, r_lo, r_hi);
     DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }

@@ -104,8 +104,9 @@ struct ReduceParams {
     unsigned long long *edges_cursor;
 };
 
+// (r_lo, r_hi: the reads to insert -- the chunked upload of api.cu inserts each chunk as it arrives; default: all)
 cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, const uint32_t *skip_bits,
-                                int num_sms, cudaStream_t s);
+                                int num_sms, cudaStream_t s, uint64_t r_lo = 0, uint64_t r_hi = ~0ULL);
 cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStream_t s);
 // ev_probe_done / ev_verify_done (optional) are recorded after the probe and verify kernels of the edge pass
 cudaError_t launch_search_edges(const SearchParams &p, int num_sms, cudaStream_t s, cudaEvent_t ev_probe_done = nullptr,

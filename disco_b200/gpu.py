@@ -24,6 +24,7 @@ EXPORTS = [
     "disco_gpu_phase_reduce_emit", "disco_gpu_set_shard", "disco_gpu_export_mem", "disco_gpu_import_peers",
     "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table", "disco_gpu_table_words", "disco_gpu_adopt_buffer",
     "disco_gpu_build_graph_multi", "disco_gpu_device_count", "disco_gpu_set_partition", "disco_gpu_compact_keys", "disco_gpu_apply_keys", "disco_gpu_simplify", "disco_gpu_get_simplified", "disco_gpu_simplify_stats", "disco_gpu_set_edge_sink",
+    "disco_gpu_use_reads_device", "disco_gpu_load_reads_async",
 ]
 MAX_SHARDS, IPC_HANDLE_BYTES, MEM_TABLE, MEM_ROWS = 8, 64, 0, 1
 
@@ -64,6 +65,8 @@ def lib():
         L.disco_gpu_set_stream.argtypes = [vp, vp]
         L.disco_gpu_load_reads.argtypes = [vp, vp, vp, u64, u32]
         L.disco_gpu_load_reads_device.argtypes = [vp, vp, vp, u64, u32, u32, u32]
+        L.disco_gpu_use_reads_device.argtypes = [vp, vp, vp, u64, u32, u32, u32]
+        L.disco_gpu_load_reads_async.argtypes = [vp, vp, vp, u64, u32, u32, u32]
         L.disco_gpu_build_graph.argtypes = [vp, u32, u32]
         L.disco_gpu_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
         L.disco_gpu_get_contained.argtypes = [vp, vp, u64, C.POINTER(u64)]
@@ -164,6 +167,19 @@ class GpuBuildGraph:
         self.n = n
         self._ck(self._L.disco_gpu_load_reads_device(self._h, C.c_void_p(d_packed_ptr), C.c_void_p(d_lens_ptr), n, wpr,
                                                      min_len, max_len), "load_reads_device")
+
+    def use_reads_device(self, d_packed_ptr: int, d_lens_ptr: int, n: int, wpr: int, min_len: int, max_len: int):
+        """the caller's device buffers in place (no copy) when wpr is the library's row pitch; they must outlive the run"""
+        self.n = n
+        self._ck(self._L.disco_gpu_use_reads_device(self._h, C.c_void_p(d_packed_ptr), C.c_void_p(d_lens_ptr), n, wpr,
+                                                    min_len, max_len), "use_reads_device")
+
+    def load_reads_async(self, packed_ptr: int, lens_ptr: int, n: int, wpr: int, min_len: int = 0, max_len: int = 0):
+        """host buffers (pinned) whose upload is deferred into build_graph and overlapped with the table build; they must
+        stay valid and unchanged until build_graph has returned"""
+        self.n = n
+        self._ck(self._L.disco_gpu_load_reads_async(self._h, C.c_void_p(packed_ptr), C.c_void_p(lens_ptr), n, wpr, min_len, max_len),
+                 "load_reads_async")
 
     def build_graph(self, min_overlap: int, max_edge_per_kmer: int = 4):
         self._ck(self._L.disco_gpu_build_graph(self._h, min_overlap, max_edge_per_kmer), "build_graph")

@@ -104,6 +104,17 @@ int disco_gpu_load_reads(disco_ctx *ctx, const uint64_t *packed, const uint16_t 
 /* Same, but the buffers already live in this device's memory. */
 int disco_gpu_load_reads_device(disco_ctx *ctx, const uint64_t *d_packed, const uint16_t *d_len, uint64_t n_reads,
                                 uint32_t words_per_read, uint32_t min_len, uint32_t max_len);
+/* The caller's device buffers used in place, no copy, when the rows already have this library's pitch (the power of two
+ * {2,4,8,16} words that holds the longest read, else an even word count; 16-byte aligned); any other pitch is copied as
+ * above.  The buffers must stay valid and unchanged until the results have been read. */
+int disco_gpu_use_reads_device(disco_ctx *ctx, const uint64_t *d_packed, const uint16_t *d_len, uint64_t n_reads,
+                               uint32_t words_per_read, uint32_t min_len, uint32_t max_len);
+/* disco_gpu_load_reads with the copy deferred into disco_gpu_build_graph (disco_gpu_phase_table(ctx, 0)): the rows cross
+ * PCIe in chunks while the hash table is built from the chunks that have arrived (the reference fills its table while it
+ * re-reads the files, HashTable.cpp:423-514).  The host buffers must stay valid and unchanged until that call returns.
+ * min_len / max_len: shortest / longest read as the loader reports them (Dataset.cpp:139-146), or 0, 0 = find them here. */
+int disco_gpu_load_reads_async(disco_ctx *ctx, const uint64_t *packed, const uint16_t *len, uint64_t n_reads,
+                               uint32_t words_per_read, uint32_t min_len, uint32_t max_len);
 
 /* ---- the whole hot path: insertDataset + buildOverlapGraphFromHashTable (HashTable.cpp:46, OverlapGraph.cpp:100)
  * min_overlap = MinOverlap4BuildGraph (main.cpp:170); max_edge_per_kmer = MAX_EDGE_PER_KMER (Common.h:62), 1..8. */
