@@ -131,6 +131,45 @@ def exchange_rowinfo(rowinfo: torch.Tensor, n: int, rank: int, world: int, group
         dist.all_reduce(rowinfo, op=dist.ReduceOp.SUM, group=group)
 
 
+def balanced_bounds(keys: torch.Tensor, world: int, block: int = 4096):
+    """Read-id bounds [world + 1] of contiguous ranges that hold (to within one block) the same number of NON-contained
+    reads each.  The edge pass and the reduction only work on those, and which reads are contained is anything but uniform
+    in the id: a duplicate is contained by its first copy, so low ids survive more often (80 M reads, 30x: the first eighth
+    of the ids keeps 9 % more reads than the average eighth).  keys = the reduced containment keys (all ones = not
+    contained), identical on every rank, hence identical bounds without an exchange.  One small device-to-host read."""
+    n = keys.numel()
+    nb = (n + block - 1) // block
+    alive = keys == -1
+    full = (n // block) * block
+    counts = torch.zeros(nb, dtype=torch.int64, device=keys.device)
+    if full:
+        counts[:n // block] = alive[:full].view(-1, block).sum(dim=1, dtype=torch.int64)
+    if full < n:
+        counts[-1] = alive[full:].sum(dtype=torch.int64)
+    cum = counts.cumsum(0)
+    targets = (cum[-1] * torch.arange(1, world, device=keys.device, dtype=torch.int64)) // world
+    idx = torch.searchsorted(cum, targets, right=False).tolist()    # first block at which the running count reaches the target
+    bounds = [0]
+    for i in idx:
+        bounds.append(max(bounds[-1], min(n, (int(i) + 1) * block)))
+    bounds.append(n)
+    return bounds
+
+
+def exchange_rowinfo_ranges(rowinfo: torch.Tensor, bounds, rank: int, world: int, group=None):
+    """exchange_rowinfo for ranges of different sizes: every rank contributes its range padded to the longest one (an
+    equal-sized all-gather through a scratch buffer) instead of all-reducing u64[n]."""
+    lens = [bounds[r + 1] - bounds[r] for r in range(world)]
+    m = max(max(lens), 1)
+    tmp = torch.empty((world, m), dtype=rowinfo.dtype, device=rowinfo.device)
+    if lens[rank]:
+        tmp[rank, :lens[rank]].copy_(rowinfo[bounds[rank]:bounds[rank + 1]])
+    dist.all_gather_into_tensor(tmp.view(-1), tmp[rank], group=group)
+    for r in range(world):
+        if r != rank and lens[r]:
+            rowinfo[bounds[r]:bounds[r + 1]].copy_(tmp[r, :lens[r]])
+
+
 def exchange_adjacency(t, max_degree: int, lo: int, hi: int, rank: int, world: int, group=None):
     """All ranks end up with every rank's rows in one common layout -- rank r's rows at [r * slot, r * slot + count_r),
     slot = the largest count -- and a row-info array that points into it.  One in-place all-gather (each rank
@@ -271,8 +310,11 @@ class KeyShardedBuildGraph:
     What the host exchanges: the IPC handles (64 bytes per rank, once per allocation), the two all-reduces, and the
     barriers that order the phases across ranks."""
 
-    def __init__(self, g, rank: int, world: int, group=None, tensors=None, symmetric=None, alloc=None, shard_table: bool = True):
-        """symmetric: allocate the table shards and the adjacency as torch symmetric memory (CUDA VMM allocations with
+    def __init__(self, g, rank: int, world: int, group=None, tensors=None, symmetric=None, alloc=None, shard_table: bool = True,
+                 balance: bool = True):
+        """balance: cut the edge pass and the reduction into ranges with equal numbers of non-contained reads
+        (balanced_bounds) instead of equal numbers of reads.
+        symmetric: allocate the table shards and the adjacency as torch symmetric memory (CUDA VMM allocations with
         2 MB pages, mapped into every peer at rendezvous) instead of exporting the library's cudaMalloc buffers through
         legacy CUDA IPC handles.  Measured on B200: through legacy IPC mappings, random remote reads collapse (8x
         slower) once the remote footprint exceeds 1-2 GB -- the requester's TLB reach for those mappings.  Default:
@@ -292,6 +334,8 @@ class KeyShardedBuildGraph:
         # shard_table=False: the hybrid of the two modes -- table (and reads) replicated and probed locally as in Mode A,
         # adjacency partitioned by query range and read through peer pointers as in Mode B: nothing is all-gathered
         self.shard_table = shard_table
+        self.balance = balance
+        self.bounds = None                   # read-id bounds of the last run's edge pass / reduction
         if shard_table:
             g.set_shard(world, rank)
         else:
@@ -353,6 +397,10 @@ class KeyShardedBuildGraph:
         g.phase_contained(lo, hi)
         allreduce_keys(self.t.keys(), self.world, self.group, self.g)
         g.phase_finish_contained()
+        if self.balance:                            # from here on a rank's share is counted in non-contained reads
+            bounds = balanced_bounds(self.t.keys(), self.world)
+            lo, hi = bounds[self.rank], bounds[self.rank + 1]
+        self.bounds = bounds
         if self.shard_table:
             self._barrier()                         # everybody done probing before the shards are rebuilt
             g.phase_table(True)                     # own shard only: 1/world of the single-GPU cost
@@ -365,7 +413,10 @@ class KeyShardedBuildGraph:
             g.phase_edges(lo, hi)               # rows of the own query range stay here
         meta = torch.tensor([int(g.stats()["max_degree"])], device=self.t.device, dtype=torch.int64)
         dist.all_reduce(meta, op=dist.ReduceOp.MAX, group=self.group)
-        exchange_rowinfo(self.t.rowinfo(), n, self.rank, self.world, self.group)  # starts are offsets in the owner's buffer
+        if self.balance:
+            exchange_rowinfo_ranges(self.t.rowinfo(), bounds, self.rank, self.world, self.group)
+        else:
+            exchange_rowinfo(self.t.rowinfo(), n, self.rank, self.world, self.group)  # starts are offsets in the owner's buffer
         g.set_max_degree(int(meta[0]))
         if self.symmetric:
             g.import_peer_ptrs(self.MEM_ROWS, self._symm[self.MEM_ROWS][1], bounds)

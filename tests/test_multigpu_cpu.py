@@ -145,25 +145,26 @@ class FakeShardCtx(FakeCtx):
     def sync(self): self.log.append("sync")
 
 
-def _worker_b(rank, world, port, q):
+def _worker_b(rank, world, port, q, balance):
     sys.path.insert(0, ROOT)
     from disco_b200 import multigpu
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     g = FakeShardCtx(rank, world)
-    multigpu.KeyShardedBuildGraph(g, rank, world, tensors=FakeTensors(g)).build_graph(50, 4)
+    multigpu.KeyShardedBuildGraph(g, rank, world, tensors=FakeTensors(g), balance=balance).build_graph(50, 4)
     q.put((rank, g.keys.numpy().copy(), g.rowinfo.numpy().copy(), g.final_maxdeg, g.log, g.imported))
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("balance", [False, True], ids=["by_reads", "by_survivors"])
 @pytest.mark.parametrize("world", [2, 3])
-def test_key_sharded_driver_gloo(world):
+def test_key_sharded_driver_gloo(world, balance):
     sys.path.insert(0, ROOT)
     from disco_b200 import multigpu
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 31500 + os.getpid() % 2000 + world
-    procs = [ctx.Process(target=_worker_b, args=(r, world, port, q)) for r in range(world)]
+    port = 31500 + os.getpid() % 2000 + world + 7 * int(balance)
+    procs = [ctx.Process(target=_worker_b, args=(r, world, port, q, balance)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
@@ -172,6 +173,10 @@ def test_key_sharded_driver_gloo(world):
         assert p.exitcode == 0
     parts = [multigpu.partition(N, r, world) for r in range(world)]
     keys = np.stack([_keys_for(r, *parts[r]) for r in range(world)]).view(np.uint64).min(axis=0).view(np.int64)
+    if balance:   # the edge pass and the reduction run on ranges with equal numbers of non-contained reads
+        b = multigpu.balanced_bounds(torch.from_numpy(keys), world, block=4096)
+        assert b[0] == 0 and b[-1] == N and all(x <= y for x, y in zip(b, b[1:]))
+        parts = [(b[r], b[r + 1]) for r in range(world)]
     _, infos, mds = zip(*[_rows_for(r, *parts[r]) for r in range(world)])
     info_sum = np.sum(np.stack(infos), axis=0)     # disjoint ranges: the sum is the union; starts stay owner-local
     for rank, k, info, md, log, imported in res:
@@ -298,3 +303,57 @@ def test_allreduce_keys_gloo(world, frac):
     want = np.stack([_sparse_keys(r, n, frac) for r in range(world)]).view(np.uint64).min(axis=0).view(np.int64)
     for _, k in res:
         assert np.array_equal(k, want)
+
+
+def test_balanced_bounds():
+    """ranges with equal numbers of non-contained reads (to within a block), whatever the distribution of the contained ones"""
+    sys.path.insert(0, ROOT)
+    from disco_b200 import multigpu
+    rng = np.random.default_rng(9)
+    n = 1_000_003
+    p = np.linspace(0.0, 0.6, n)                      # reads late in the file are contained far more often
+    keys = np.where(rng.random(n) < p, rng.integers(0, 1 << 40, size=n), -1).astype(np.int64)
+    alive = keys == -1
+    for world in (1, 2, 3, 8):
+        for block in (64, 4096):
+            b = multigpu.balanced_bounds(torch.from_numpy(keys), world, block)
+            assert len(b) == world + 1 and b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+            assert all(x % block == 0 for x in b[1:-1])
+            per = [int(alive[b[r]:b[r + 1]].sum()) for r in range(world)]
+            assert max(per) - min(per) <= 2 * block, (world, block, per)
+    # degenerate inputs: nothing contained, everything contained, fewer reads than one block
+    for keys in (np.full(5000, -1, dtype=np.int64), np.zeros(5000, dtype=np.int64), np.full(10, -1, dtype=np.int64)):
+        b = multigpu.balanced_bounds(torch.from_numpy(keys), 4, 4096)
+        assert b[0] == 0 and b[-1] == len(keys) and all(x <= y for x, y in zip(b, b[1:]))
+
+
+def _ranges_worker(rank, world, port, q, bounds, n):
+    sys.path.insert(0, ROOT)
+    from disco_b200 import multigpu
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    info = torch.zeros(n, dtype=torch.int64)
+    info[bounds[rank]:bounds[rank + 1]] = torch.arange(bounds[rank], bounds[rank + 1]) * 1000 + rank + 1
+    multigpu.exchange_rowinfo_ranges(info, bounds, rank, world)
+    q.put((rank, info.numpy().copy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("bounds", [[0, 300, 1000], [0, 0, 700, 1000], [0, 512, 512, 1000]], ids=["uneven2", "empty_first", "empty_middle"])
+def test_exchange_rowinfo_ranges_gloo(bounds):
+    n, world = bounds[-1], len(bounds) - 1
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + os.getpid() % 2000 + sum(bounds) % 97
+    procs = [ctx.Process(target=_ranges_worker, args=(r, world, port, q, bounds, n)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    want = np.zeros(n, dtype=np.int64)
+    for r in range(world):
+        want[bounds[r]:bounds[r + 1]] = np.arange(bounds[r], bounds[r + 1]) * 1000 + r + 1
+    for _, info in res:
+        assert np.array_equal(info, want)

@@ -21,9 +21,11 @@ packed, lens = host.pack_codes(rs.codes, rs.off)
 g = gpu.GpuBuildGraph(local)
 g.set_stream(torch.cuda.current_stream().cuda_stream)
 g.load_reads(packed, lens)
-getattr(multigpu, %r)(g, rank, world).build_graph(50, 4)
+drv = %s
+drv.build_graph(50, 4)
 e = g.edges(); c = g.contained()
-lo, hi = multigpu.partition(rs.n, rank, world)
+b = getattr(drv, "bounds", None)           # ranges with equal numbers of non-contained reads, or the plain partition
+lo, hi = (b[rank], b[rank + 1]) if b else multigpu.partition(rs.n, rank, world)
 assert ((e["src"] >= lo) & (e["src"] < hi)).all()          # each rank emits the edges whose lower endpoint it owns
 gathered = [None] * world
 dist.all_gather_object(gathered, (e.tobytes(), c.tobytes()))
@@ -38,7 +40,10 @@ dist.destroy_process_group()
 '''
 
 
-@pytest.mark.parametrize("driver", ["ShardedBuildGraph", "KeyShardedBuildGraph"], ids=["modeA_replicated", "modeB_key_sharded"])
+@pytest.mark.parametrize("driver", ["multigpu.ShardedBuildGraph(g, rank, world)", "multigpu.KeyShardedBuildGraph(g, rank, world)",
+                                    "multigpu.KeyShardedBuildGraph(g, rank, world, shard_table=False)",
+                                    "multigpu.KeyShardedBuildGraph(g, rank, world, shard_table=False, balance=False)"],
+                         ids=["modeA_gathered", "modeB_key_sharded", "replicated_table_partitioned_adjacency", "the_same_unbalanced"])
 def test_two_gpus_match_one(tmp_path, driver):
     import torch
     if torch.cuda.device_count() < 2:
