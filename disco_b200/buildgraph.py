@@ -94,12 +94,12 @@ class BuildGraph:
         return out
 
     def write(self, prefix: str, shards: int = 1):
-        """Writes the files runDisco.sh expects for -n <shards>: all edges go to shard 0 with mark
-        flag 2, the other shards are created empty."""
+        """Writes the files runDisco.sh expects for -n <shards>: the edges as the reference's per-thread
+        partial graphs (shard t owns a contiguous range of reads; mark flags 2 / 0 / 1, OverlapGraph.cpp:826-859), the
+        contained rows in shard 0 (rows of one container stay together), the other containedReads files empty."""
         res = self.result
         os.makedirs(os.path.dirname(os.path.abspath(prefix)) or ".", exist_ok=True)
+        host.write_pargraph_sharded(prefix, shards, res.edges, res.n, res.file_index, res.lens)
         for t in range(shards):
-            e = res.edges if t == 0 else res.edges[:0]
             c = res.crows if t == 0 else res.crows[:0]
-            host.write_pargraph(f"{prefix}_{t}_parGraph.txt", e, res.file_index, res.lens, flag=2)
             host.write_contained(f"{prefix}_{t}_containedReads.txt", c, res.file_index, res.lens)

@@ -1168,6 +1168,21 @@ int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, ui
     return DISCO_OK;
 }
 
+// The reduced edges put into (src, dst) order where they lie in HBM, so that disco_gpu_get_edges returns them sorted and
+// the host has nothing left to sort (the emission kernel appends them in whatever order its warps finish).  The pinned
+// sink, if any, keeps the emission order: after this call disco_gpu_get_edges copies from the device again.
+int disco_gpu_sort_edges(disco_ctx *ctx)
+{
+    if (!ctx || !ctx->have_reduced) return fail(ctx, DISCO_E_ARG, "reduction not finished");
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long launches = 0;
+    const cudaError_t e = sort_edges_device(ctx->d_edges, ctx->n_edges, ctx->reads.n, ctx->stream, &launches);
+    count_launches(launches);
+    if (e != cudaSuccess) return fail(ctx, e == cudaErrorMemoryAllocation ? DISCO_E_NOMEM : DISCO_E_CUDA, "edge sort failed: %s", cudaGetErrorString(e));
+    ctx->sink_filled = false;
+    return DISCO_OK;
+}
+
 // ---- first consumer step on the device-resident edges (simplify.cu) ----------------------------------------------------
 int disco_gpu_simplify(disco_ctx *ctx, uint32_t min_overlap, uint32_t min_reads, uint32_t min_len, uint64_t *n_edges, uint64_t *n_inner)
 {

@@ -137,6 +137,8 @@ bool edges_flat_supported(int max_len, int stride, int K);
 // candidate-buffer entries the flat probe kernel may leave unused (one partly filled slice per resident warp)
 uint64_t edges_flat_slack(int num_sms);
 // simplify.cu: composite-edge contraction + dead-end removal on a reduced edge list; allocates *d_out / *d_inner (cudaFree)
+// reduced edges sorted by (src, dst) on the device (simplify.cu)
+cudaError_t sort_edges_device(disco_edge *d_edges, uint64_t n, uint64_t n_reads, cudaStream_t s, unsigned long long *launches);
 cudaError_t run_simplify(const disco_edge *d_edges, uint64_t ne, uint64_t n_reads, const uint16_t *d_len, int uniform_len,
                          uint32_t min_ovl, uint32_t min_reads, uint32_t min_len, cudaStream_t s,
                          disco_cedge **d_out, uint64_t *n_out, uint64_t **d_inner, uint64_t *n_inner, uint64_t *rounds, uint64_t *removed_edges,

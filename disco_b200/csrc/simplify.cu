@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_radix_sort.cuh>
 
 namespace disco {
 
@@ -229,6 +230,43 @@ struct SimplifyBuffers {
     SLink *L[2] = {nullptr, nullptr};
     unsigned long long *counters = nullptr; // [0] active / removed, [1..3] output cursors
 };
+
+// ---- the reduced edge list in the order the files want it (src, dst ascending: the writers and parsimplify's loader walk it
+// node by node) -- one radix sort of the 64-bit key (src << 32 | dst) with the 16-byte records as values.  A pair of reads
+// has at most one reduced edge (the lower id's overlap wins), so the key is a total order.
+__global__ void k_edge_keys(const disco_edge *e, uint64_t n, uint64_t *keys)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ((uint64_t)e[i].src << 32) | e[i].dst;
+}
+
+struct Edge16 { uint64_t a, b; }; // disco_edge as an opaque 16-byte value
+
+cudaError_t sort_edges_device(disco_edge *d_edges, uint64_t n, uint64_t n_reads, cudaStream_t s, unsigned long long *launches)
+{
+    if (n < 2) return cudaSuccess;
+    cudaError_t err = cudaSuccess;
+    uint64_t *k0 = nullptr, *k1 = nullptr;
+    Edge16 *v1 = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    int hi_bit = 33; // bits of the key that can be set: 32 for dst + what the largest read id needs
+    while (hi_bit < 64 && (n_reads >> (hi_bit - 32))) hi_bit++;
+    Edge16 *v0 = reinterpret_cast<Edge16 *>(d_edges);
+    if ((err = cudaMalloc(&k0, n * 8)) != cudaSuccess) goto out;
+    if ((err = cudaMalloc(&k1, n * 8)) != cudaSuccess) goto out;
+    if ((err = cudaMalloc(&v1, n * 16)) != cudaSuccess) goto out;
+    k_edge_keys<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_edges, n, k0);
+    if ((err = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, v0, v1, (int64_t)n, 0, hi_bit, s)) != cudaSuccess) goto out;
+    if ((err = cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16)) != cudaSuccess) goto out;
+    if ((err = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, v0, v1, (int64_t)n, 0, hi_bit, s)) != cudaSuccess) goto out;
+    if ((err = cudaMemcpyAsync(d_edges, v1, n * 16, cudaMemcpyDeviceToDevice, s)) != cudaSuccess) goto out;
+    err = cudaStreamSynchronize(s);
+    if (launches) *launches += 2 + (unsigned long long)((hi_bit + 7) / 8) * 2; // key kernel + copy + the sort's passes (histogram / onesweep)
+out:
+    cudaFree(k0); cudaFree(k1); cudaFree(v1); cudaFree(tmp);
+    return err != cudaSuccess ? err : cudaGetLastError();
+}
 
 #define SCK(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { err = e__; goto done; } } while (0)
 

@@ -24,7 +24,7 @@ EXPORTS = [
     "disco_gpu_phase_reduce_emit", "disco_gpu_set_shard", "disco_gpu_export_mem", "disco_gpu_import_peers",
     "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table", "disco_gpu_table_words", "disco_gpu_adopt_buffer",
     "disco_gpu_build_graph_multi", "disco_gpu_device_count", "disco_gpu_set_partition", "disco_gpu_compact_keys", "disco_gpu_apply_keys", "disco_gpu_simplify", "disco_gpu_get_simplified", "disco_gpu_simplify_stats", "disco_gpu_set_edge_sink",
-    "disco_gpu_use_reads_device", "disco_gpu_load_reads_async",
+    "disco_gpu_use_reads_device", "disco_gpu_load_reads_async", "disco_gpu_sort_edges",
 ]
 MAX_SHARDS, IPC_HANDLE_BYTES, MEM_TABLE, MEM_ROWS = 8, 64, 0, 1
 
@@ -85,6 +85,7 @@ def lib():
         L.disco_gpu_set_partition.argtypes = [vp, u32, u32, i32]
         L.disco_gpu_compact_keys.argtypes = [vp, vp, u64, C.POINTER(u64)]
         L.disco_gpu_set_edge_sink.argtypes = [vp, vp, u64]
+        L.disco_gpu_sort_edges.argtypes = [vp]
         L.disco_gpu_simplify.argtypes = [vp, u32, u32, u32, C.POINTER(u64), C.POINTER(u64)]
         L.disco_gpu_get_simplified.argtypes = [vp, vp, u64, vp, u64]
         L.disco_gpu_simplify_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), C.POINTER(C.c_float)]
@@ -310,6 +311,10 @@ class GpuBuildGraph:
         w = C.c_uint64()
         self._ck(self._L.disco_gpu_get_edges(self._h, out.ctypes.data, len(out), C.byref(w)), "get_edges")
         return out[:w.value]
+
+    def sort_edges(self):
+        """sort the reduced edges by (src, dst) on the device; edges() then returns them in file order"""
+        self._ck(self._L.disco_gpu_sort_edges(self._h), "sort_edges")
 
     def set_edge_sink(self, host_ptr: int, capacity: int):
         """pinned host buffer (EDGE_DTYPE[capacity]) the emission kernel fills while it runs; 0 clears it"""

@@ -10,7 +10,7 @@ EXPORTS = ["disco_host_last_error", "disco_host_test_read", "disco_reads_new", "
            "disco_reads_add_records", "disco_reads_finalize", "disco_reads_count", "disco_reads_records",
            "disco_reads_words_per_read", "disco_reads_packed", "disco_reads_len", "disco_reads_file_index",
            "disco_reads_min_len", "disco_reads_max_len", "disco_host_pack_codes", "disco_write_pargraph",
-           "disco_write_contained", "disco_host_sort_contained", "disco_host_sort_edges"]
+           "disco_write_contained", "disco_host_sort_contained", "disco_host_sort_edges", "disco_write_pargraph_sharded"]
 
 _lib = None
 
@@ -47,6 +47,7 @@ def lib():
         L.disco_host_pack_codes.argtypes = [vp, vp, u64, u32, vp, vp, i32]
         L.disco_write_pargraph.argtypes = [C.c_char_p, vp, u64, vp, vp, i32, i32]
         L.disco_write_contained.argtypes = [C.c_char_p, vp, u64, vp, vp, i32]
+        L.disco_write_pargraph_sharded.argtypes = [C.c_char_p, u32, vp, u64, u64, vp, vp]
         L.disco_host_sort_contained.argtypes = [vp, u64, vp, u32]
         L.disco_host_sort_edges.argtypes = [vp, u64]
         _lib = L
@@ -146,6 +147,15 @@ def write_pargraph(path, edges, file_index, lens, flag=2, append=False):
     fi = np.ascontiguousarray(file_index, dtype=np.uint64)
     ln = np.ascontiguousarray(lens, dtype=np.uint16)
     _ck(lib().disco_write_pargraph(path.encode(), edges.ctypes.data, len(edges), fi.ctypes.data, ln.ctypes.data, flag, int(append)))
+
+
+def write_pargraph_sharded(prefix, shards, edges, n_reads, file_index, lens):
+    """<prefix>_<t>_parGraph.txt, t = 0..shards-1: the reference's per-thread partial graphs with their mark flags
+    (edges sorted by (src, dst))"""
+    edges = np.ascontiguousarray(edges)
+    fi = np.ascontiguousarray(file_index, dtype=np.uint64)
+    ln = np.ascontiguousarray(lens, dtype=np.uint16)
+    _ck(lib().disco_write_pargraph_sharded(prefix.encode(), shards, edges.ctypes.data, len(edges), n_reads, fi.ctypes.data, ln.ctypes.data))
 
 
 def write_contained(path, rows, file_index, lens, append=False):

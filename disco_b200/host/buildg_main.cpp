@@ -7,9 +7,11 @@
 // Mirrors: parseArguments (main.cpp:79-150: unknown option -> usage + exit 1; no args / -h -> usage + exit 0),
 // readOverlapParameter (main.cpp:152-176: MinOverlap4BuildGraph, default 30, missing file -> exit 1),
 // readCheckpointInfo (main.cpp:178-204: GC=Complete -> nothing to do), Dataset's ReadIDMap (Dataset.cpp:103-129),
-// the file set runDisco.sh lists for -n <t>.  -t is the number of output shards (and host threads); all
-// edges and rows go to shard 0 with mark flag 2, the other shards are created empty (accepted by parsimplify /
-// fullsimplify).  -m and -w are accepted and ignored (the reference ignores -w too, OverlapGraph.cpp:59-81).
+// the file set runDisco.sh lists for -n <t>.  -t is the number of output shards (and host threads): shard t
+// gets the edges of a contiguous range of reads with the reference's mark flags (2 = both endpoints in this shard, 0 / 1 =
+// only the source / destination, the edge then also appears in the other endpoint's shard: OverlapGraph.cpp:826-859), so
+// that runDisco.sh's one-parsimplify-per-file step runs in parallel; the contained rows go to shard 0 (rows of one
+// container must stay together).  -m and -w are accepted and ignored (the reference ignores -w too, OverlapGraph.cpp:59-81).
 // New, optional: -g <device>[,<device>...] (or env DISCO_GPUS / DISCO_GPU), default 0.  Several devices = the key-sharded
 // partitioning of buildG-MPIRMA inside this one process (disco_gpu_build_graph_multi: reads replicated, table sharded
 // by key, adjacency by read range, remote shards read over NVLink).  Fatal errors print the reference's message and, unlike the
@@ -191,6 +193,9 @@ int main(int argc, char **argv)
     vector<disco_edge> edges(n_edges);
     disco_stats st{};
     for (size_t r = 0; r < ctxs.size(); r++) {
+        // sorted by (src, dst) where they lie in HBM; context r holds the edges whose source is in its read range, so the
+        // concatenation in context order is sorted too
+        if (disco_gpu_sort_edges(ctxs[r])) die(disco_gpu_last_error(ctxs[r]));
         if (disco_gpu_get_edges(ctxs[r], edges.data() + first[r], first[r + 1] - first[r], &w)) die(disco_gpu_last_error(ctxs[r]));
         disco_stats sr;
         disco_gpu_get_stats(ctxs[r], &sr);
@@ -217,11 +222,10 @@ int main(int argc, char **argv)
     const uint64_t *fi = disco_reads_file_index(reads);
     const uint16_t *len = disco_reads_len(reads);
     disco_host_sort_contained(rows.data(), rows.size(), len, (uint32_t)min_overlap);
-    disco_host_sort_edges(edges.data(), edges.size());
+    if (disco_write_pargraph_sharded(prefix.c_str(), (uint32_t)threads, edges.data(), edges.size(), n, fi, len)) die(disco_host_last_error());
     for (unsigned long long t = 0; t < threads; t++) {
         const string tp = prefix + "_" + to_string(t);
         if (disco_write_contained((tp + "_containedReads.txt").c_str(), rows.data(), t == 0 ? rows.size() : 0, fi, len, 0)) die(disco_host_last_error());
-        if (disco_write_pargraph((tp + "_parGraph.txt").c_str(), edges.data(), t == 0 ? edges.size() : 0, fi, len, 2, 0)) die(disco_host_last_error());
         touch(tp + "_startRead.txt", t == 0 ? "1\n" : "");
     }
     touch(prefix + "_CheckpointInfo.txt", "CCR=Complete\nGC=Complete\n"); // OverlapGraph.cpp:486-493, main.cpp:64-70

@@ -537,26 +537,80 @@ int write_lines(const char *path, int append, uint64_t n, size_t max_line, const
 
 extern "C" {
 
+namespace {
+// src dst orient,ovl,0,0,srcLen,offset,srcLen-1,dstLen,0,ovl-1,NA,flag   (OverlapGraph.cpp:811-867)
+inline char *put_edge(char *p, const disco_edge &e, const uint64_t *file_index, const uint16_t *len, int flag)
+{
+    const uint64_t sl = len[e.src], dl = len[e.dst], off = e.offset, ovl = sl - off;
+    p = put_u64(p, file_index[e.src]); *p++ = '\t';
+    p = put_u64(p, file_index[e.dst]); *p++ = '\t';
+    p = put_u64(p, e.orient); *p++ = ',';
+    p = put_u64(p, ovl); p = put_str(p, ",0,0,");
+    p = put_u64(p, sl); *p++ = ',';
+    p = put_u64(p, off); *p++ = ',';
+    p = put_u64(p, sl - 1); *p++ = ',';
+    p = put_u64(p, dl); p = put_str(p, ",0,");
+    p = put_u64(p, ovl - 1); p = put_str(p, ",NA,");
+    if (flag < 0) { *p++ = '-'; p = put_u64(p, (uint64_t)(-(long long)flag)); } else p = put_u64(p, (uint64_t)flag);
+    *p++ = '\n';
+    return p;
+}
+} // namespace
+
 int disco_write_pargraph(const char *path, const disco_edge *edges, uint64_t n, const uint64_t *file_index,
                          const uint16_t *len, int flag, int append)
 {
-    // src dst orient,ovl,0,0,srcLen,offset,srcLen-1,dstLen,0,ovl-1,NA,flag   (OverlapGraph.cpp:811-867)
-    return write_lines(path, append, n, 160, [&](uint64_t i, char *p) {
-        const disco_edge &e = edges[i];
-        const uint64_t sl = len[e.src], dl = len[e.dst], off = e.offset, ovl = sl - off;
-        p = put_u64(p, file_index[e.src]); *p++ = '\t';
-        p = put_u64(p, file_index[e.dst]); *p++ = '\t';
-        p = put_u64(p, e.orient); *p++ = ',';
-        p = put_u64(p, ovl); p = put_str(p, ",0,0,");
-        p = put_u64(p, sl); *p++ = ',';
-        p = put_u64(p, off); *p++ = ',';
-        p = put_u64(p, sl - 1); *p++ = ',';
-        p = put_u64(p, dl); p = put_str(p, ",0,");
-        p = put_u64(p, ovl - 1); p = put_str(p, ",NA,");
-        if (flag < 0) { *p++ = '-'; p = put_u64(p, (uint64_t)(-(long long)flag)); } else p = put_u64(p, (uint64_t)flag);
-        *p++ = '\n';
-        return p;
-    });
+    return write_lines(path, append, n, 160, [&](uint64_t i, char *p) { return put_edge(p, edges[i], file_index, len, flag); });
+}
+
+// The reference's partial graphs: each BuildGraph thread finalises its own set of nodes and appends their edges to its own
+// file; an edge whose two endpoints were finalised by the same thread is written once with mark flag 2, an edge between
+// nodes of different threads twice -- by the source's thread with flag 0 ("only source is marked") and by the
+// destination's thread with flag 1 (OverlapGraph.cpp:826-833, :852-859).  One parsimplify per file then contracts
+// through the nodes marked in that file only (OverlapGraphSimple.cpp:632-641), which is what lets them run in parallel.
+// Here shard t owns the reads [t * n_reads / shards, (t+1) * n_reads / shards).  `edges` sorted by (src, dst).
+int disco_write_pargraph_sharded(const char *prefix, uint32_t shards, const disco_edge *edges, uint64_t n, uint64_t n_reads,
+                                 const uint64_t *file_index, const uint16_t *len)
+{
+    if (!prefix || shards < 1) return fail("bad arguments");
+    std::vector<uint64_t> bound(shards + 1);
+    for (uint32_t t = 0; t <= shards; t++) bound[t] = (uint64_t)((unsigned __int128)n_reads * t / shards);
+    auto shard_of = [&](uint32_t r) { return (uint32_t)(std::upper_bound(bound.begin() + 1, bound.end(), (uint64_t)r) - (bound.begin() + 1)); };
+    for (uint64_t i = 1; i < n; i++)
+        if (edges[i].src < edges[i - 1].src) return fail("disco_write_pargraph_sharded: edges must be sorted by source read");
+    // edges that cross into a later shard, grouped by the destination's shard (sources ascending inside a group)
+    std::vector<std::vector<uint64_t>> incoming(shards);
+    if (shards > 1) {
+        const int T = std::max(1, omp_get_max_threads());
+        std::vector<std::vector<std::vector<uint64_t>>> part(T, std::vector<std::vector<uint64_t>>(shards));
+#pragma omp parallel num_threads(T)
+        {
+            const int me = omp_get_thread_num();
+            const uint64_t lo = n * (uint64_t)me / T, hi = n * (uint64_t)(me + 1) / T;
+            for (uint64_t i = lo; i < hi; i++) {
+                const uint32_t a = shard_of(edges[i].src), b = shard_of(edges[i].dst);
+                if (a != b) part[me][b].push_back(i);
+            }
+        }
+        for (uint32_t t = 0; t < shards; t++)
+            for (int k = 0; k < T; k++) incoming[t].insert(incoming[t].end(), part[k][t].begin(), part[k][t].end());
+    }
+    for (uint32_t t = 0; t < shards; t++) {
+        const std::string path = std::string(prefix) + "_" + std::to_string(t) + "_parGraph.txt";
+        const disco_edge *first = std::lower_bound(edges, edges + n, bound[t], [](const disco_edge &e, uint64_t v) { return (uint64_t)e.src < v; });
+        const disco_edge *last = std::lower_bound(edges, edges + n, bound[t + 1], [](const disco_edge &e, uint64_t v) { return (uint64_t)e.src < v; });
+        const uint64_t own = (uint64_t)(last - first);
+        const std::vector<uint64_t> &in = incoming[t];
+        const int rc = write_lines(path.c_str(), 0, own + in.size(), 160, [&](uint64_t i, char *p) {
+            if (i < own) {
+                const disco_edge &e = first[i];
+                return put_edge(p, e, file_index, len, e.dst < bound[t + 1] ? 2 : 0); // (src < dst: the destination cannot lie in an earlier shard)
+            }
+            return put_edge(p, edges[in[i - own]], file_index, len, 1);
+        });
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 int disco_write_contained(const char *path, const disco_crow *rows, uint64_t n, const uint64_t *file_index,

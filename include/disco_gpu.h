@@ -126,6 +126,9 @@ int disco_gpu_counts(disco_ctx *ctx, uint64_t *n_contained, uint64_t *n_edges);
 int disco_gpu_get_contained(disco_ctx *ctx, disco_crow *rows, uint64_t capacity, uint64_t *n_written);
 /* edges in device emission order (callers sort if they need a canonical order) */
 int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, uint64_t *n_written);
+/* Sorts the reduced edges by (src, dst) on the device: disco_gpu_get_edges then returns them in the order the parGraph
+ * writer wants (replaces the host-side sort of ~10^7 records). */
+int disco_gpu_sort_edges(disco_ctx *ctx);
 /* Optional: a page-locked host buffer the emission kernel fills itself (over PCIe while it runs); disco_gpu_get_edges into
  * that same buffer then needs no copy.  NULL clears it; results larger than the capacity are not mirrored. */
 int disco_gpu_set_edge_sink(disco_ctx *ctx, disco_edge *host_pinned, uint64_t capacity);

@@ -59,6 +59,12 @@ int disco_write_pargraph(const char *path, const disco_edge *edges, uint64_t n, 
                          const uint16_t *len, int flag, int append);
 int disco_write_contained(const char *path, const disco_crow *rows, uint64_t n, const uint64_t *file_index,
                           const uint16_t *len, int append);
+/* <prefix>_<t>_parGraph.txt for t = 0..shards-1, the reference's partial graphs (one file per BuildGraph thread): shard t
+ * owns the reads [t*n_reads/shards, (t+1)*n_reads/shards); an edge inside one shard is written once with mark flag 2, an
+ * edge between shards by the source's shard with flag 0 and by the destination's with flag 1 (OverlapGraph.cpp:826-859),
+ * so that one parsimplify per file can run in parallel (OverlapGraphSimple.cpp:632-641).  edges sorted by (src, dst). */
+int disco_write_pargraph_sharded(const char *prefix, uint32_t shards, const disco_edge *edges, uint64_t n, uint64_t n_reads,
+                                 const uint64_t *file_index, const uint16_t *len);
 
 #ifdef __cplusplus
 }

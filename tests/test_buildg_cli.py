@@ -2,7 +2,7 @@
 import os
 import subprocess
 import pytest
-from helpers import GOLDEN, load_golden, HERE
+from helpers import GOLDEN, load_golden, HERE, check_partial_graphs
 
 BUILDG = os.path.join(os.path.dirname(HERE), "disco_b200", "bin", "buildG")
 
@@ -48,8 +48,10 @@ def test_files_match_reference(tmp_path, name):
     for t in range(3):   # every file runDisco.sh lists for -n 3 must exist
         for suffix in ("parGraph", "containedReads", "startRead"):
             assert os.path.exists(f"{prefix}_{t}_{suffix}.txt")
-    edges = sorted(l.rstrip("\n") for t in range(3) for l in open(f"{prefix}_{t}_parGraph.txt"))
-    assert edges == sorted(l + ",2" for l in g["ref_edges"])
+    # -t 3: three partial graphs with the reference's mark flags; their union is the reference's edge set
+    assert check_partial_graphs(prefix, 3) == set(g["ref_edges"])
+    if len(g["ref_edges"]) > 50:
+        assert all(os.path.getsize(f"{prefix}_{t}_parGraph.txt") > 0 for t in range(3))
     rows = [l.rstrip("\n") for t in range(3) for l in open(f"{prefix}_{t}_containedReads.txt")]
     assert rows == g["ref_crows"]
     kind = "Paired-end" if paired else "Singleton"
@@ -75,8 +77,8 @@ def test_several_gpus_in_one_process(tmp_path, name):
     devs = "0,1,0" if torch.cuda.device_count() >= 2 else "0,0,0"
     r = _run(["-pe" if "paired" in name else "-se", str(fa), "-f", prefix, "-p", str(cfg), "-t", "2", "-g", devs])
     assert r.returncode == 0, r.stdout + r.stderr
-    edges = sorted(l.rstrip("\n") for t in range(2) for l in open(f"{prefix}_{t}_parGraph.txt"))
-    assert edges == sorted(l + ",2" for l in g["ref_edges"])
+    assert check_partial_graphs(prefix, 2) == set(g["ref_edges"])
+    edges = sorted(l + ",2" for l in g["ref_edges"])
     rows = [l.rstrip("\n") for t in range(2) for l in open(f"{prefix}_{t}_containedReads.txt")]
     assert rows == g["ref_crows"]
     # -g all: every visible device

@@ -77,3 +77,27 @@ def test_loaders_agree(name, monkeypatch):
     g2.build_graph(m, 4)
     _same(_result(g), _result(g2))
     g.close(); g2.close()
+
+
+@pytest.mark.parametrize("n", [5, 3000, 400_000])
+def test_device_edge_sort(n):
+    """disco_gpu_sort_edges puts the reduced edges into (src, dst) order where they lie in HBM: get_edges then returns
+    exactly what the host-side sort of the emission order gives -- also when a pinned sink mirrored the emission."""
+    import torch
+    rs = synth.single_genome(n, 150, 30.0 if n > 100 else 2.0, seed=3)
+    packed, lens = host.pack_codes(rs.codes, rs.off)
+    g = gpu.GpuBuildGraph(0)
+    g.load_reads(packed, lens)
+    sink = torch.empty((n * 2 + 16, 4), dtype=torch.int32).pin_memory()
+    view = sink.numpy().view(gpu.EDGE_DTYPE).reshape(-1)
+    g.set_edge_sink(sink.data_ptr(), sink.shape[0])
+    g.build_graph(50, 4)
+    raw = g.edges(out=view).copy()              # emission order, from the sink
+    want = gpu.sort_edges(raw)
+    g.sort_edges()
+    got = g.edges()
+    assert np.array_equal(got, want)
+    assert np.array_equal(g.edges(out=view), want)   # the sink is refreshed from the device after a sort
+    if n > 100:
+        assert len(got) > n // 2 and not np.array_equal(raw, want)
+    g.close()

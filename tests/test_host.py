@@ -238,3 +238,44 @@ def test_writers_many_lines_and_append(tmp_path):
     e2 = e.copy()
     host.sort_edges(e2)
     assert np.array_equal(e2, gpu.sort_edges(e))
+
+
+def test_sharded_pargraph_writer(tmp_path):
+    """the reference's per-thread partial graphs: flags 2 / 0 / 1 by read range, every edge of a node in its shard's file"""
+    from helpers import check_partial_graphs
+    rng = np.random.default_rng(8)
+    n, ne = 20_000, 150_000
+    fi = np.cumsum(rng.integers(1, 3, n)).astype(np.uint64)
+    lens = rng.integers(60, 300, n).astype(np.uint16)
+    src = rng.integers(0, n - 1, ne)
+    dst = np.minimum(src + 1 + rng.geometric(0.002, ne), n - 1)     # mostly near neighbours, some far ones
+    pairs = np.unique(np.stack([src, dst], axis=1)[src < dst], axis=0)
+    e = np.zeros(len(pairs), dtype=gpu.EDGE_DTYPE)
+    e["src"], e["dst"] = pairs[:, 0], pairs[:, 1]
+    e["offset"] = rng.integers(1, 59, len(e)); e["orient"] = rng.integers(0, 4, len(e))
+    e = gpu.sort_edges(e)
+    want = None
+    for shards in (1, 2, 3, 16):
+        prefix = str(tmp_path / f"s{shards}")
+        host.write_pargraph_sharded(prefix, shards, e, n, fi, lens)
+        got = check_partial_graphs(prefix, shards)
+        if want is None:
+            one = str(tmp_path / "one.txt")
+            host.write_pargraph(one, e, fi, lens, flag=2)
+            want = set(l.rstrip("\n").rsplit(",", 1)[0] for l in open(one))
+            assert [l.rstrip("\n") for l in open(prefix + "_0_parGraph.txt")] == [l.rstrip("\n") for l in open(one)]
+        assert got == want and len(got) == len(e)
+        for t in range(shards):          # shard t owns a contiguous range of reads
+            lo, hi = n * t // shards, n * (t + 1) // shards
+            for line in list(open(f"{prefix}_{t}_parGraph.txt"))[:2000]:
+                a, b, rest = line.rstrip("\n").split("\t")
+                flag = int(rest.rsplit(",", 1)[1])
+                sa, sb = int(np.searchsorted(fi, int(a))), int(np.searchsorted(fi, int(b)))
+                assert (lo <= sa < hi) if flag in (0, 2) else not (lo <= sa < hi)
+                assert (lo <= sb < hi) if flag in (1, 2) else not (lo <= sb < hi)
+    # unsorted input is refused, an empty edge list gives empty files
+    import pytest as _pt
+    with _pt.raises(host.HostError):
+        host.write_pargraph_sharded(str(tmp_path / "bad"), 2, e[::-1].copy(), n, fi, lens)
+    host.write_pargraph_sharded(str(tmp_path / "empty"), 3, e[:0], n, fi, lens)
+    assert all(open(str(tmp_path / f"empty_{t}_parGraph.txt")).read() == "" for t in range(3))
