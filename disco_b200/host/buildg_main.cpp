@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <future>
 #include <iomanip>
 #include <iostream>
 #include <sstream>
@@ -58,8 +59,11 @@ static void usage()
     cerr << "  -g\tCUDA device(s) to run on, comma separated, or 'all' (default 0 or $DISCO_GPUS)" << endl;
 }
 
+static future<string> g_ctx_ready; // the GPU contexts, being created on another thread
+
 [[noreturn]] static void die(const string &msg)
 {
+    if (g_ctx_ready.valid()) g_ctx_ready.wait(); // do not tear the process down under a thread that is inside the CUDA driver
     cout << endl << "Exit from buildG (B200)" << endl << "Message: " << msg << endl;
     exit(1);
 }
@@ -130,6 +134,28 @@ int main(int argc, char **argv)
         }
     }
 
+    // ---- the GPU contexts are created on another thread while the input is parsed (creating a CUDA context takes as long
+    // as parsing ten million reads)
+    vector<int> devs;
+    if (trimmed(devices) == "all") {
+        const int nd = disco_gpu_device_count();
+        if (nd < 1) die("no CUDA device");
+        for (int d = 0; d < nd && d < DISCO_MAX_SHARDS; d++) devs.push_back(d);
+    } else {
+        for (auto &d : split_tok(devices, ',')) if (!trimmed(d).empty()) devs.push_back(atoi(trimmed(d).c_str()));
+    }
+    if (devs.empty()) devs.push_back(0);
+    if (devs.size() > DISCO_MAX_SHARDS) die("at most " + to_string(DISCO_MAX_SHARDS) + " GPUs");
+    vector<disco_ctx *> ctxs(devs.size(), nullptr);
+    double t_ctx = 0;
+    g_ctx_ready = async(launch::async, [&]() -> string {
+        const double t = now();
+        for (size_t r = 0; r < devs.size(); r++)
+            if (disco_gpu_create(&ctxs[r], devs[r])) return string("GPU context: ") + disco_gpu_last_error(nullptr);
+        t_ctx = now() - t;
+        return string();
+    });
+
     // ---- Dataset (Dataset.cpp:34-149): paired files first, then single files; ReadIDMap in file-index space
     double t0 = now();
     disco_reads *reads = disco_reads_new((uint32_t)min_overlap, (int)threads);
@@ -158,21 +184,17 @@ int main(int argc, char **argv)
 
     // ---- hot path on the GPU(s)
     t0 = now();
-    vector<int> devs;
-    if (trimmed(devices) == "all") {
-        const int nd = disco_gpu_device_count();
-        if (nd < 1) die("no CUDA device");
-        for (int d = 0; d < nd && d < DISCO_MAX_SHARDS; d++) devs.push_back(d);
-    } else {
-        for (auto &d : split_tok(devices, ',')) if (!trimmed(d).empty()) devs.push_back(atoi(trimmed(d).c_str()));
+    double t_load = 0, t_graph = 0, t_fetch = 0, t1 = now();
+    {
+        const string err = g_ctx_ready.get();
+        if (!err.empty()) die(err);
     }
-    if (devs.empty()) devs.push_back(0);
-    if (devs.size() > DISCO_MAX_SHARDS) die("at most " + to_string(DISCO_MAX_SHARDS) + " GPUs");
-    vector<disco_ctx *> ctxs(devs.size(), nullptr);
+    const double t_wait = now() - t1;
+    t1 = now();
     for (size_t r = 0; r < devs.size(); r++) {
-        if (disco_gpu_create(&ctxs[r], devs[r])) die(string("GPU context: ") + disco_gpu_last_error(nullptr));
         if (disco_gpu_load_reads(ctxs[r], disco_reads_packed(reads), disco_reads_len(reads), n, disco_reads_words_per_read(reads)))
             die(string("load reads: ") + disco_gpu_last_error(ctxs[r]));
+        t_load += now() - t1; t1 = now();
     }
     if (ctxs.size() == 1) {
         if (disco_gpu_build_graph(ctxs[0], (uint32_t)min_overlap, 4 /* MAX_EDGE_PER_KMER, Common.h:62 */))
@@ -182,6 +204,7 @@ int main(int argc, char **argv)
         for (auto c : ctxs) if (*disco_gpu_last_error(c)) msg += string(" [") + disco_gpu_last_error(c) + "]";
         die(msg);
     }
+    t_graph = now() - t1; t1 = now();
     // contained rows: every context holds all of them; edges: each context holds those of its read range
     uint64_t n_contained = 0, n_edges = 0, w = 0;
     disco_gpu_counts(ctxs[0], &n_contained, nullptr);
@@ -206,8 +229,11 @@ int main(int argc, char **argv)
             st.ms_total = max(st.ms_total, sr.ms_total);
         }
     }
+    t_fetch = now() - t1; t1 = now();
     for (auto c : ctxs) disco_gpu_destroy(c);
     const double t_gpu = now() - t0;
+    cout << "GPU stage: context " << t_ctx << " s (created while the input was parsed; waited " << t_wait << " s for it), upload " << t_load << " s, graph " << t_graph << " s, sort + download " << t_fetch
+         << " s, release " << now() - t1 << " s" << endl;
     cout << "Hash Table size set to: " << st.table_buckets * 4 << endl;
     cout << "Function insertDataset() finished in " << (st.ms_table_all + st.ms_table_nc) / 1000.0 << " Seconds." << endl;
     cout << "Function markContainedReads() finished in " << (st.ms_contained + st.ms_finish_contained) / 1000.0 << " Seconds." << endl;
