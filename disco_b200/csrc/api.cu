@@ -21,7 +21,7 @@ using namespace disco;
 namespace {
 thread_local std::string g_create_error;
 
-enum Cursor { CUR_WORK = 0, CUR_WORK2, CUR_WORK3, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_CANDS, CUR_TABLE_FULL, CUR_COUNT };
+enum Cursor { CUR_WORK = 0, CUR_WORK2, CUR_WORK3, CUR_ROWS, CUR_EDGES, CUR_NCONTAINED, CUR_CROWS, CUR_CANDS, CUR_TABLE_FULL, CUR_BIN_OVERFLOW, CUR_COUNT };
 enum Ev { EV_T0 = 0, EV_TABLE_ALL, EV_CONTAINED, EV_FINISH, EV_TABLE_NC, EV_EDGES, EV_MARK, EV_EMIT, EV_EDGES_K0, EV_EDGES_K1,
           EV_CONT_K0, EV_CONT_K1, EV_PROBE_K1, EV_VERIFY_K1, EV_MARK_K0, EV_EMIT_K0, EV_COUNT };
 } // namespace
@@ -58,6 +58,12 @@ struct disco_ctx {
     uint64_t nbuckets = 0;
     uint32_t *d_filter = nullptr;
     uint64_t filter_bits = 0;
+    // binned build (kernels.cu: k_table_bin / k_table_fill): the records sorted by bucket range; kept for the rebuild
+    ulonglong2 *d_bins = nullptr;
+    unsigned long long *d_bin_count = nullptr;
+    uint64_t bin_cap = 0;
+    uint32_t nbins = 0;       // 0: direct inserts
+    bool bins_valid = false;  // the bins hold this run's records
     // containment
     unsigned long long *d_best = nullptr;
     uint32_t *d_bits = nullptr;
@@ -166,6 +172,7 @@ void free_run_buffers(disco_ctx *c)
     c->own_slots = c->own_rows = true;
     c->peer_table.ready = c->peer_rows.ready = false; // whatever the peers mapped is gone
     dfree(c->d_filter); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
+    dfree(c->d_bins); dfree(c->d_bin_count); c->nbins = 0; c->bin_cap = 0; c->bins_valid = false;
     dfree(c->d_rowinfo); dfree(c->d_edges); dfree(c->d_cands); dfree(c->d_batchinfo); dfree(c->d_cedges); dfree(c->d_inner);
     c->n_cedges = c->n_inner = 0;
     c->d_rows_active = nullptr;
@@ -526,8 +533,34 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
         CK(cudaMalloc(&ctx->d_best, n * sizeof(unsigned long long)));
         CK(cudaMalloc(&ctx->d_bits, ((n + 31) / 32) * sizeof(uint32_t)));
         CK(cudaMalloc(&ctx->d_rowinfo, n * sizeof(uint64_t)));
+        // Binned build for tables that do not fit L2 (single / replicated tables, short reads): one bin per 16 MB of
+        // table, 25 % head room per bin (a bin that overflows -- skewed k-mers -- hands the build to the direct kernel).
+        // DISCO_BINNED=0 keeps the direct inserts.
+        ctx->nbins = 0; ctx->bin_cap = 0;
+        if (ctx->tw() == 1 && table_bin_supported(ctx->reads.max_len) && !(getenv("DISCO_BINNED") && atoi(getenv("DISCO_BINNED")) == 0)) {
+            uint64_t slice = 16ULL << 20;
+            if (const char *e = getenv("DISCO_BIN_SLICE_KB")) slice = (uint64_t)std::max(1, atoi(e)) << 10; // (tests: bins on small inputs)
+            uint32_t nb = 1;
+            while ((uint64_t)nb * slice < ctx->nbuckets * 32 && nb < 1024) nb <<= 1;
+            const bool unbinned = getenv("DISCO_UNBINNED") && atoi(getenv("DISCO_UNBINNED")) == 1; // records in read order (A/B)
+            if (unbinned && nb >= 4) nb = 1;
+            if (nb >= 4 || unbinned) {
+                uint64_t cap = unbinned ? 2 * n : (2 * n / nb) + (2 * n / nb) / 4 + 4096;
+                if (const char *e = getenv("DISCO_BIN_HEADROOM")) cap = (2 * n / nb) + (uint64_t)std::max(0, atoi(e)); // (tests: force the overflow path)
+                size_t free_b = 0, total_b = 0;
+                CK(cudaMemGetInfo(&free_b, &total_b));
+                if ((uint64_t)nb * cap * sizeof(ulonglong2) < free_b / 4 &&
+                    cudaMalloc(&ctx->d_bins, (uint64_t)nb * cap * sizeof(ulonglong2)) == cudaSuccess) {
+                    CK(cudaMalloc(&ctx->d_bin_count, nb * sizeof(unsigned long long)));
+                    ctx->nbins = nb; ctx->bin_cap = cap;
+                } else {
+                    cudaGetLastError();
+                }
+            }
+        }
         ctx->run_n = n;
     }
+    ctx->bins_valid = false;
     if (ctx->pending) CK(cudaEventRecord(ctx->ev_copy[16], ctx->stream));
     CK(cudaMemsetAsync(ctx->d_best, 0xFF, n * sizeof(unsigned long long), ctx->stream));
     CK(cudaMemsetAsync(ctx->d_bits, 0, ((n + 31) / 32) * sizeof(uint32_t), ctx->stream));
@@ -555,6 +588,14 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
 }
 
 namespace {
+BinView bin_view(const disco_ctx *c)
+{
+    BinView b{};
+    b.recs = c->d_bins; b.count = c->d_bin_count; b.cap = c->bin_cap; b.nbins = c->nbins;
+    b.overflow = reinterpret_cast<unsigned int *>(c->d_cursors + CUR_BIN_OVERFLOW);
+    return b;
+}
+
 // The deferred upload (disco_gpu_load_reads_async) and the first table build as one pipeline: chunk c crosses PCIe on the
 // copy stream while the main stream re-strides chunk c-1, derives its tail sectors and inserts its records.
 int upload_and_insert(disco_ctx *ctx, const TableView &tv)
@@ -583,7 +624,8 @@ int upload_and_insert(disco_ctx *ctx, const TableView &tv)
         part.words += lo * stride; part.len += lo; part.n = m; part.tails = nullptr;
         if (ctx->reads.tails) CK(launch_make_tails(part, ctx->d_tails + lo * 4, ctx->stream));
         if (ctx->d_words_rc) CK(launch_revcomp_rows(part, ctx->d_words_rc + lo * stride, ctx->stream));
-        CK(launch_table_insert(ctx->reads, tv, ctx->K, nullptr, ctx->num_sms, ctx->stream, lo, hi));
+        if (ctx->nbins) CK(launch_table_bin(ctx->reads, tv, ctx->K, bin_view(ctx), ctx->num_sms, ctx->stream, lo, hi));
+        else CK(launch_table_insert(ctx->reads, tv, ctx->K, nullptr, ctx->num_sms, ctx->stream, lo, hi));
     }
     ctx->pending = false;
     return DISCO_OK;
@@ -599,13 +641,29 @@ int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained)
     if (ctx->d_filter) CK(cudaMemsetAsync(ctx->d_filter, 0, ctx->filter_bits / 8, ctx->stream));
     ctx->table_has_contained = !exclude_contained;
     const TableView tv = table_view(ctx);
-    if (ctx->pending) { // the reads are still on the host: upload and insert chunk by chunk
-        if (exclude_contained) return fail(ctx, DISCO_E_ARG, "reads not uploaded yet");
-        const int rc = upload_and_insert(ctx, tv);
-        if (rc) return rc;
-    } else {
-        CK(launch_table_insert(ctx->reads, tv, ctx->K, exclude_contained ? ctx->d_bits : nullptr, ctx->num_sms, ctx->stream));
+    const uint32_t *skip = exclude_contained ? ctx->d_bits : nullptr;
+    if (ctx->pending && exclude_contained) return fail(ctx, DISCO_E_ARG, "reads not uploaded yet");
+    if (!ctx->nbins) { // direct inserts
+        if (ctx->pending) { const int rc = upload_and_insert(ctx, tv); if (rc) return rc; }
+        else CK(launch_table_insert(ctx->reads, tv, ctx->K, skip, ctx->num_sms, ctx->stream));
+        return record(ctx, exclude_contained ? EV_TABLE_NC : EV_TABLE_ALL);
     }
+    // binned build: hash + bin (first build of a run; the rebuild without the contained reads re-uses the bins), fill bin by
+    // bin; if a bin overflowed (flag on the device, no host round trip) the fill does nothing and the gated direct kernel runs
+    const BinView bv = bin_view(ctx);
+    if (!ctx->bins_valid) {
+        CK(cudaMemsetAsync(ctx->d_bin_count, 0, ctx->nbins * sizeof(unsigned long long), ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_BIN_OVERFLOW, 0, sizeof(unsigned long long), ctx->stream));
+        if (ctx->pending) { const int rc = upload_and_insert(ctx, tv); if (rc) return rc; }
+        else CK(launch_table_bin(ctx->reads, tv, ctx->K, bv, ctx->num_sms, ctx->stream));
+        ctx->bins_valid = true;
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
+        CK(launch_table_fill(tv, bv, skip, skip ? 1 : 0, ctx->d_cursors + CUR_WORK, 2 * ctx->reads.n, ctx->num_sms, ctx->stream));
+    } else {
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_WORK, 0, sizeof(unsigned long long), ctx->stream));
+        CK(launch_table_fill(tv, bv, skip, 1, ctx->d_cursors + CUR_WORK, 2 * ctx->reads.n, ctx->num_sms, ctx->stream));
+    }
+    CK(launch_table_insert(ctx->reads, tv, ctx->K, skip, ctx->num_sms, ctx->stream, 0, ~0ULL, bv.overflow));
     return record(ctx, exclude_contained ? EV_TABLE_NC : EV_TABLE_ALL);
 }
 

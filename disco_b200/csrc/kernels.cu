@@ -18,6 +18,7 @@
 // read table buckets / adjacency rows of other GPUs through NVLink peer pointers.
 #include "dna.cuh"
 #include "kernels.cuh"
+#include <algorithm>
 #include <atomic>
 #include <cstdlib>
 #include "../../include/disco_gpu.h"
@@ -274,9 +275,10 @@ __device__ __forceinline__ void warp_stat_add(unsigned long long *stats, int slo
 // Warp per read; quad 0 inserts the prefix record and quad 1 the suffix record cooperatively: each lane of the quad
 // reads one slot of the bucket (one coalesced sector), the quad votes, the first empty lane does the CAS.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits, uint64_t r_lo, uint64_t r_hi)
+__global__ void __launch_bounds__(kThreads) k_table_insert(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits, uint64_t r_lo, uint64_t r_hi, const unsigned int *gate)
 {
     extern __shared__ uint64_t smem[];
+    if (gate && !*gate) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int WP = ((rv.max_len + 31) >> 5) + 2;
     uint32_t *A = reinterpret_cast<uint32_t *>(smem + (size_t)wib * 2 * WP), *R = A + 2 * WP;
@@ -341,9 +343,10 @@ __device__ __forceinline__ void stage_lane(const ReadsView &rv, uint64_t r, bool
 // Table build, 32 reads per warp step.  Each lane hashes the prefix and suffix k-mer of its read; the 64 records are
 // then inserted eight at a time, one record per quad, cooperatively (four lanes read the four slots of the bucket --
 // one sector --, vote, the first empty lane does the CAS).
-__global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits, uint64_t r_lo, uint64_t r_hi)
+__global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, TableView tv, int K, const uint32_t *skip_bits, uint64_t r_lo, uint64_t r_hi, const unsigned int *gate)
 {
     extern __shared__ uint64_t smem[];
+    if (gate && !*gate) return;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int WP = ((rv.max_len + 31) >> 5) + 2;
     const int AU = lane_array_u32(rv.max_len);
@@ -400,6 +403,122 @@ __global__ void __launch_bounds__(kThreads) k_table_insert_lanes(ReadsView rv, T
             }
         }
         __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Binned table build.  Inserting 2n records at random into a table of 96n bytes costs two DRAM transactions per record
+// (the bucket's sector comes in, the dirty sector goes out) at the random-access rate -- and on a table replicated over
+// the GPUs of a node every rank inserts ALL reads.  So the records are first sorted by bucket range: k_table_bin hashes
+// the reads (lane per read, as k_table_insert_lanes) and appends every (fingerprint, slot value) to the bin its bucket
+// falls into -- a block-wide histogram in shared memory, one global atomic per bin and block step, 16-byte stores that L2
+// merges into full lines; k_table_fill then walks the bins in order with a few warps per SM, so that the 16 MB slice of
+// the table one bin maps to is filled while it sits in L2: the inserts become L2 atomics and the slice goes to DRAM once.
+// The table's content is the same set of records; which of a bucket's four slots a record lands in was never defined.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_table_bin(ReadsView rv, TableView tv, int K, BinView bv, uint64_t r_lo, uint64_t r_hi)
+{
+    extern __shared__ uint64_t smem[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int WP = ((rv.max_len + 31) >> 5) + 2;
+    const int AU = lane_array_u32(rv.max_len);
+    uint32_t *base = reinterpret_cast<uint32_t *>(smem) + (size_t)wib * 64 * AU;
+    uint32_t *A = base + (size_t)lane * 2 * AU, *R = A + AU;
+    // behind the lane arrays: where this step's records of each bin start (u64[nbins]) and how many there are (u32[nbins])
+    unsigned long long *start = reinterpret_cast<unsigned long long *>(smem + ((size_t)kWarps * 64 * AU + 1) / 2);
+    uint32_t *hist = reinterpret_cast<uint32_t *>(start + bv.nbins);
+    const uint32_t nbins = bv.nbins;
+    for (uint64_t rb = r_lo + (uint64_t)blockIdx.x * kThreads; rb < r_hi; rb += (uint64_t)gridDim.x * kThreads) { // block-uniform
+        const uint64_t r = rb + threadIdx.x;
+        const bool valid = r < r_hi;
+        const int L = valid ? read_len(rv, r) : 0;
+        stage_lane(rv, r, valid, L, A, R, WP);
+        uint64_t h0 = 0, h1 = 0;
+        int f0 = 0, f1 = 0;
+        if (valid) {
+            // record 2r = prefix k-mer (j = 0), record 2r+1 = suffix k-mer (j = L-K): HashTable.cpp:430-431
+            h0 = canon_kmer_hash(A, R, L, 0, K, &f0);
+            h1 = canon_kmer_hash(A, R, L, L - K, K, &f1);
+            if (tv.filter) {
+                uint32_t bit = (uint32_t)(h0 >> 13) & tv.filter_mask;
+                atomicOr(tv.filter + (bit >> 5), 1u << (bit & 31));
+                bit = (uint32_t)(h1 >> 13) & tv.filter_mask;
+                atomicOr(tv.filter + (bit >> 5), 1u << (bit & 31));
+            }
+        }
+        if (nbins == 1) { // no sorting: record i of the table at recs[i] (32 contiguous bytes per lane)
+            if (valid) {
+                bv.recs[2 * r] = make_ulonglong2(h0, make_slot(h0, f0, (uint32_t)(2 * r)));
+                bv.recs[2 * r + 1] = make_ulonglong2(h1, make_slot(h1, f1, (uint32_t)(2 * r + 1)));
+            }
+            continue;
+        }
+        for (uint32_t t = threadIdx.x; t < nbins; t += kThreads) hist[t] = 0;
+        __syncthreads();
+        // bucket = mulhi(h, nbuckets) and bin = mulhi(h, nbins) are both monotone in h: a bin is a range of buckets
+        const uint32_t b0 = (uint32_t)__umul64hi(h0, (uint64_t)nbins), b1 = (uint32_t)__umul64hi(h1, (uint64_t)nbins);
+        uint32_t k0 = 0, k1 = 0;
+        if (valid) { k0 = atomicAdd(&hist[b0], 1u); k1 = atomicAdd(&hist[b1], 1u); }
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < nbins; t += kThreads) {
+            const uint32_t c = hist[t];
+            start[t] = c ? atomicAdd(bv.count + t, (unsigned long long)c) : 0ULL;
+        }
+        __syncthreads();
+        if (valid) {
+            const unsigned long long p0 = start[b0] + k0, p1 = start[b1] + k1;
+            if (p0 < bv.cap) bv.recs[(uint64_t)b0 * bv.cap + p0] = make_ulonglong2(h0, make_slot(h0, f0, (uint32_t)(2 * r)));
+            else atomicExch(bv.overflow, 1u);
+            if (p1 < bv.cap) bv.recs[(uint64_t)b1 * bv.cap + p1] = make_ulonglong2(h1, make_slot(h1, f1, (uint32_t)(2 * r + 1)));
+            else atomicExch(bv.overflow, 1u);
+        }
+        // (the next step's writes to hist / start are separated from this step's reads by its first two barriers)
+    }
+}
+
+// k_table_fill: one lane per record -- 32 independent bucket loads + CAS per warp instead of the eight a warp of the direct
+// kernel has in flight between its hashing steps.  (nbins == 1: the records lie in read order, record i at recs[i].)
+__global__ void __launch_bounds__(kThreads) k_table_fill(TableView tv, BinView bv, const uint32_t *skip_bits, int set_filter,
+                                                         unsigned long long *work, uint32_t chunks_per_bin, uint32_t fill_chunk,
+                                                         unsigned long long n_unbinned)
+{
+    const int lane = threadIdx.x & 31;
+    if (*reinterpret_cast<volatile unsigned int *>(bv.overflow)) return; // incomplete bins: the gated direct kernel builds the table
+    const unsigned long long items = (unsigned long long)bv.nbins * chunks_per_bin;
+    unsigned long long *slots = reinterpret_cast<unsigned long long *>(tv.slots);
+    for (;;) {
+        unsigned long long it = 0;
+        if (lane == 0) it = atomicAdd(work, 1ULL);
+        it = __shfl_sync(FULL, it, 0);
+        if (it >= items) break;
+        const uint32_t b = (uint32_t)(it / chunks_per_bin), c = (uint32_t)(it % chunks_per_bin);
+        const unsigned long long cnt = bv.nbins == 1 ? n_unbinned : __ldg(bv.count + b); // (final: k_table_bin has finished)
+        const unsigned long long lo = (unsigned long long)c * fill_chunk;
+        if (lo >= cnt) continue;
+        const unsigned long long hi = cnt < lo + fill_chunk ? cnt : lo + fill_chunk;
+        const ulonglong2 *recs = bv.recs + (uint64_t)b * bv.cap;
+        for (unsigned long long i = lo + lane; i < hi; i += 32) {
+            const ulonglong2 rec = __ldcs(recs + i);
+            const uint64_t h = rec.x, val = rec.y;
+            if (val == kEmptySlot) continue; // (unbinned layout: no record -- a read the binning pass did not see)
+            if (skip_bits && is_contained(skip_bits, (uint32_t)val >> 1)) continue;
+            if (set_filter && tv.filter) {
+                const uint32_t bit = (uint32_t)(h >> 13) & tv.filter_mask;
+                atomicOr(tv.filter + (bit >> 5), 1u << (bit & 31));
+            }
+            uint64_t bk = bucket_of(h, tv.nbuckets);
+            for (uint64_t walked = 0;;) {
+                unsigned long long *s = slots + 4 * bk;
+                const ulonglong2 x = __ldcg(reinterpret_cast<const ulonglong2 *>(s)), y = __ldcg(reinterpret_cast<const ulonglong2 *>(s + 2));
+                const int q = x.x == kEmptySlot ? 0 : x.y == kEmptySlot ? 1 : y.x == kEmptySlot ? 2 : y.y == kEmptySlot ? 3 : -1;
+                if (q >= 0) {
+                    if (atomicCAS(s + q, (unsigned long long)kEmptySlot, (unsigned long long)val) == kEmptySlot) break;
+                    continue; // somebody else took that slot: look at the bucket again
+                }
+                if (++walked == tv.nbuckets) { atomicExch(tv.full, 1u); break; } // table full: reported, not spun on
+                bk = (bk + 1 == tv.nbuckets) ? 0 : bk + 1;
+            }
+        }
     }
 }
 
@@ -1742,7 +1861,7 @@ static cudaError_t persistent_grid(Kern kern, size_t smem, int num_sms, int *gri
 constexpr size_t kLaneSmemPerWarp = 12 * 1024; // lane-per-read kernels are used while 32 private array pairs fit in this
 
 cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, const uint32_t *skip_bits,
-                                int num_sms, cudaStream_t s, uint64_t r_lo, uint64_t r_hi)
+                                int num_sms, cudaStream_t s, uint64_t r_lo, uint64_t r_hi, const unsigned int *gate)
 {
     if (r_hi > r.n) r_hi = r.n; // (default: all reads)
     if (r_lo >= r_hi) return cudaSuccess;
@@ -1756,7 +1875,7 @@ cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, c
             if (e != cudaSuccess) return e;
             const uint64_t need = (nr + kWarps * 32 - 1) / (kWarps * 32);
             if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
-            k_table_insert_lanes<<<grid, kThreads, smem, s>>>(r, t, K, skip_bits, r_lo, r_hi);
+            k_table_insert_lanes<<<grid, kThreads, smem, s>>>(r, t, K, skip_bits, r_lo, r_hi, gate);
             DISCO_COUNT_LAUNCH();
             return cudaGetLastError();
         }
@@ -1770,7 +1889,7 @@ cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, c
     if (e != cudaSuccess) return e;
     const uint64_t need = (nr + warps - 1) / warps;
     if ((uint64_t)grid > need) grid = (int)(need ? need : 1);
-    k_table_insert<<<grid, warps * 32, smem, s>>>(r, t, K, skip_bits, r_lo, r_hi);
+    k_table_insert<<<grid, warps * 32, smem, s>>>(r, t, K, skip_bits, r_lo, r_hi, gate);
     DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }
@@ -1851,6 +1970,41 @@ static cudaError_t launch_warps(Kern kern, const SearchParams &p, size_t per_war
     cudaError_t e = persistent_grid(kern, per_warp_bytes * warps, num_sms, &grid, warps * 32);
     if (e != cudaSuccess) return e;
     kern<<<grid, warps * 32, per_warp_bytes * warps, s>>>(p);
+    DISCO_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+bool table_bin_supported(int max_len)
+{
+    return (size_t)64 * lane_array_u32(max_len) * sizeof(uint32_t) <= kLaneSmemPerWarp;
+}
+
+cudaError_t launch_table_bin(const ReadsView &r, const TableView &t, int K, const BinView &b, int num_sms, cudaStream_t s,
+                             uint64_t r_lo, uint64_t r_hi)
+{
+    if (r_hi > r.n) r_hi = r.n;
+    if (r_lo >= r_hi) return cudaSuccess;
+    const size_t lanes = ((size_t)kWarps * 64 * lane_array_u32(r.max_len) * sizeof(uint32_t) + 7) / 8 * 8;
+    const size_t smem = lanes + (size_t)b.nbins * (sizeof(unsigned long long) + sizeof(uint32_t)) + 8;
+    int grid = 0;
+    cudaError_t e = persistent_grid(k_table_bin, smem, num_sms, &grid);
+    if (e != cudaSuccess) return e;
+    const uint64_t need = (r_hi - r_lo + kThreads - 1) / kThreads;
+    if ((uint64_t)grid > need) grid = (int)need;
+    k_table_bin<<<grid, kThreads, smem, s>>>(r, t, K, b, r_lo, r_hi);
+    DISCO_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_table_fill(const TableView &t, const BinView &b, const uint32_t *skip_bits, int set_filter,
+                              unsigned long long *work_counter, uint64_t n_unbinned, int num_sms, cudaStream_t s)
+{
+    int per_sm = 8;
+    uint32_t chunk = 256;
+    if (const char *e = getenv("DISCO_FILL_BLOCKS")) per_sm = std::max(1, std::min(8, atoi(e)));
+    if (const char *e = getenv("DISCO_FILL_CHUNK")) chunk = (uint32_t)std::max(32, std::min(65536, atoi(e)));
+    const uint32_t chunks_per_bin = (uint32_t)((b.cap + chunk - 1) / chunk);
+    k_table_fill<<<num_sms * per_sm, kThreads, 0, s>>>(t, b, skip_bits, set_filter, work_counter, chunks_per_bin, chunk, n_unbinned);
     DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }

@@ -51,6 +51,16 @@ struct TableView {
     uint32_t world, rank;
 };
 
+// Binned table build: the records (fingerprint, slot value) sorted by bucket range into `nbins` bins before they are
+// inserted, so that the slice of the table a bin maps to is filled while it is L2 resident (k_table_bin / k_table_fill)
+struct BinView {
+    ulonglong2 *recs;             // nbins * cap records
+    unsigned long long *count;    // records per bin (keeps counting past cap: then *overflow is set)
+    uint64_t cap;                 // records a bin holds
+    uint32_t nbins;
+    unsigned int *overflow;       // some bin was too small (skewed k-mers): the direct insert kernel takes over
+};
+
 struct SearchParams {
     ReadsView reads;
     TableView table;
@@ -104,9 +114,17 @@ struct ReduceParams {
     unsigned long long *edges_cursor;
 };
 
-// (r_lo, r_hi: the reads to insert -- the chunked upload of api.cu inserts each chunk as it arrives; default: all)
+// (r_lo, r_hi: the reads to insert -- the chunked upload of api.cu inserts each chunk as it arrives; default: all.
+//  gate: the kernel only runs when *gate != 0 -- the fallback behind a binned build whose bins overflowed)
 cudaError_t launch_table_insert(const ReadsView &r, const TableView &t, int K, const uint32_t *skip_bits,
-                                int num_sms, cudaStream_t s, uint64_t r_lo = 0, uint64_t r_hi = ~0ULL);
+                                int num_sms, cudaStream_t s, uint64_t r_lo = 0, uint64_t r_hi = ~0ULL, const unsigned int *gate = nullptr);
+// binned build: hash + bin the reads [r_lo, r_hi) (sets the filter bits), then fill the table bin by bin (skip_bits: leave
+// out the records of contained reads; set_filter: the filter was cleared and is rebuilt from the records that are kept)
+bool table_bin_supported(int max_len);
+cudaError_t launch_table_bin(const ReadsView &r, const TableView &t, int K, const BinView &b, int num_sms, cudaStream_t s,
+                             uint64_t r_lo = 0, uint64_t r_hi = ~0ULL);
+cudaError_t launch_table_fill(const TableView &t, const BinView &b, const uint32_t *skip_bits, int set_filter,
+                              unsigned long long *work_counter, uint64_t n_unbinned, int num_sms, cudaStream_t s);
 cudaError_t launch_search_contained(const SearchParams &p, int num_sms, cudaStream_t s);
 // ev_probe_done / ev_verify_done (optional) are recorded after the probe and verify kernels of the edge pass
 cudaError_t launch_search_edges(const SearchParams &p, int num_sms, cudaStream_t s, cudaEvent_t ev_probe_done = nullptr,
