@@ -511,6 +511,7 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
             uint64_t nb = 3 * n;
+            if (const char *e = getenv("DISCO_TABLE_BUCKETS_X10")) nb = n * (uint64_t)std::max(6, std::min(80, atoi(e))) / 10; // (tuning knob)
             if (nb * 32 > free_b / 10 * ctx->tw()) nb = n + n / 2;
             nb = (nb + ctx->tw() - 1) / ctx->tw(); // key-sharded: buckets of this GPU's shard
             ctx->nbuckets = std::max<uint64_t>(1024, nb);
@@ -520,8 +521,10 @@ int disco_gpu_begin(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edge_per_
         // look-ups run at full L2 speed up to 16 MB, -5% at 32 MB, -17% at 64 MB while 1.2 GB of buckets stream by; at
         // 10 M reads 32 MB is the best trade between look-up speed and false-positive bucket reads.  Pointless once it
         // has fewer bits than records.
-        // (a replicated table over many GPUs' reads: one more doubling per 4x records keeps the false positives in check)
-        const uint64_t filter_cap = n > 160000000ULL ? (1ULL << 30) : n > 40000000ULL ? (1ULL << 29) : (1ULL << 28);
+        // (a replicated table over 80 M reads, one rank's 10 M queries -- profiles/probe_big_table.py: 2^28 bits probe 18.7 ms /
+        //  table 11.7 ms, 2^29: 18.6 / 12.7, 2^30: 20.8 / 14.6, 2^31: 24.7 / 16.0 -- the false positives a larger filter saves
+        //  cost less than its own misses: stay L2 resident)
+        const uint64_t filter_cap = n > 160000000ULL ? (1ULL << 29) : (1ULL << 28);
         ctx->filter_bits = 1ULL << 16;
         while (ctx->filter_bits < 32 * n && ctx->filter_bits < filter_cap) ctx->filter_bits <<= 1;
         if (const char *e = getenv("DISCO_FILTER_LOG2")) { // tuning knob: 0 disables the filter

@@ -15,7 +15,7 @@ torch.cuda.synchronize()
 
 
 def run(env, rebuild=False):
-    for k in ("DISCO_FILTER_LOG2",):
+    for k in ("DISCO_FILTER_LOG2", "DISCO_TABLE_BUCKETS_X10"):
         os.environ.pop(k, None)
     os.environ.update(env)
     g = gpu.GpuBuildGraph(0)
@@ -38,6 +38,5 @@ def run(env, rebuild=False):
     return out
 
 
-for lg in ("28", "29", "30", "31", "32"):
-    print("filter 2^%s bits, one table (contained candidates dropped through the bitmap):" % lg, run({"DISCO_FILTER_LOG2": lg}), flush=True)
-print("filter default, table rebuilt without the contained reads:", run({}, rebuild=True), flush=True)
+for x10 in ("30", "20", "15", "10"):
+    print("buckets per read x10 = %s, filter 2^28:" % x10, run({"DISCO_FILTER_LOG2": "28", "DISCO_TABLE_BUCKETS_X10": x10}), flush=True)
