@@ -29,7 +29,7 @@ def run(env):
 
 
 print("direct", "%.3f ms" % run({"DISCO_BINNED": "0"}), flush=True)
-for env in ({"DISCO_UNBINNED": "1"}, {"DISCO_UNBINNED": "1", "DISCO_FILL_CHUNK": "1024"}, {"DISCO_UNBINNED": "1", "DISCO_FILL_CHUNK": "4096"},
-            {"DISCO_UNBINNED": "1", "DISCO_FILL_BLOCKS": "4"}, {}, {"DISCO_FILL_CHUNK": "512"}, {"DISCO_BIN_SLICE_KB": "32768"}, {"DISCO_BIN_SLICE_KB": "65536"},
-            {"DISCO_BIN_SLICE_KB": "4096"}):
+import itertools
+for slice_kb, blocks, chunk in itertools.product(("2048", "4096", "16384"), ("4", "8"), ("256", "1024", "4096")):
+    env = {"DISCO_BIN_SLICE_KB": slice_kb, "DISCO_FILL_BLOCKS": blocks, "DISCO_FILL_CHUNK": chunk}
     print(env, "%.3f ms" % run(env), flush=True)
