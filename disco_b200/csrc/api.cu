@@ -69,6 +69,8 @@ struct disco_ctx {
     uint32_t *d_bits = nullptr;
     disco_crow *d_crows = nullptr;
     uint64_t crows_cap = 0;
+    disco_crow *d_crows_part = nullptr; // disco_gpu_get_contained_range: the rows of one read range, compacted
+    uint64_t crows_part_cap = 0;
     uint64_t n_contained = 0;
     uint64_t run_n = 0; // reads the run buffers are sized for
     // adjacency
@@ -171,7 +173,7 @@ void free_run_buffers(disco_ctx *c)
     c->d_slots = nullptr; c->d_rows = nullptr;
     c->own_slots = c->own_rows = true;
     c->peer_table.ready = c->peer_rows.ready = false; // whatever the peers mapped is gone
-    dfree(c->d_filter); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows);
+    dfree(c->d_filter); dfree(c->d_best); dfree(c->d_bits); dfree(c->d_crows); dfree(c->d_crows_part); c->crows_part_cap = 0;
     dfree(c->d_bins); dfree(c->d_bin_count); c->nbins = 0; c->bin_cap = 0; c->bins_valid = false;
     dfree(c->d_rowinfo); dfree(c->d_edges); dfree(c->d_cands); dfree(c->d_batchinfo); dfree(c->d_cedges); dfree(c->d_inner);
     c->n_cedges = c->n_inner = 0;
@@ -1216,6 +1218,36 @@ int disco_gpu_get_contained(disco_ctx *ctx, disco_crow *rows, uint64_t capacity,
         CK(cudaStreamSynchronize(ctx->stream));
     }
     if (n_written) *n_written = n;
+    return DISCO_OK;
+}
+
+// Only the rows whose contained read lies in [read_lo, read_hi): every context of a multi-GPU run holds all rows; each
+// rank hands out (writes) those of its own read range, as it does with the edges.  Order not defined.
+int disco_gpu_get_contained_range(disco_ctx *ctx, uint64_t read_lo, uint64_t read_hi, disco_crow *rows, uint64_t capacity, uint64_t *n_written)
+{
+    if (!ctx || !ctx->have_contained) return fail(ctx, DISCO_E_ARG, "containment pass not finished");
+    if (read_lo > read_hi) return fail(ctx, DISCO_E_ARG, "bad read range");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t n = ctx->n_contained;
+    unsigned long long k = 0;
+    if (n) {
+        if (ctx->crows_part_cap < n) {
+            dfree(ctx->d_crows_part);
+            ctx->crows_part_cap = 0;
+            CK(cudaMalloc(&ctx->d_crows_part, n * sizeof(disco_crow)));
+            ctx->crows_part_cap = n;
+        }
+        CK(cudaMemsetAsync(ctx->d_cursors + CUR_CROWS, 0, sizeof(unsigned long long), ctx->stream));
+        CK(launch_crows_in_range(ctx->d_crows, n, read_lo, read_hi, ctx->d_crows_part, ctx->d_cursors + CUR_CROWS, ctx->stream));
+        CK(cudaMemcpyAsync(&k, ctx->d_cursors + CUR_CROWS, sizeof k, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (k > capacity) return fail(ctx, DISCO_E_ARG, "capacity %llu < %llu rows", (unsigned long long)capacity, k);
+        if (k) {
+            CK(cudaMemcpyAsync(rows, ctx->d_crows_part, k * sizeof(disco_crow), cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    if (n_written) *n_written = k;
     return DISCO_OK;
 }
 

@@ -1566,6 +1566,18 @@ __global__ void k_contained_rows(const unsigned long long *best, ReadsView rv, i
     }
 }
 
+// the contained rows whose read lies in [lo, hi): a rank of a multi-GPU run hands out the rows of its own range only
+__global__ void k_crows_in_range(const disco_crow *in, uint64_t n, uint32_t lo, uint32_t hi, disco_crow *out, unsigned long long *cursor)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    disco_crow r{};
+    if (i < n) r = in[i];
+    const bool c = i < n && r.contained >= lo && r.contained < hi;
+    const unsigned m = __ballot_sync(FULL, c);
+    const unsigned long long base = block_reserve(m, cursor);
+    if (c) out[base + __popc(m & ((1u << (threadIdx.x & 31)) - 1))] = r;
+}
+
 // packed reads arrive with the caller's row pitch; the kernels want power-of-two rows (one DRAM line per candidate)
 __global__ void k_restride(const uint64_t *src, int src_stride, int src_words, uint64_t *dst, int dst_stride, uint64_t n)
 {
@@ -2190,6 +2202,15 @@ cudaError_t launch_contained_rows(const unsigned long long *best, const ReadsVie
     if (r.n == 0) return cudaSuccess;
     const uint64_t blocks = (r.n + 255) / 256;
     k_contained_rows<<<(unsigned)blocks, 256, 0, s>>>(best, r, K, reinterpret_cast<disco_crow *>(rows_out), cursor);
+    DISCO_COUNT_LAUNCH();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_crows_in_range(const void *in, uint64_t n, uint64_t lo, uint64_t hi, void *out, unsigned long long *cursor, cudaStream_t s)
+{
+    if (n == 0) return cudaSuccess;
+    k_crows_in_range<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(reinterpret_cast<const disco_crow *>(in), n, (uint32_t)lo, (uint32_t)std::min<uint64_t>(hi, 0xFFFFFFFFULL),
+                                                                reinterpret_cast<disco_crow *>(out), cursor);
     DISCO_COUNT_LAUNCH();
     return cudaGetLastError();
 }

@@ -134,6 +134,8 @@ cudaError_t launch_contained_finish(const unsigned long long *best, uint64_t n, 
 // rows for contained reads: keys -> (contained, container, orient, start), compacted in read order
 cudaError_t launch_contained_rows(const unsigned long long *best, const ReadsView &r, int K, void *rows_out,
                                   unsigned long long *cursor, cudaStream_t s);
+// out = the rows of `in` whose contained read lies in [lo, hi) (order not kept); *cursor (zeroed by the caller) = how many
+cudaError_t launch_crows_in_range(const void *in, uint64_t n, uint64_t lo, uint64_t hi, void *out, unsigned long long *cursor, cudaStream_t s);
 cudaError_t launch_reduce_mark(const ReduceParams &p, int num_sms, cudaStream_t s);
 cudaError_t launch_reduce_emit(const ReduceParams &p, int num_sms, cudaStream_t s);
 cudaError_t launch_rebase_rowinfo(uint64_t *rowinfo, uint64_t u_lo, uint64_t u_hi, uint64_t base, cudaStream_t s);

@@ -24,7 +24,7 @@ EXPORTS = [
     "disco_gpu_phase_reduce_emit", "disco_gpu_set_shard", "disco_gpu_export_mem", "disco_gpu_import_peers",
     "disco_gpu_import_peer_ptrs", "disco_gpu_dev_table", "disco_gpu_table_words", "disco_gpu_adopt_buffer",
     "disco_gpu_build_graph_multi", "disco_gpu_device_count", "disco_gpu_set_partition", "disco_gpu_compact_keys", "disco_gpu_apply_keys", "disco_gpu_simplify", "disco_gpu_get_simplified", "disco_gpu_simplify_stats", "disco_gpu_set_edge_sink",
-    "disco_gpu_use_reads_device", "disco_gpu_load_reads_async", "disco_gpu_sort_edges",
+    "disco_gpu_use_reads_device", "disco_gpu_load_reads_async", "disco_gpu_sort_edges", "disco_gpu_get_contained_range",
 ]
 MAX_SHARDS, IPC_HANDLE_BYTES, MEM_TABLE, MEM_ROWS = 8, 64, 0, 1
 
@@ -70,6 +70,7 @@ def lib():
         L.disco_gpu_build_graph.argtypes = [vp, u32, u32]
         L.disco_gpu_counts.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
         L.disco_gpu_get_contained.argtypes = [vp, vp, u64, C.POINTER(u64)]
+        L.disco_gpu_get_contained_range.argtypes = [vp, u64, u64, vp, u64, C.POINTER(u64)]
         L.disco_gpu_get_edges.argtypes = [vp, vp, u64, C.POINTER(u64)]
         L.disco_gpu_get_row.argtypes = [vp, u64, vp, u64, C.POINTER(u64)]
         L.disco_gpu_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -302,6 +303,12 @@ class GpuBuildGraph:
     def contained_into(self, out: np.ndarray) -> np.ndarray:
         w = C.c_uint64()
         self._ck(self._L.disco_gpu_get_contained(self._h, out.ctypes.data, len(out), C.byref(w)), "get_contained")
+        return out[:w.value]
+
+    def contained_range_into(self, out: np.ndarray, read_lo: int, read_hi: int) -> np.ndarray:
+        """the rows of the contained reads in [read_lo, read_hi) only (a rank's share of a multi-GPU run)"""
+        w = C.c_uint64()
+        self._ck(self._L.disco_gpu_get_contained_range(self._h, read_lo, read_hi, out.ctypes.data, len(out), C.byref(w)), "get_contained_range")
         return out[:w.value]
 
     def edges(self, out: np.ndarray = None) -> np.ndarray:

@@ -124,6 +124,9 @@ int disco_gpu_build_graph(disco_ctx *ctx, uint32_t min_overlap, uint32_t max_edg
 int disco_gpu_counts(disco_ctx *ctx, uint64_t *n_contained, uint64_t *n_edges);
 /* rows in device order; the host library's sort helper (disco_host.h) restores the reference's -t 1 emission order */
 int disco_gpu_get_contained(disco_ctx *ctx, disco_crow *rows, uint64_t capacity, uint64_t *n_written);
+/* only the rows of the contained reads in [read_lo, read_hi): what one rank of a multi-GPU run writes (every context holds
+ * all rows; BuildGraphMPI's ranks each write their own files, BuildGraphMPI/src/OverlapGraph.cpp:127, :370, :518) */
+int disco_gpu_get_contained_range(disco_ctx *ctx, uint64_t read_lo, uint64_t read_hi, disco_crow *rows, uint64_t capacity, uint64_t *n_written);
 /* edges in device emission order (callers sort if they need a canonical order) */
 int disco_gpu_get_edges(disco_ctx *ctx, disco_edge *edges, uint64_t capacity, uint64_t *n_written);
 /* Sorts the reduced edges by (src, dst) on the device: disco_gpu_get_edges then returns them in the order the parGraph

@@ -101,3 +101,23 @@ def test_device_edge_sort(n):
     if n > 100:
         assert len(got) > n // 2 and not np.array_equal(raw, want)
     g.close()
+
+
+def test_contained_rows_by_range():
+    """disco_gpu_get_contained_range: the ranges of a partition hand out every contained row exactly once"""
+    rs = synth.dup_contained(60_000, read_len=150, coverage=40.0, min_len=100, seed=6)
+    packed, lens = host.pack_codes(rs.codes, rs.off)
+    g = gpu.GpuBuildGraph(0)
+    g.load_reads(packed, lens)
+    g.build_graph(35, 4)
+    allrows = np.sort(g.contained(), order=["contained"])
+    assert len(allrows) > 1000
+    buf = np.zeros(len(allrows), dtype=gpu.CROW_DTYPE)
+    for bounds in ([0, rs.n], [0, 1, 4096, 4097, 30_000, rs.n], [0, 0, rs.n, rs.n]):
+        parts = [g.contained_range_into(buf, a, b).copy() for a, b in zip(bounds, bounds[1:])]
+        for (a, b), p in zip(zip(bounds, bounds[1:]), parts):
+            assert ((p["contained"] >= a) & (p["contained"] < b)).all()
+        assert np.array_equal(np.sort(np.concatenate(parts), order=["contained"]), allrows)
+    with pytest.raises(gpu.DiscoError):
+        g.contained_range_into(buf[:10], 0, rs.n)        # capacity too small: reported
+    g.close()
