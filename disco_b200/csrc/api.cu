@@ -644,7 +644,7 @@ int disco_gpu_phase_table(disco_ctx *ctx, int exclude_contained)
     CK(cudaSetDevice(ctx->device));
     CK(cudaMemsetAsync(ctx->d_slots, 0xFF, ctx->nbuckets * 4 * sizeof(uint64_t), ctx->stream));
     // (rebuild from the bins: the presence filter of the first build is kept -- a superset: the k-mers only contained reads
-    //  have cost a wasted bucket read when probed, clearing and re-setting 2n bits costs more: 1.08 -> 0.6 ms per 10 M reads)
+    //  have cost a wasted bucket read when probed; clearing and re-setting 2n bits costs more -- 20 M-read table: 2.39 -> 1.52 ms)
     const bool keep_filter = exclude_contained && ctx->nbins && ctx->bins_valid;
     if (ctx->d_filter && !keep_filter) CK(cudaMemsetAsync(ctx->d_filter, 0, ctx->filter_bits / 8, ctx->stream));
     ctx->table_has_contained = !exclude_contained;
